@@ -1,0 +1,806 @@
+/*
+ * dcp_engine.cu -- the sm_100a scan engine behind include/dcpgpu.h (Part 2).
+ *
+ * Replaces, for a whole batch of (sequence, profile) pairs, what the reference does per pair
+ * in thread_run (src/server/scan_thread.c:86-135): protein_profile_setup, imm_dp_viterbi on the
+ * null and alt DPs, xmath_lrt + threshold and the traceback that feeds prod_fwrite.
+ *
+ * Kernels (all fp32 max-plus, no tensor cores):
+ *   k_rows       per (null table, sequence row): window codes + N/J/C/R and insert emissions
+ *   k_null       1-state null Viterbi per (sequence, null table)
+ *   k_score<Q>   alt Viterbi score, one warp per pair, Q consecutive core nodes per lane,
+ *                last five rows of Tin_M/Tin_I in registers, D chain resolved exactly by lazy
+ *                warp-shuffle propagation, E by redux.sync.max.f32 (CREDUX)
+ *   k_lrt        LRT filter -> hit flags / hit list
+ *   k_trace<Q>   same DP for hits only, with imm's (transition, source length) first-max
+ *                tie-break and packed 11-bit backpointers per cell
+ *   k_walk       backpointers -> (state_id, seqlen) steps
+ *
+ * Emission tables live in HBM transposed: [profile][code 0..1363][lane][QP] so that the 32 lanes
+ * of a warp read one contiguous 32*QP*4-byte line per (row, length) with LDG.128.
+ */
+#include "dcp_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+
+namespace
+{
+
+/* ----------------------------------------------------------------------------------------- */
+/* prep kernels                                                                              */
+/* ----------------------------------------------------------------------------------------- */
+__constant__ uint32_t c_frame_off[6] = {0, 0, 4, 20, 84, 340};
+
+__global__ void k_rows(const uint8_t *__restrict__ bases, const SeqMeta *__restrict__ seqs, uint32_t nseq,
+                       const float *__restrict__ null_tabs, const float *__restrict__ ins_tab,
+                       uint32_t n_null, uint64_t total_rows, RowRec *__restrict__ rows)
+{
+    uint32_t s = blockIdx.x;
+    if (s >= nseq) return;
+    SeqMeta sm = seqs[s];
+    const uint8_t *b = bases + sm.row_off;
+    for (uint32_t j = 1 + threadIdx.x; j <= sm.len; j += blockDim.x)
+    {
+        uint32_t code[5];
+        uint32_t w = 0;
+#pragma unroll
+        for (int l = 1; l <= 5; ++l)
+        {
+            /* window grows to the left: seq[j-l] becomes the most significant base */
+            if (j >= (uint32_t)l)
+            {
+                w |= (uint32_t)b[j - l] << (2 * (l - 1));
+                code[l - 1] = c_frame_off[l] + w;
+            }
+            else
+                code[l - 1] = 0; /* unused: Tin of a negative row is -inf */
+        }
+        for (uint32_t t = 0; t < n_null; ++t)
+        {
+            RowRec r;
+#pragma unroll
+            for (int l = 0; l < 5; ++l)
+            {
+                r.eN[l] = null_tabs[(size_t)t * kTab + code[l]];
+                r.eI[l] = ins_tab[code[l]];
+                r.code[l] = code[l];
+            }
+            r.pad = 0;
+            rows[(size_t)t * total_rows + sm.row_off + (j - 1)] = r;
+        }
+    }
+}
+
+/* imm_dp_viterbi on the null dp (scan_thread.c:115): V_R[j] = max_l Tin_R[j-l] + e_R(seq[j-l:j]) */
+__global__ void k_null(const SeqMeta *__restrict__ seqs, uint32_t nseq, uint32_t n_null, uint64_t total_rows,
+                       const RowRec *__restrict__ rows, const float *__restrict__ spec,
+                       float *__restrict__ null_out)
+{
+    uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= nseq * n_null) return;
+    uint32_t s = tid / n_null, t = tid % n_null;
+    SeqMeta sm = seqs[s];
+    const float RR = spec[(size_t)s * 16 + 6];
+    const RowRec *r = rows + (size_t)t * total_rows + sm.row_off;
+    /* ring of Tin_R for the last five rows; Tin_R[0] = start lprob 0 */
+    float tin[5] = {NEG_INF, NEG_INF, NEG_INF, NEG_INF, 0.0f};
+    float v = NEG_INF;
+    for (uint32_t j = 1; j <= sm.len; ++j)
+    {
+        const float4 *q = reinterpret_cast<const float4 *>(r + (j - 1));
+        float4 a = __ldg(q);
+        float e5 = __ldg(reinterpret_cast<const float *>(q + 1));
+        v = fmaxf(fmaxf(fmaxf(tin[4] + a.x, tin[3] + a.y), fmaxf(tin[2] + a.z, tin[1] + a.w)), tin[0] + e5);
+        tin[0] = tin[1], tin[1] = tin[2], tin[2] = tin[3], tin[3] = tin[4];
+        tin[4] = v + RR;
+    }
+    null_out[(size_t)s * n_null + t] = v;
+}
+
+/* ----------------------------------------------------------------------------------------- */
+/* alt Viterbi, score pass                                                                   */
+/* ----------------------------------------------------------------------------------------- */
+/*
+ * One DP row.  R = ring slot this row writes ((j-1) % 5); the slot holding row j-l is
+ * (R - l + 5) % 5, so slot R still holds row j-5 while it is read.
+ * Lanes 0,1,2 also carry the N, J, C special states (tx ring); cE/cX are their lane-specific
+ * E->X and X->X scores.  Returns E[j] and this lane's V_X[j].
+ */
+template <int Q, int R>
+__device__ __forceinline__ void score_row(float (&tm)[5][Q], float (&ti)[5][Q], float (&tx)[5],
+                                          const NodeParams<Q> &p, const float *__restrict__ emis_lane,
+                                          const RowRec *__restrict__ rec, int lane, float NB, float JB,
+                                          float EB, float cE, float cX, float &E_out, float &vx_out)
+{
+    constexpr int S1 = (R + 4) % 5, S2 = (R + 3) % 5, S3 = (R + 2) % 5, S4 = (R + 1) % 5, S5 = R;
+    RowIn in = load_row(rec);
+    float em[5][Q];
+    load_emis<Q>(em, emis_lane, in.code);
+
+    float vm[Q], vi[Q];
+#pragma unroll
+    for (int i = 0; i < Q; ++i)
+    {
+        vm[i] = fmaxf(max3(tm[S1][i] + em[0][i], tm[S2][i] + em[1][i], tm[S3][i] + em[2][i]),
+                      fmaxf(tm[S4][i] + em[3][i], tm[S5][i] + em[4][i]));
+        vi[i] = fmaxf(max3(ti[S1][i] + in.eI[0], ti[S2][i] + in.eI[1], ti[S3][i] + in.eI[2]),
+                      fmaxf(ti[S4][i] + in.eI[3], ti[S5][i] + in.eI[4]));
+    }
+    /* special state carried by this lane */
+    float vx = fmaxf(max3(tx[S1] + in.eN[0], tx[S2] + in.eN[1], tx[S3] + in.eN[2]),
+                     fmaxf(tx[S4] + in.eN[3], tx[S5] + in.eN[4]));
+
+    /* E[j]: every M_k -> E is 0 and D_k <= max V_M because MD, DD <= 0 (checked at commit) */
+    float eloc = vm[0];
+#pragma unroll
+    for (int i = 1; i < Q; ++i) eloc = fmaxf(eloc, vm[i]);
+    float E = warp_max(eloc);
+
+    /* node k0-1 lives in the previous lane */
+    float vm_prev = __shfl_up_sync(FULL, vm[Q - 1], 1);
+    float vi_prev = __shfl_up_sync(FULL, vi[Q - 1], 1);
+    if (lane == 0) vm_prev = NEG_INF, vi_prev = NEG_INF;
+
+    /* D chain: local pass with no carry-in, then exact lazy propagation across lanes */
+    float d[Q];
+    d[0] = vm_prev + p.MD[0];
+#pragma unroll
+    for (int i = 1; i < Q; ++i) d[i] = fmaxf(vm[i - 1] + p.MD[i], d[i - 1] + p.DD[i]);
+    float din;
+    for (;;)
+    {
+        float old = d[Q - 1];
+        din = __shfl_up_sync(FULL, old, 1);
+        if (lane == 0) din = NEG_INF;
+        float x = din;
+#pragma unroll
+        for (int i = 0; i < Q; ++i)
+        {
+            x = x + p.DD[i];
+            d[i] = fmaxf(d[i], x);
+            x = d[i];
+        }
+        if (!__any_sync(FULL, d[Q - 1] > old)) break;
+    }
+
+    /* B[j] = max(V_N + NB, V_J + JB, E + (EJ+JB)) */
+    float vN = __shfl_sync(FULL, vx, 0);
+    float vJ = __shfl_sync(FULL, vx, 1);
+    float B = max3(vN + NB, vJ + JB, E + EB);
+    tx[R] = fmaxf(E + cE, vx + cX);
+
+#pragma unroll
+    for (int i = 0; i < Q; ++i)
+    {
+        float pm = i == 0 ? vm_prev : vm[i - 1];
+        float pi = i == 0 ? vi_prev : vi[i - 1];
+        float pd = i == 0 ? din : d[i - 1];
+        tm[R][i] = fmaxf(fmaxf(B + p.ent[i], pm + p.MM[i]), fmaxf(pi + p.IM[i], pd + p.DM[i]));
+        ti[R][i] = fmaxf(vm[i] + p.MI[i], vi[i] + p.II[i]);
+    }
+    E_out = E;
+    vx_out = vx;
+}
+
+template <int Q>
+__device__ __forceinline__ float score_pair(const NodeParams<Q> &p, const float *__restrict__ emis_lane,
+                                            const RowRec *__restrict__ rows, uint32_t L,
+                                            const float *__restrict__ sp, int lane)
+{
+    const float NN = sp[0], CC = sp[1], JJ = sp[2], NB = sp[3], CT = sp[4], JB = sp[5];
+    const float ET = sp[9], ECC = sp[10], EB = sp[11], EJJ = sp[12];
+    const float cE = lane == 0 ? NEG_INF : (lane == 1 ? EJJ : ECC);
+    const float cX = lane == 0 ? NN : (lane == 1 ? JJ : CC);
+
+    float tm[5][Q], ti[5][Q], tx[5];
+#pragma unroll
+    for (int s = 0; s < 5; ++s)
+    {
+        tx[s] = NEG_INF;
+#pragma unroll
+        for (int i = 0; i < Q; ++i) tm[s][i] = NEG_INF, ti[s][i] = NEG_INF;
+    }
+    /* row 0: S = 0, B[0] = NB, Tin_N[0] = NN, Tin_Mk[0] = B[0] + entry_k */
+#pragma unroll
+    for (int i = 0; i < Q; ++i) tm[4][i] = NB + p.ent[i];
+    tx[4] = lane == 0 ? NN : NEG_INF;
+
+    float E = NEG_INF, vx = NEG_INF;
+    uint32_t j = 1;
+    for (; j + 4 <= L; j += 5)
+    {
+        score_row<Q, 0>(tm, ti, tx, p, emis_lane, rows + (j - 1), lane, NB, JB, EB, cE, cX, E, vx);
+        score_row<Q, 1>(tm, ti, tx, p, emis_lane, rows + j, lane, NB, JB, EB, cE, cX, E, vx);
+        score_row<Q, 2>(tm, ti, tx, p, emis_lane, rows + (j + 1), lane, NB, JB, EB, cE, cX, E, vx);
+        score_row<Q, 3>(tm, ti, tx, p, emis_lane, rows + (j + 2), lane, NB, JB, EB, cE, cX, E, vx);
+        score_row<Q, 4>(tm, ti, tx, p, emis_lane, rows + (j + 3), lane, NB, JB, EB, cE, cX, E, vx);
+    }
+    if (j <= L) score_row<Q, 0>(tm, ti, tx, p, emis_lane, rows + (j - 1), lane, NB, JB, EB, cE, cX, E, vx);
+    if (j + 1 <= L) score_row<Q, 1>(tm, ti, tx, p, emis_lane, rows + j, lane, NB, JB, EB, cE, cX, E, vx);
+    if (j + 2 <= L) score_row<Q, 2>(tm, ti, tx, p, emis_lane, rows + (j + 1), lane, NB, JB, EB, cE, cX, E, vx);
+    if (j + 3 <= L) score_row<Q, 3>(tm, ti, tx, p, emis_lane, rows + (j + 2), lane, NB, JB, EB, cE, cX, E, vx);
+    /* T[L] = max(E[L] + (EC+CT), V_C[L] + CT); V_C lives in lane 2 */
+    float vC = __shfl_sync(FULL, vx, 2);
+    return fmaxf(E + ET, vC + CT);
+}
+
+template <int Q>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 1)
+k_score(const float *__restrict__ emis, const float *__restrict__ trans, const ProfMeta *__restrict__ metas,
+        const uint32_t *__restrict__ class_profs, uint32_t n_class_profs, const SeqMeta *__restrict__ seqs,
+        uint32_t nseq, uint64_t total_rows, const RowRec *__restrict__ rows, const float *__restrict__ spec,
+        float *__restrict__ alt_out, uint32_t nprof, unsigned long long *__restrict__ counter)
+{
+    constexpr int QP = Q <= 4 ? 4 : 8;
+    const int lane = threadIdx.x & 31;
+    const uint32_t nchunks = (nseq + kSeqChunk - 1) / kSeqChunk;
+    const unsigned long long n_items = (unsigned long long)n_class_profs * nchunks;
+    for (;;)
+    {
+        unsigned long long item = 0;
+        if (lane == 0) item = atomicAdd(counter, 1ULL);
+        item = __shfl_sync(FULL, item, 0);
+        if (item >= n_items) break;
+        uint32_t pi = (uint32_t)(item / nchunks), ci = (uint32_t)(item % nchunks);
+        uint32_t prof = class_profs[pi];
+        ProfMeta pm = metas[prof];
+        NodeParams<Q> p;
+        load_params<Q>(p, trans + pm.trans_off, lane);
+        const float *emis_lane = emis + pm.emis_off + lane * QP;
+        const RowRec *rows_t = rows + (size_t)pm.null_id * total_rows;
+        uint32_t s_end = min(nseq, (ci + 1) * kSeqChunk);
+        for (uint32_t s = ci * kSeqChunk; s < s_end; ++s)
+        {
+            SeqMeta sm = seqs[s];
+            float T = score_pair<Q>(p, emis_lane, rows_t + sm.row_off, sm.len, spec + (size_t)s * 16, lane);
+            if (lane == 0) alt_out[(size_t)s * nprof + prof] = T;
+        }
+    }
+}
+
+/* xmath_lrt + threshold (scan_thread.c:121-123): hit iff finite and not (lrt < threshold) */
+__global__ void k_lrt(const float *__restrict__ alt, const float *__restrict__ null_by_tab,
+                      const ProfMeta *__restrict__ metas, uint32_t nseq, uint32_t nprof, uint32_t n_null,
+                      double thr, uint8_t *__restrict__ hit, unsigned long long *__restrict__ nhits)
+{
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t n = (size_t)nseq * nprof;
+    if (idx >= n) return;
+    uint32_t s = (uint32_t)(idx / nprof), pr = (uint32_t)(idx % nprof);
+    float nl = null_by_tab[(size_t)s * n_null + metas[pr].null_id];
+    float lrt = -2.0f * (nl - alt[idx]);
+    bool h = isfinite(lrt) && !((double)lrt < thr);
+    hit[idx] = h ? 1 : 0;
+    if (h) atomicAdd(nhits, 1ULL);
+}
+
+__global__ void k_collect(const uint8_t *__restrict__ hit, size_t n, unsigned long long *__restrict__ cursor,
+                          unsigned long long *__restrict__ list)
+{
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    if (hit[idx]) list[atomicAdd(cursor, 1ULL)] = idx;
+}
+
+
+__global__ void k_gather(const unsigned long long *__restrict__ list, size_t nhits, const float *__restrict__ alt,
+                         const float *__restrict__ null_by_tab, const ProfMeta *__restrict__ metas, uint32_t nprof,
+                         uint32_t n_null, float *__restrict__ out_alt, float *__restrict__ out_null)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nhits) return;
+    unsigned long long idx = list[i];
+    uint32_t s = (uint32_t)(idx / nprof), pr = (uint32_t)(idx % nprof);
+    out_alt[i] = alt[idx];
+    out_null[i] = null_by_tab[(size_t)s * n_null + metas[pr].null_id];
+}
+
+template <int Q>
+void launch_score(int nblocks, cudaStream_t st, const float *emis, const float *trans, const ProfMeta *metas,
+                  const uint32_t *class_profs, uint32_t n_class, const SeqMeta *seqs, uint32_t nseq,
+                  uint64_t total_rows, const RowRec *rows, const float *spec, float *alt, uint32_t nprof,
+                  unsigned long long *counter)
+{
+    k_score<Q><<<nblocks, kWarpsPerBlock * 32, 0, st>>>(emis, trans, metas, class_profs, n_class, seqs, nseq,
+                                                        total_rows, rows, spec, alt, nprof, counter);
+}
+
+} // namespace
+
+/* ----------------------------------------------------------------------------------------- */
+/* host objects                                                                              */
+/* ----------------------------------------------------------------------------------------- */
+static protein_profile *profile_clone(protein_profile const *src)
+{
+    protein_profile *p = (protein_profile *)calloc(1, sizeof *p);
+    if (!p) return nullptr;
+    *p = *src;
+    unsigned n = src->core_size;
+    p->consensus = (char *)malloc(n + 1);
+    p->match_ndists = (dcp_nuclt_dist *)malloc(n * sizeof *p->match_ndists);
+    p->match_emission = (float *)malloc((size_t)n * kTab * sizeof(float));
+    p->trans = (protein_trans *)malloc((n + 1) * sizeof *p->trans);
+    p->entry = (float *)malloc(n * sizeof(float));
+    if (!p->consensus || !p->match_ndists || !p->match_emission || !p->trans || !p->entry)
+    {
+        protein_profile_del(p);
+        return nullptr;
+    }
+    memcpy(p->consensus, src->consensus, n + 1);
+    memcpy(p->match_ndists, src->match_ndists, n * sizeof *p->match_ndists);
+    memcpy(p->match_emission, src->match_emission, (size_t)n * kTab * sizeof(float));
+    memcpy(p->trans, src->trans, (n + 1) * sizeof *p->trans);
+    memcpy(p->entry, src->entry, n * sizeof(float));
+    return p;
+}
+
+extern "C" enum rc dcpgpu_db_new(struct dcpgpu_db **out, int device)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return dcp_error(RC_EFAIL, "no CUDA device: the scan engine has no CPU fallback");
+    if (device < 0 || device >= ndev) return dcp_error(RC_EINVAL, "no such CUDA device");
+    CU_TRY(cudaSetDevice(device));
+    dcpgpu_db *db = new (std::nothrow) dcpgpu_db;
+    if (!db) return dcp_error(RC_ENOMEM, "alloc db");
+    db->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) db->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking) != cudaSuccess)
+    {
+        delete db;
+        return dcp_error(RC_EFAIL, "cudaStreamCreate failed");
+    }
+    *out = db;
+    return RC_OK;
+}
+
+extern "C" enum rc dcpgpu_db_add(struct dcpgpu_db *db, struct protein_profile const *prof)
+{
+    if (db->committed) return dcp_error(RC_EFAIL, "database already committed");
+    if (prof->core_size == 0) return dcp_error(RC_EINVAL, "profile has not been absorbed");
+    if (prof->core_size > 32 * kMaxQ)
+        return dcp_error(RC_EINVAL, "core_size > 256 is not supported by this build yet");
+    if (db->epsilon >= 0.0f && db->epsilon != prof->cfg.epsilon)
+        return dcp_error(RC_EINVAL, "all profiles of a database share one epsilon");
+    /* the score pass takes E[j] = max_k V_Mk[j]; that needs delete scores to be log-probabilities */
+    for (unsigned i = 0; i <= prof->core_size; ++i)
+        if (prof->trans[i].MD > 0.0f || prof->trans[i].DD > 0.0f)
+            return dcp_error(RC_EINVAL, "MD/DD transition scores must be <= 0");
+    protein_profile *copy = profile_clone(prof);
+    if (!copy) return dcp_error(RC_ENOMEM, "clone profile");
+    db->epsilon = prof->cfg.epsilon;
+    uint32_t id = UINT32_MAX;
+    for (size_t t = 0; t < db->null_tabs.size(); ++t)
+        if (!memcmp(db->null_tabs[t].data(), prof->null_emission, kTab * sizeof(float)))
+        {
+            id = (uint32_t)t;
+            break;
+        }
+    if (id == UINT32_MAX)
+    {
+        id = (uint32_t)db->null_tabs.size();
+        db->null_tabs.emplace_back(prof->null_emission, prof->null_emission + kTab);
+    }
+    db->profs.push_back(copy);
+    db->null_id.push_back(id);
+    return RC_OK;
+}
+
+extern "C" enum rc dcpgpu_db_commit(struct dcpgpu_db *db)
+{
+    if (db->committed) return dcp_error(RC_EFAIL, "database already committed");
+    if (db->profs.empty()) return dcp_error(RC_EINVAL, "database is empty");
+    CU_TRY(cudaSetDevice(db->device));
+    size_t nprof = db->profs.size();
+    db->metas.resize(nprof);
+    uint64_t emis_floats = 0, trans_floats = 0;
+    for (size_t i = 0; i < nprof; ++i)
+    {
+        uint32_t M = db->profs[i]->core_size;
+        uint32_t Q = (M + 31) / 32;
+        uint32_t QP = Q <= 4 ? 4 : 8;
+        ProfMeta &m = db->metas[i];
+        m.M = M, m.Q = Q, m.QP = QP, m.null_id = db->null_id[i];
+        m.emis_off = emis_floats;
+        m.trans_off = trans_floats;
+        emis_floats += (uint64_t)kTab * 32 * QP;
+        trans_floats += (uint64_t)8 * 32 * Q;
+        db->class_list[Q].push_back((uint32_t)i);
+    }
+    CU_TRY(cudaMalloc(&db->d_emis, emis_floats * sizeof(float)));
+    CU_TRY(cudaMalloc(&db->d_trans, trans_floats * sizeof(float)));
+    CU_TRY(cudaMalloc(&db->d_metas, nprof * sizeof(ProfMeta)));
+    CU_TRY(cudaMalloc(&db->d_null_tabs, db->null_tabs.size() * kTab * sizeof(float)));
+    CU_TRY(cudaMalloc(&db->d_ins_tab, kTab * sizeof(float)));
+    db->device_bytes = (emis_floats + trans_floats + (db->null_tabs.size() + 1) * kTab) * sizeof(float) +
+                       nprof * sizeof(ProfMeta);
+
+    /* transpose per profile into pinned staging, upload in large pieces */
+    const size_t stage_floats = (size_t)kTab * 32 * 8;
+    float *stage = nullptr;
+    CU_TRY(cudaMallocHost(&stage, stage_floats * sizeof(float)));
+    std::vector<float> tr;
+    for (size_t i = 0; i < nprof; ++i)
+    {
+        const ProfMeta &m = db->metas[i];
+        const protein_profile *p = db->profs[i];
+        const uint32_t ROW = 32 * m.QP;
+        for (size_t x = 0; x < (size_t)kTab * ROW; ++x) stage[x] = NEG_INF;
+        for (uint32_t k = 0; k < m.M; ++k)
+        {
+            uint32_t lane = k / m.Q, sub = k % m.Q;
+            const float *src = p->match_emission + (size_t)k * kTab;
+            for (int c = 0; c < kTab; ++c) stage[(size_t)c * ROW + lane * m.QP + sub] = src[c];
+        }
+        CU_TRY(cudaMemcpyAsync(db->d_emis + m.emis_off, stage, (size_t)kTab * ROW * sizeof(float),
+                               cudaMemcpyHostToDevice, db->stream));
+        const uint32_t NP = 32 * m.Q;
+        tr.assign((size_t)8 * NP, NEG_INF);
+        for (uint32_t k = 1; k <= m.M; ++k) /* node k, slot k-1 */
+        {
+            uint32_t n = k - 1;
+            if (k >= 2)
+            {
+                const protein_trans &t = p->trans[k - 1];
+                tr[0 * NP + n] = t.MM, tr[1 * NP + n] = t.IM, tr[2 * NP + n] = t.DM;
+                tr[3 * NP + n] = t.MD, tr[4 * NP + n] = t.DD;
+            }
+            if (k <= m.M - 1)
+            {
+                const protein_trans &t = p->trans[k];
+                tr[5 * NP + n] = t.MI, tr[6 * NP + n] = t.II;
+            }
+            tr[7 * NP + n] = p->entry[k - 1];
+        }
+        CU_TRY(cudaStreamSynchronize(db->stream)); /* stage is reused */
+        CU_TRY(cudaMemcpy(db->d_trans + m.trans_off, tr.data(), tr.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    cudaFreeHost(stage);
+    CU_TRY(cudaMemcpy(db->d_metas, db->metas.data(), nprof * sizeof(ProfMeta), cudaMemcpyHostToDevice));
+    for (size_t t = 0; t < db->null_tabs.size(); ++t)
+        CU_TRY(cudaMemcpy(db->d_null_tabs + t * kTab, db->null_tabs[t].data(), kTab * sizeof(float),
+                          cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(db->d_ins_tab, db->profs[0]->insert_emission, kTab * sizeof(float), cudaMemcpyHostToDevice));
+    for (int q = 1; q <= kMaxQ; ++q)
+        if (!db->class_list[q].empty())
+        {
+            CU_TRY(cudaMalloc(&db->d_class[q], db->class_list[q].size() * sizeof(uint32_t)));
+            CU_TRY(cudaMemcpy(db->d_class[q], db->class_list[q].data(), db->class_list[q].size() * sizeof(uint32_t),
+                              cudaMemcpyHostToDevice));
+        }
+    db->committed = true;
+    return RC_OK;
+}
+
+extern "C" unsigned dcpgpu_db_nprofiles(struct dcpgpu_db const *db) { return (unsigned)db->profs.size(); }
+extern "C" uint64_t dcpgpu_db_device_bytes(struct dcpgpu_db const *db) { return db->device_bytes; }
+
+extern "C" void dcpgpu_db_del(struct dcpgpu_db *db)
+{
+    if (!db) return;
+    cudaSetDevice(db->device);
+    for (auto *p : db->profs) protein_profile_del(p);
+    cudaFree(db->d_emis), cudaFree(db->d_trans), cudaFree(db->d_metas);
+    cudaFree(db->d_null_tabs), cudaFree(db->d_ins_tab);
+    for (int q = 0; q <= kMaxQ; ++q) cudaFree(db->d_class[q]);
+    if (db->stream) cudaStreamDestroy(db->stream);
+    delete db;
+}
+
+const protein_profile *dcp_db_profile(struct dcpgpu_db const *db, unsigned i) { return db->profs[i]; }
+
+extern "C" enum rc dcpgpu_seqs_new(struct dcpgpu_seqs **out, struct dcpgpu_db *db, unsigned nseqs,
+                                   char const *const *seqs, unsigned const *lens)
+{
+    if (!db->committed) return dcp_error(RC_EFAIL, "commit the database first");
+    if (nseqs == 0) return dcp_error(RC_EINVAL, "no sequences");
+    CU_TRY(cudaSetDevice(db->device));
+    dcpgpu_seqs *sq = new (std::nothrow) dcpgpu_seqs;
+    if (!sq) return dcp_error(RC_ENOMEM, "alloc seqs");
+    sq->db = db;
+    sq->nseq = nseqs;
+    sq->metas.resize(nseqs);
+    uint64_t total = 0;
+    for (unsigned i = 0; i < nseqs; ++i)
+    {
+        if (lens[i] == 0)
+        {
+            delete sq;
+            return dcp_error(RC_EINVAL, "sequence cannot be empty"); /* protein_profile.c:158 */
+        }
+        sq->metas[i].len = lens[i], sq->metas[i].pad = 0, sq->metas[i].row_off = total;
+        total += lens[i];
+    }
+    sq->total = total;
+    uint8_t *h = nullptr;
+    if (cudaMallocHost(&h, total) != cudaSuccess)
+    {
+        delete sq;
+        return dcp_error(RC_ENOMEM, "pinned staging for sequences");
+    }
+    static const int8_t lut_init = 0;
+    (void)lut_init;
+    int8_t lut[256];
+    memset(lut, -1, sizeof lut);
+    lut['A'] = 0, lut['C'] = 1, lut['G'] = 2, lut['T'] = 3;
+    bool bad = false;
+    for (unsigned i = 0; i < nseqs && !bad; ++i)
+    {
+        uint8_t *dst = h + sq->metas[i].row_off;
+        const unsigned char *src = (const unsigned char *)seqs[i];
+        for (unsigned j = 0; j < lens[i]; ++j)
+        {
+            int8_t c = lut[src[j]];
+            if (c < 0)
+            {
+                bad = true;
+                break;
+            }
+            dst[j] = (uint8_t)c;
+        }
+    }
+    if (bad)
+    {
+        cudaFreeHost(h);
+        delete sq;
+        return dcp_error(RC_EINVAL, "sequence symbol outside ACGT");
+    }
+    cudaError_t e = cudaMalloc(&sq->d_bases, total);
+    if (e == cudaSuccess) e = cudaMalloc(&sq->d_metas, nseqs * sizeof(SeqMeta));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sq->d_bases, h, total, cudaMemcpyHostToDevice, db->stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(sq->d_metas, sq->metas.data(), nseqs * sizeof(SeqMeta), cudaMemcpyHostToDevice, db->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(db->stream);
+    cudaFreeHost(h);
+    if (e != cudaSuccess)
+    {
+        dcp_set_error(cudaGetErrorString(e));
+        dcpgpu_seqs_del(sq);
+        return RC_EFAIL;
+    }
+    sq->h2d_bytes = total + nseqs * sizeof(SeqMeta);
+    *out = sq;
+    return RC_OK;
+}
+
+extern "C" void dcpgpu_seqs_del(struct dcpgpu_seqs *sq)
+{
+    if (!sq) return;
+    cudaSetDevice(sq->db->device);
+    cudaFree(sq->d_bases), cudaFree(sq->d_metas);
+    delete sq;
+}
+
+namespace
+{
+struct DevBuf
+{
+    void *p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+    template <class T>
+    T *as() { return (T *)p; }
+};
+} // namespace
+
+extern "C" enum rc dcpgpu_scan_resident(struct dcpgpu_db *db, struct dcpgpu_seqs *sq,
+                                        struct dcpgpu_params const *prm, struct dcpgpu_result **out)
+{
+    if (!db->committed || sq->db != db) return dcp_error(RC_EINVAL, "sequences were staged for another database");
+    CU_TRY(cudaSetDevice(db->device));
+    cudaStream_t st = db->stream;
+    const uint32_t nseq = sq->nseq, nprof = (uint32_t)db->profs.size(), n_null = (uint32_t)db->null_tabs.size();
+    const size_t npairs = (size_t)nseq * nprof;
+
+    dcpgpu_result *res = new (std::nothrow) dcpgpu_result;
+    if (!res) return dcp_error(RC_ENOMEM, "alloc result");
+    res->db = db, res->nseq = nseq, res->nprof = nprof, res->n_null = n_null;
+    struct Guard
+    {
+        dcpgpu_result *r;
+        ~Guard() { if (r) dcpgpu_result_del(r); }
+    } guard{res};
+
+    /* protein_profile_setup per sequence length (host libm, exactly once per distinct L) */
+    std::vector<float> spec((size_t)nseq * 16, 0.0f);
+    {
+        std::vector<std::pair<uint32_t, uint32_t>> byL(nseq);
+        for (uint32_t s = 0; s < nseq; ++s) byL[s] = {sq->metas[s].len, s};
+        std::sort(byL.begin(), byL.end());
+        float x[13];
+        uint32_t last = 0;
+        for (auto &e : byL)
+        {
+            if (e.first != last) dcp_specials(e.first, prm->multi_hits, prm->hmmer3_compat, x), last = e.first;
+            memcpy(&spec[(size_t)e.second * 16], x, sizeof x);
+        }
+    }
+    DevBuf b_spec, b_rows, b_counter, b_nhits;
+    CU_TRY(cudaMalloc(&b_spec.p, spec.size() * sizeof(float)));
+    CU_TRY(cudaMalloc(&b_rows.p, (size_t)n_null * sq->total * sizeof(RowRec)));
+    CU_TRY(cudaMalloc(&b_counter.p, (kMaxQ + 1) * sizeof(unsigned long long)));
+    CU_TRY(cudaMalloc(&b_nhits.p, 2 * sizeof(unsigned long long)));
+    CU_TRY(cudaMalloc(&res->d_alt, npairs * sizeof(float)));
+    CU_TRY(cudaMalloc(&res->d_null, (size_t)nseq * n_null * sizeof(float)));
+    CU_TRY(cudaMalloc(&res->d_hit, npairs));
+
+    cudaEvent_t ev[5];
+    for (auto &e : ev) CU_TRY(cudaEventCreate(&e));
+    uint64_t launches = 0;
+
+    CU_TRY(cudaEventRecord(ev[0], st));
+    CU_TRY(cudaMemcpyAsync(b_spec.p, spec.data(), spec.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemsetAsync(b_counter.p, 0, (kMaxQ + 1) * sizeof(unsigned long long), st));
+    CU_TRY(cudaMemsetAsync(b_nhits.p, 0, 2 * sizeof(unsigned long long), st));
+    k_rows<<<nseq, 128, 0, st>>>(sq->d_bases, sq->d_metas, nseq, db->d_null_tabs, db->d_ins_tab, n_null, sq->total,
+                                 b_rows.as<RowRec>());
+    k_null<<<(nseq * n_null + 127) / 128, 128, 0, st>>>(sq->d_metas, nseq, n_null, sq->total, b_rows.as<RowRec>(),
+                                                        b_spec.as<float>(), res->d_null);
+    launches += 2;
+    CU_TRY(cudaEventRecord(ev[1], st));
+
+    const int nblocks = db->sm_count; /* persistent: one 8-warp block per SM (255 regs/thread) */
+    uint64_t cells = 0;
+    for (int q = 1; q <= kMaxQ; ++q)
+    {
+        if (db->class_list[q].empty()) continue;
+        uint32_t n_class = (uint32_t)db->class_list[q].size();
+        unsigned long long *ctr = b_counter.as<unsigned long long>() + q;
+#define LAUNCH(QQ)                                                                                         \
+    case QQ:                                                                                               \
+        launch_score<QQ>(nblocks, st, db->d_emis, db->d_trans, db->d_metas, db->d_class[q], n_class,       \
+                         sq->d_metas, nseq, sq->total, b_rows.as<RowRec>(), b_spec.as<float>(), res->d_alt, \
+                         nprof, ctr);                                                                      \
+        break;
+        switch (q)
+        {
+            LAUNCH(1) LAUNCH(2) LAUNCH(3) LAUNCH(4) LAUNCH(5) LAUNCH(6) LAUNCH(7) LAUNCH(8)
+        }
+#undef LAUNCH
+        launches++;
+        for (uint32_t id : db->class_list[q]) cells += (uint64_t)db->metas[id].M * sq->total;
+    }
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaEventRecord(ev[2], st));
+
+    k_lrt<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(res->d_alt, res->d_null, db->d_metas, nseq, nprof, n_null,
+                                                            prm->lrt_threshold, res->d_hit,
+                                                            b_nhits.as<unsigned long long>());
+    launches++;
+    unsigned long long nhits = 0;
+    CU_TRY(cudaMemcpyAsync(&nhits, b_nhits.p, sizeof nhits, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    uint64_t d2h = sizeof nhits;
+
+    if (nhits)
+    {
+        DevBuf b_list;
+        CU_TRY(cudaMalloc(&b_list.p, nhits * sizeof(unsigned long long)));
+        k_collect<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(res->d_hit, npairs,
+                                                                    b_nhits.as<unsigned long long>() + 1,
+                                                                    b_list.as<unsigned long long>());
+        launches++;
+        std::vector<unsigned long long> list(nhits);
+        CU_TRY(cudaMemcpyAsync(list.data(), b_list.p, nhits * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        d2h += nhits * sizeof(unsigned long long);
+        std::sort(list.begin(), list.end()); /* (sequence, profile) order, independent of scheduling */
+        DevBuf b_ga, b_gn;
+        CU_TRY(cudaMalloc(&b_ga.p, nhits * sizeof(float)));
+        CU_TRY(cudaMalloc(&b_gn.p, nhits * sizeof(float)));
+        CU_TRY(cudaMemcpyAsync(b_list.p, list.data(), nhits * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
+        k_gather<<<(unsigned)((nhits + 255) / 256), 256, 0, st>>>(b_list.as<unsigned long long>(), nhits, res->d_alt,
+                                                                  res->d_null, db->d_metas, nprof, n_null,
+                                                                  b_ga.as<float>(), b_gn.as<float>());
+        launches++;
+        res->hit_alt.resize(nhits), res->hit_null.resize(nhits);
+        CU_TRY(cudaMemcpyAsync(res->hit_alt.data(), b_ga.p, nhits * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(res->hit_null.data(), b_gn.p, nhits * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        d2h += nhits * 2 * sizeof(float);
+        res->hits.resize(nhits);
+        for (size_t i = 0; i < nhits; ++i)
+        {
+            res->hits[i].seq = (uint32_t)(list[i] / nprof);
+            res->hits[i].prof = (uint32_t)(list[i] % nprof);
+            res->hits[i].step_off = 0, res->hits[i].nsteps = 0;
+        }
+    }
+    CU_TRY(cudaEventRecord(ev[3], st));
+    if (nhits && prm->want_paths)
+    {
+        enum rc rc = dcp_trace_hits(db, sq, res, b_rows.as<RowRec>(), b_spec.as<float>(), &launches);
+        if (rc) return rc;
+        res->have_paths = true;
+    }
+    CU_TRY(cudaEventRecord(ev[4], st));
+    CU_TRY(cudaStreamSynchronize(st));
+    CU_TRY(cudaGetLastError());
+
+    dcpgpu_timing &t = res->timing;
+    cudaEventElapsedTime(&t.prep_ms, ev[0], ev[1]);
+    cudaEventElapsedTime(&t.score_ms, ev[1], ev[2]);
+    cudaEventElapsedTime(&t.trace_ms, ev[3], ev[4]);
+    cudaEventElapsedTime(&t.total_ms, ev[0], ev[4]);
+    t.launches = launches;
+    t.alt_cells = cells;
+    t.h2d_bytes = spec.size() * sizeof(float);
+    t.d2h_bytes = d2h + res->steps.size() * sizeof(dcp_step) + res->hits.size() * 8;
+    for (auto &e : ev) cudaEventDestroy(e);
+    guard.r = nullptr;
+    *out = res;
+    return RC_OK;
+}
+
+extern "C" enum rc dcpgpu_scan(struct dcpgpu_db *db, unsigned nseqs, char const *const *seqs, unsigned const *lens,
+                               struct dcpgpu_params const *prm, struct dcpgpu_result **out)
+{
+    dcpgpu_seqs *sq = nullptr;
+    enum rc rc = dcpgpu_seqs_new(&sq, db, nseqs, seqs, lens);
+    if (rc) return rc;
+    rc = dcpgpu_scan_resident(db, sq, prm, out);
+    if (!rc) (*out)->timing.h2d_bytes += sq->h2d_bytes;
+    dcpgpu_seqs_del(sq);
+    return rc;
+}
+
+static enum rc result_fetch(dcpgpu_result *r)
+{
+    if (r->fetched) return RC_OK;
+    CU_TRY(cudaSetDevice(r->db->device));
+    size_t n = (size_t)r->nseq * r->nprof;
+    r->alt.resize(n), r->null_ll.resize(n), r->hit.resize(n);
+    std::vector<float> nt((size_t)r->nseq * r->n_null);
+    CU_TRY(cudaMemcpy(r->alt.data(), r->d_alt, n * sizeof(float), cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(nt.data(), r->d_null, nt.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(r->hit.data(), r->d_hit, n, cudaMemcpyDeviceToHost));
+    for (uint32_t s = 0; s < r->nseq; ++s)
+        for (uint32_t p = 0; p < r->nprof; ++p)
+            r->null_ll[(size_t)s * r->nprof + p] = nt[(size_t)s * r->n_null + r->db->null_id[p]];
+    r->fetched = true;
+    return RC_OK;
+}
+
+extern "C" unsigned dcpgpu_result_nseqs(struct dcpgpu_result const *r) { return r->nseq; }
+extern "C" unsigned dcpgpu_result_nprofiles(struct dcpgpu_result const *r) { return r->nprof; }
+extern "C" float const *dcpgpu_result_null_loglik(struct dcpgpu_result const *r)
+{
+    return result_fetch(const_cast<dcpgpu_result *>(r)) ? nullptr : r->null_ll.data();
+}
+extern "C" float const *dcpgpu_result_alt_loglik(struct dcpgpu_result const *r)
+{
+    return result_fetch(const_cast<dcpgpu_result *>(r)) ? nullptr : r->alt.data();
+}
+extern "C" uint8_t const *dcpgpu_result_hit(struct dcpgpu_result const *r)
+{
+    return result_fetch(const_cast<dcpgpu_result *>(r)) ? nullptr : r->hit.data();
+}
+extern "C" uint64_t dcpgpu_result_nhits(struct dcpgpu_result const *r) { return r->hits.size(); }
+
+extern "C" enum rc dcpgpu_result_hit_at(struct dcpgpu_result const *r, uint64_t i, unsigned *seq_idx,
+                                        unsigned *prof_idx, struct dcp_step const **steps, unsigned *nsteps)
+{
+    if (i >= r->hits.size()) return dcp_error(RC_EINVAL, "hit index out of range");
+    const HitRec &h = r->hits[i];
+    if (seq_idx) *seq_idx = h.seq;
+    if (prof_idx) *prof_idx = h.prof;
+    if (steps) *steps = r->have_paths ? r->steps.data() + h.step_off : nullptr;
+    if (nsteps) *nsteps = r->have_paths ? h.nsteps : 0;
+    return RC_OK;
+}
+
+extern "C" void dcpgpu_result_timing(struct dcpgpu_result const *r, struct dcpgpu_timing *t) { *t = r->timing; }
+
+extern "C" void dcpgpu_result_del(struct dcpgpu_result *r)
+{
+    if (!r) return;
+    cudaSetDevice(r->db->device);
+    cudaFree(r->d_alt), cudaFree(r->d_null), cudaFree(r->d_hit);
+    delete r;
+}

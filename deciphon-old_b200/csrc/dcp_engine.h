@@ -1,0 +1,115 @@
+/* dcp_engine.h -- types shared by the CUDA translation units of libdcpgpu (C++ only). */
+#ifndef DCP_ENGINE_H
+#define DCP_ENGINE_H
+
+#include "dcp_internal.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdint>
+#include <vector>
+
+#define NEG_INF (-INFINITY)
+#define FULL 0xffffffffu
+
+constexpr int kTab = DCP_FRAME_TABLE_SIZE;
+constexpr int kMaxQ = 8;          /* nodes per lane, single-warp classes cover M <= 256 */
+constexpr int kWarpsPerBlock = 8; /* k_score block = 8 independent warps */
+constexpr int kSeqChunk = 4;      /* sequences per work item */
+
+#define CU_TRY(expr)                                                                           \
+    do                                                                                         \
+    {                                                                                          \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+        {                                                                                      \
+            dcp_set_error(cudaGetErrorString(e_));                                             \
+            return RC_EFAIL;                                                                   \
+        }                                                                                      \
+    } while (0)
+
+/* one DP row of one sequence under one null table: 64 bytes */
+struct __align__(16) RowRec
+{
+    float eN[5];      /* N/J/C/R emission of seq[j-l:j], l = 1..5 */
+    float eI[5];      /* insert emission */
+    uint32_t code[5]; /* frame-table code of seq[j-l:j] */
+    uint32_t pad;
+};
+static_assert(sizeof(RowRec) == 64, "row record is one 64-byte line");
+
+struct ProfMeta
+{
+    uint32_t M, Q, QP, null_id;
+    uint64_t emis_off;  /* floats into d_emis */
+    uint64_t trans_off; /* floats into d_trans */
+};
+
+struct SeqMeta
+{
+    uint32_t len;
+    uint32_t pad;
+    uint64_t row_off; /* first row record (row j=1) / first base */
+};
+
+
+struct dcpgpu_db
+{
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool committed = false;
+    float epsilon = -1.0f;
+    std::vector<protein_profile *> profs; /* deep copies, host side (decode, products) */
+    std::vector<std::vector<float>> null_tabs;
+    std::vector<uint32_t> null_id;
+    std::vector<ProfMeta> metas;
+    std::vector<uint32_t> class_list[kMaxQ + 1]; /* profile ids by Q */
+    float *d_emis = nullptr, *d_trans = nullptr, *d_null_tabs = nullptr, *d_ins_tab = nullptr;
+    ProfMeta *d_metas = nullptr;
+    uint32_t *d_class[kMaxQ + 1] = {nullptr};
+    uint64_t device_bytes = 0;
+};
+
+struct dcpgpu_seqs
+{
+    dcpgpu_db *db = nullptr;
+    uint32_t nseq = 0;
+    uint64_t total = 0; /* nucleotides == row records per null table */
+    std::vector<SeqMeta> metas;
+    uint8_t *d_bases = nullptr;
+    SeqMeta *d_metas = nullptr;
+    uint64_t h2d_bytes = 0;
+};
+
+struct HitRec
+{
+    uint32_t seq, prof;
+    uint64_t step_off;
+    uint32_t nsteps;
+};
+
+struct dcpgpu_result
+{
+    dcpgpu_db *db = nullptr;
+    uint32_t nseq = 0, nprof = 0, n_null = 0;
+    float *d_alt = nullptr, *d_null = nullptr;
+    uint8_t *d_hit = nullptr;
+    bool fetched = false;
+    std::vector<float> alt, null_ll;
+    std::vector<uint8_t> hit;
+    std::vector<HitRec> hits;
+    std::vector<float> hit_alt, hit_null;
+    std::vector<dcp_step> steps;
+    bool have_paths = false;
+    dcpgpu_timing timing = {};
+};
+
+
+/* dcp_trace.cu */
+enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const RowRec *d_rows,
+                       const float *d_spec, uint64_t *launches);
+const protein_profile *dcp_db_profile(struct dcpgpu_db const *db, unsigned i);
+
+#endif

@@ -1,0 +1,534 @@
+/*
+ * dcp_trace.cu -- traceback pass for hits only (imm_prod.path of imm_dp_viterbi on the alt dp,
+ * consumed by prod_fwrite, src/server/prod.c:153-181).
+ *
+ * k_trace<Q> re-runs the alt recurrence of one (sequence, profile) hit with the same warp /
+ * lane / register layout and the same fp32 operation order as k_score<Q> (so T[L] is bit-equal),
+ * and records for every state and row which incoming (transition, source length) won.  The
+ * winner is imm's: first maximum, strict '>', over incoming transitions in canonical order and,
+ * inside one transition, over the source's emission length ascending -- evaluated on the rounded
+ * sums fl(fl(Tin + e) + t), exactly like a start-position interpreter would.
+ *
+ * Canonical incoming order (imm's own order is not recoverable from the reference tree):
+ *   M_k: B, M_{k-1}, I_{k-1}, D_{k-1}    I_k: M_k, I_k    D_k: M_{k-1}, D_{k-1}
+ *   E: M_1, M_2, D_2, M_3, D_3, ...      N: S, N    B: S, N, J, E    J: E, J   C: E, C   T: E, C
+ *
+ * Backpointers: one uint16 per (row, node) [mcode:4 | icode:4 | dcode:3] stored as
+ * [row][sub-node][lane] (64-byte coalesced stores) and one uint32 per row for the specials
+ * [ecode:15 | n:3 | b:4 | j:3 | c:3 | t:3].
+ */
+#include "dcp_kernels.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+namespace
+{
+
+struct TraceJob
+{
+    uint32_t seq, prof;
+    uint64_t cell_off; /* uint16 units */
+    uint64_t row_off;  /* uint32 units */
+};
+
+__device__ __forceinline__ void first_max5(const float (&s)[5], float t, int base, float &best, int &code)
+{
+#pragma unroll
+    for (int l = 0; l < 5; ++l)
+    {
+        float v = s[l] + t;
+        if (v > best) best = v, code = base + l;
+    }
+}
+
+template <int Q, int R>
+__device__ __forceinline__ void trace_row(float (&tm)[5][Q], float (&ti)[5][Q], float (&tn)[5], float (&tj)[5],
+                                          float (&tc)[5], const NodeParams<Q> &p,
+                                          const float *__restrict__ emis_lane, const RowRec *__restrict__ rec,
+                                          int lane, const float *__restrict__ sp, uint16_t *__restrict__ cell_bp,
+                                          uint32_t *__restrict__ row_bp, float &T_out)
+{
+    constexpr int S[5] = {(R + 4) % 5, (R + 3) % 5, (R + 2) % 5, (R + 1) % 5, R};
+    const float NN = sp[0], CC = sp[1], JJ = sp[2], NB = sp[3], CT = sp[4], JB = sp[5];
+    const float ET = sp[9], ECC = sp[10], EB = sp[11], EJJ = sp[12];
+    RowIn in = load_row(rec);
+    float em[5][Q];
+    load_emis<Q>(em, emis_lane, in.code);
+
+    /* W[j-l][X][l] for every emitting state: the five candidate sums per state */
+    float sM[Q][5], sI[Q][5], vm[Q], vi[Q];
+#pragma unroll
+    for (int i = 0; i < Q; ++i)
+    {
+#pragma unroll
+        for (int l = 0; l < 5; ++l)
+        {
+            sM[i][l] = tm[S[l]][i] + em[l][i];
+            sI[i][l] = ti[S[l]][i] + in.eI[l];
+        }
+        vm[i] = fmaxf(max3(sM[i][0], sM[i][1], sM[i][2]), fmaxf(sM[i][3], sM[i][4]));
+        vi[i] = fmaxf(max3(sI[i][0], sI[i][1], sI[i][2]), fmaxf(sI[i][3], sI[i][4]));
+    }
+    float sN[5], sJ[5], sC[5];
+#pragma unroll
+    for (int l = 0; l < 5; ++l)
+    {
+        sN[l] = tn[S[l]] + in.eN[l];
+        sJ[l] = tj[S[l]] + in.eN[l];
+        sC[l] = tc[S[l]] + in.eN[l];
+    }
+    /* sums of the node to the left of this lane's first node */
+    float pM0[5], pI0[5];
+#pragma unroll
+    for (int l = 0; l < 5; ++l)
+    {
+        pM0[l] = __shfl_up_sync(FULL, sM[Q - 1][l], 1);
+        pI0[l] = __shfl_up_sync(FULL, sI[Q - 1][l], 1);
+        if (lane == 0) pM0[l] = NEG_INF, pI0[l] = NEG_INF;
+    }
+
+    /* D chain (order: M_{k-1} by length, then D_{k-1}) */
+    float d[Q];
+    int dcode[Q];
+#pragma unroll
+    for (int i = 0; i < Q; ++i)
+    {
+        float best = NEG_INF;
+        int code = 0;
+        if (i == 0)
+            first_max5(pM0, p.MD[0], 0, best, code);
+        else
+        {
+            first_max5(sM[i - 1], p.MD[i], 0, best, code);
+            float x = d[i - 1] + p.DD[i];
+            if (x > best) best = x, code = 5;
+        }
+        d[i] = best, dcode[i] = code;
+    }
+    float din;
+    for (;;)
+    {
+        float old = d[Q - 1];
+        din = __shfl_up_sync(FULL, old, 1);
+        if (lane == 0) din = NEG_INF;
+        float x = din;
+#pragma unroll
+        for (int i = 0; i < Q; ++i)
+        {
+            x = x + p.DD[i];
+            if (x > d[i]) d[i] = x, dcode[i] = 5;
+            x = d[i];
+        }
+        if (!__any_sync(FULL, d[Q - 1] > old)) break;
+    }
+
+    /* E: first max over M_1, M_2, D_2, ... ; lanes hold increasing k */
+    float ebest = NEG_INF;
+    int ecode = 0;
+#pragma unroll
+    for (int i = 0; i < Q; ++i)
+    {
+        int k0 = lane * Q + i; /* k - 1 */
+        float zero = 0.0f;
+        first_max5(sM[i], zero, k0 * 6, ebest, ecode);
+        if (k0 >= 1)
+        {
+            float v = d[i] + zero;
+            if (v > ebest) ebest = v, ecode = k0 * 6 + 5;
+        }
+    }
+    float E = warp_max(ebest);
+    unsigned who = __ballot_sync(FULL, ebest == E);
+    ecode = __shfl_sync(FULL, ecode, who ? __ffs(who) - 1 : 0);
+
+    /* specials */
+    float best;
+    int ncode = 0, bcode = 0, jcode = 0, ccode = 0, tcode = 0;
+    best = NEG_INF;
+    first_max5(sN, NN, 1, best, ncode);
+    float tinN = best;
+    best = NEG_INF;
+    first_max5(sN, NB, 1, best, bcode);
+    first_max5(sJ, JB, 6, best, bcode);
+    {
+        float v = E + EB;
+        if (v > best) best = v, bcode = 11;
+    }
+    float B = best;
+    best = E + EJJ, jcode = 0;
+    first_max5(sJ, JJ, 1, best, jcode);
+    float tinJ = best;
+    best = E + ECC, ccode = 0;
+    first_max5(sC, CC, 1, best, ccode);
+    float tinC = best;
+    best = E + ET, tcode = 0;
+    first_max5(sC, CT, 1, best, tcode);
+    T_out = best;
+    tn[R] = tinN, tj[R] = tinJ, tc[R] = tinC;
+    if (lane == 0)
+        *row_bp = (uint32_t)ecode | (uint32_t)ncode << 15 | (uint32_t)bcode << 18 | (uint32_t)jcode << 22 |
+                  (uint32_t)ccode << 25 | (uint32_t)tcode << 28;
+
+    /* core Tin + backpointers */
+#pragma unroll
+    for (int i = 0; i < Q; ++i)
+    {
+        float mb = B + p.ent[i];
+        int mcode = 0;
+        if (i == 0)
+        {
+            first_max5(pM0, p.MM[0], 1, mb, mcode);
+            first_max5(pI0, p.IM[0], 6, mb, mcode);
+            float v = din + p.DM[0];
+            if (v > mb) mb = v, mcode = 11;
+        }
+        else
+        {
+            first_max5(sM[i - 1], p.MM[i], 1, mb, mcode);
+            first_max5(sI[i - 1], p.IM[i], 6, mb, mcode);
+            float v = d[i - 1] + p.DM[i];
+            if (v > mb) mb = v, mcode = 11;
+        }
+        float ib = NEG_INF;
+        int icode = 0;
+        first_max5(sM[i], p.MI[i], 0, ib, icode);
+        first_max5(sI[i], p.II[i], 5, ib, icode);
+        tm[R][i] = mb;
+        ti[R][i] = ib;
+        cell_bp[i * 32 + lane] = (uint16_t)(mcode | icode << 4 | dcode[i] << 8);
+    }
+}
+
+template <int Q>
+__global__ void __launch_bounds__(128) k_trace(const float *__restrict__ emis, const float *__restrict__ trans,
+                                               const ProfMeta *__restrict__ metas,
+                                               const SeqMeta *__restrict__ seqs, uint64_t total_rows,
+                                               const RowRec *__restrict__ rows, const float *__restrict__ spec,
+                                               const TraceJob *__restrict__ jobs, uint32_t njobs,
+                                               uint16_t *__restrict__ cell_bp, uint32_t *__restrict__ row_bp,
+                                               float *__restrict__ alt_out)
+{
+    constexpr int QP = Q <= 4 ? 4 : 8;
+    const int lane = threadIdx.x & 31;
+    uint32_t job = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (job >= njobs) return;
+    TraceJob tj_ = jobs[job];
+    ProfMeta pm = metas[tj_.prof];
+    SeqMeta sm = seqs[tj_.seq];
+    NodeParams<Q> p;
+    load_params<Q>(p, trans + pm.trans_off, lane);
+    const float *emis_lane = emis + pm.emis_off + lane * QP;
+    const RowRec *r = rows + (size_t)pm.null_id * total_rows + sm.row_off;
+    const float *sp = spec + (size_t)tj_.seq * 16;
+    uint16_t *cb = cell_bp + tj_.cell_off;
+    uint32_t *rb = row_bp + tj_.row_off;
+    const uint32_t L = sm.len;
+
+    float tm[5][Q], ti[5][Q], tn[5], tjr[5], tc[5];
+#pragma unroll
+    for (int s = 0; s < 5; ++s)
+    {
+        tn[s] = tjr[s] = tc[s] = NEG_INF;
+#pragma unroll
+        for (int i = 0; i < Q; ++i) tm[s][i] = NEG_INF, ti[s][i] = NEG_INF;
+    }
+    /* row 0: S starts; N <- S, B <- S, M_k <- B; codes are all 0 */
+    const float NN = sp[0], NB = sp[3];
+#pragma unroll
+    for (int i = 0; i < Q; ++i)
+    {
+        tm[4][i] = NB + p.ent[i];
+        cb[i * 32 + lane] = 0;
+    }
+    tn[4] = NN;
+    if (lane == 0) rb[0] = 0;
+
+    float T = NEG_INF;
+    uint32_t j = 1;
+    constexpr uint32_t CS = Q * 32; /* cell backpointers per row */
+    for (; j + 4 <= L; j += 5)
+    {
+        trace_row<Q, 0>(tm, ti, tn, tjr, tc, p, emis_lane, r + (j - 1), lane, sp, cb + (size_t)j * CS, rb + j, T);
+        trace_row<Q, 1>(tm, ti, tn, tjr, tc, p, emis_lane, r + j, lane, sp, cb + (size_t)(j + 1) * CS, rb + j + 1, T);
+        trace_row<Q, 2>(tm, ti, tn, tjr, tc, p, emis_lane, r + (j + 1), lane, sp, cb + (size_t)(j + 2) * CS, rb + j + 2, T);
+        trace_row<Q, 3>(tm, ti, tn, tjr, tc, p, emis_lane, r + (j + 2), lane, sp, cb + (size_t)(j + 3) * CS, rb + j + 3, T);
+        trace_row<Q, 4>(tm, ti, tn, tjr, tc, p, emis_lane, r + (j + 3), lane, sp, cb + (size_t)(j + 4) * CS, rb + j + 4, T);
+    }
+    if (j <= L) trace_row<Q, 0>(tm, ti, tn, tjr, tc, p, emis_lane, r + (j - 1), lane, sp, cb + (size_t)j * CS, rb + j, T);
+    if (j + 1 <= L) trace_row<Q, 1>(tm, ti, tn, tjr, tc, p, emis_lane, r + j, lane, sp, cb + (size_t)(j + 1) * CS, rb + j + 1, T);
+    if (j + 2 <= L) trace_row<Q, 2>(tm, ti, tn, tjr, tc, p, emis_lane, r + (j + 1), lane, sp, cb + (size_t)(j + 2) * CS, rb + j + 2, T);
+    if (j + 3 <= L) trace_row<Q, 3>(tm, ti, tn, tjr, tc, p, emis_lane, r + (j + 2), lane, sp, cb + (size_t)(j + 3) * CS, rb + j + 3, T);
+    if (lane == 0) alt_out[job] = T;
+}
+
+/*
+ * Follow the backpointers from (T, row L) to S.  mode 0: count steps; mode 1: write them
+ * (reversed, then flipped in place) at steps + step_off[job].
+ */
+enum { W_S, W_N, W_B, W_E, W_J, W_C, W_T, W_M, W_I, W_D };
+
+__global__ void k_walk(const ProfMeta *__restrict__ metas, const SeqMeta *__restrict__ seqs,
+                       const TraceJob *__restrict__ jobs, uint32_t njobs, const uint16_t *__restrict__ cell_bp,
+                       const uint32_t *__restrict__ row_bp, int mode, uint32_t *__restrict__ nsteps,
+                       const uint64_t *__restrict__ step_off, dcp_step *__restrict__ steps,
+                       uint32_t *__restrict__ errors)
+{
+    uint32_t job = blockIdx.x * blockDim.x + threadIdx.x;
+    if (job >= njobs) return;
+    TraceJob tj = jobs[job];
+    const uint32_t Q = metas[tj.prof].Q;
+    const uint32_t CS = Q * 32;
+    const uint16_t *cb = cell_bp + tj.cell_off;
+    const uint32_t *rb = row_bp + tj.row_off;
+    const uint32_t L = seqs[tj.seq].len;
+    dcp_step *out = mode ? steps + step_off[job] : nullptr;
+    const uint32_t limit = mode ? nsteps[job] : 0xffffffffu;
+
+    int st = W_T;
+    uint32_t k = 0, r = L, len = 0, n = 0;
+    bool bad = false;
+    for (;;)
+    {
+        uint16_t id;
+        switch (st)
+        {
+        case W_M: id = (uint16_t)(PROTEIN_MATCH_STATE | k); break;
+        case W_I: id = (uint16_t)(PROTEIN_INSERT_STATE | k); break;
+        case W_D: id = (uint16_t)(PROTEIN_DELETE_STATE | k); break;
+        case W_S: id = PROTEIN_S_STATE; break;
+        case W_N: id = PROTEIN_N_STATE; break;
+        case W_B: id = PROTEIN_B_STATE; break;
+        case W_E: id = PROTEIN_E_STATE; break;
+        case W_J: id = PROTEIN_J_STATE; break;
+        case W_C: id = PROTEIN_C_STATE; break;
+        default: id = PROTEIN_T_STATE; break;
+        }
+        if (mode)
+        {
+            if (n >= limit) { bad = true; break; }
+            out[n].state_id = id, out[n].seqlen = (uint8_t)len;
+        }
+        n++;
+        if (st == W_S) break;
+        if (n > 0x7ffffff0u) { bad = true; break; }
+        uint32_t rw = rb[r];
+        uint32_t src_len = 0;
+        int nst = st;
+        uint32_t nk = k;
+        if (st == W_M || st == W_I || st == W_D)
+        {
+            uint32_t node = k - 1;
+            uint16_t c = cb[(size_t)r * CS + (node % Q) * 32 + node / Q];
+            if (st == W_M)
+            {
+                uint32_t m = c & 15;
+                if (m == 0) nst = W_B;
+                else if (m <= 5) nst = W_M, nk = k - 1, src_len = m;
+                else if (m <= 10) nst = W_I, nk = k - 1, src_len = m - 5;
+                else nst = W_D, nk = k - 1;
+            }
+            else if (st == W_I)
+            {
+                uint32_t m = (c >> 4) & 15;
+                if (m <= 4) nst = W_M, src_len = m + 1;
+                else nst = W_I, src_len = m - 4;
+            }
+            else
+            {
+                uint32_t m = (c >> 8) & 7;
+                if (m <= 4) nst = W_M, nk = k - 1, src_len = m + 1;
+                else nst = W_D, nk = k - 1;
+            }
+            if (nk == 0 && nst != W_B) { bad = true; break; }
+        }
+        else if (st == W_T)
+        {
+            uint32_t m = (rw >> 28) & 7;
+            if (m == 0) nst = W_E; else nst = W_C, src_len = m;
+        }
+        else if (st == W_C)
+        {
+            uint32_t m = (rw >> 25) & 7;
+            if (m == 0) nst = W_E; else nst = W_C, src_len = m;
+        }
+        else if (st == W_J)
+        {
+            uint32_t m = (rw >> 22) & 7;
+            if (m == 0) nst = W_E; else nst = W_J, src_len = m;
+        }
+        else if (st == W_B)
+        {
+            uint32_t m = (rw >> 18) & 15;
+            if (m == 0) nst = W_S;
+            else if (m <= 5) nst = W_N, src_len = m;
+            else if (m <= 10) nst = W_J, src_len = m - 5;
+            else nst = W_E;
+        }
+        else if (st == W_N)
+        {
+            uint32_t m = (rw >> 15) & 7;
+            if (m == 0) nst = W_S; else nst = W_N, src_len = m;
+        }
+        else /* W_E */
+        {
+            uint32_t m = rw & 0x7fff;
+            nk = m / 6 + 1;
+            uint32_t sub = m % 6;
+            if (sub <= 4) nst = W_M, src_len = sub + 1; else nst = W_D;
+        }
+        if (src_len > r) { bad = true; break; }
+        if (nst == W_S && r != 0) { bad = true; break; }
+        r -= src_len;
+        st = nst, k = nk, len = src_len;
+    }
+    if (bad)
+    {
+        atomicAdd(errors, 1u);
+        if (!mode) nsteps[job] = 0;
+        return;
+    }
+    if (!mode)
+        nsteps[job] = n;
+    else
+        for (uint32_t a = 0, b = n - 1; a < b; ++a, --b)
+        {
+            dcp_step t = out[a];
+            out[a] = out[b], out[b] = t;
+        }
+}
+
+struct DevBuf
+{
+    void *p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+    template <class T>
+    T *as() { return (T *)p; }
+};
+
+template <int Q>
+void launch_trace(cudaStream_t st, uint32_t njobs, const dcpgpu_db *db, const dcpgpu_seqs *sq, const RowRec *rows,
+                  const float *spec, const TraceJob *jobs, uint16_t *cell_bp, uint32_t *row_bp, float *alt)
+{
+    k_trace<Q><<<(njobs + 3) / 4, 128, 0, st>>>(db->d_emis, db->d_trans, db->d_metas, sq->d_metas, sq->total, rows,
+                                                spec, jobs, njobs, cell_bp, row_bp, alt);
+}
+
+} // namespace
+
+enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const RowRec *d_rows,
+                       const float *d_spec, uint64_t *launches)
+{
+    cudaStream_t st = db->stream;
+    const size_t nhits = res->hits.size();
+    /* backpointer budget per batch */
+    size_t free_b = 0, total_b = 0;
+    CU_TRY(cudaMemGetInfo(&free_b, &total_b));
+    const size_t budget = std::max<size_t>(free_b / 2, (size_t)64 << 20);
+
+    const std::vector<float> &score_alt = res->hit_alt; /* score pass result of each hit */
+
+    size_t done = 0;
+    while (done < nhits)
+    {
+        /* take hits while their backpointers fit the budget; group the batch by class */
+        std::vector<TraceJob> jobs;
+        size_t cells = 0, rowsz = 0, end = done;
+        while (end < nhits)
+        {
+            const HitRec &h = res->hits[end];
+            uint32_t Q = db->metas[h.prof].Q;
+            size_t L1 = (size_t)sq->metas[h.seq].len + 1;
+            size_t need = L1 * Q * 32 * sizeof(uint16_t) + L1 * sizeof(uint32_t);
+            if (!jobs.empty() && (cells * 2 + rowsz * 4 + need > budget)) break;
+            jobs.push_back({h.seq, h.prof, cells, rowsz});
+            cells += L1 * Q * 32;
+            rowsz += L1;
+            ++end;
+        }
+        const uint32_t nj = (uint32_t)jobs.size();
+        /* order jobs by class so each launch sees a contiguous range */
+        std::vector<uint32_t> order(nj);
+        for (uint32_t i = 0; i < nj; ++i) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+            return db->metas[jobs[a].prof].Q < db->metas[jobs[b].prof].Q;
+        });
+        std::vector<TraceJob> sorted(nj);
+        for (uint32_t i = 0; i < nj; ++i) sorted[i] = jobs[order[i]];
+
+        DevBuf b_jobs, b_cells, b_rows, b_alt, b_n, b_off, b_err, b_steps;
+        CU_TRY(cudaMalloc(&b_jobs.p, nj * sizeof(TraceJob)));
+        CU_TRY(cudaMalloc(&b_cells.p, cells * sizeof(uint16_t)));
+        CU_TRY(cudaMalloc(&b_rows.p, rowsz * sizeof(uint32_t)));
+        CU_TRY(cudaMalloc(&b_alt.p, nj * sizeof(float)));
+        CU_TRY(cudaMalloc(&b_n.p, nj * sizeof(uint32_t)));
+        CU_TRY(cudaMalloc(&b_off.p, nj * sizeof(uint64_t)));
+        CU_TRY(cudaMalloc(&b_err.p, sizeof(uint32_t)));
+        CU_TRY(cudaMemcpyAsync(b_jobs.p, sorted.data(), nj * sizeof(TraceJob), cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemsetAsync(b_err.p, 0, sizeof(uint32_t), st));
+        for (uint32_t a = 0; a < nj;)
+        {
+            uint32_t Q = db->metas[sorted[a].prof].Q, b = a;
+            while (b < nj && db->metas[sorted[b].prof].Q == Q) ++b;
+#define LT(QQ)                                                                                                   \
+    case QQ:                                                                                                     \
+        launch_trace<QQ>(st, b - a, db, sq, d_rows, d_spec, b_jobs.as<TraceJob>() + a, b_cells.as<uint16_t>(),   \
+                         b_rows.as<uint32_t>(), b_alt.as<float>() + a);                                          \
+        break;
+            switch (Q)
+            {
+                LT(1) LT(2) LT(3) LT(4) LT(5) LT(6) LT(7) LT(8)
+            }
+#undef LT
+            (*launches)++;
+            a = b;
+        }
+        CU_TRY(cudaGetLastError());
+        k_walk<<<(nj + 63) / 64, 64, 0, st>>>(db->d_metas, sq->d_metas, b_jobs.as<TraceJob>(), nj,
+                                              b_cells.as<uint16_t>(), b_rows.as<uint32_t>(), 0, b_n.as<uint32_t>(),
+                                              nullptr, nullptr, b_err.as<uint32_t>());
+        (*launches)++;
+        std::vector<uint32_t> ns(nj);
+        std::vector<float> talt(nj);
+        uint32_t nerr = 0;
+        CU_TRY(cudaMemcpyAsync(ns.data(), b_n.p, nj * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(talt.data(), b_alt.p, nj * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(&nerr, b_err.p, sizeof nerr, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        if (nerr) return dcp_error(RC_EFAIL, "traceback walked off the DP matrix");
+        std::vector<uint64_t> off(nj);
+        uint64_t tot = 0;
+        for (uint32_t i = 0; i < nj; ++i) off[i] = tot, tot += ns[i];
+        for (uint32_t i = 0; i < nj; ++i)
+        {
+            size_t hit = done + order[i];
+            if (memcmp(&talt[i], &score_alt[hit], sizeof(float)) != 0)
+                return dcp_error(RC_EFAIL, "trace pass and score pass disagree on the alt log-likelihood");
+        }
+        CU_TRY(cudaMalloc(&b_steps.p, std::max<uint64_t>(tot, 1) * sizeof(dcp_step)));
+        CU_TRY(cudaMemcpyAsync(b_off.p, off.data(), nj * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+        k_walk<<<(nj + 63) / 64, 64, 0, st>>>(db->d_metas, sq->d_metas, b_jobs.as<TraceJob>(), nj,
+                                              b_cells.as<uint16_t>(), b_rows.as<uint32_t>(), 1, b_n.as<uint32_t>(),
+                                              b_off.as<uint64_t>(), b_steps.as<dcp_step>(), b_err.as<uint32_t>());
+        (*launches)++;
+        std::vector<dcp_step> got(tot);
+        CU_TRY(cudaMemcpyAsync(got.data(), b_steps.p, tot * sizeof(dcp_step), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(&nerr, b_err.p, sizeof nerr, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        if (nerr) return dcp_error(RC_EFAIL, "traceback walked off the DP matrix");
+        /* append in hit order */
+        std::vector<uint32_t> inv(nj);
+        for (uint32_t i = 0; i < nj; ++i) inv[order[i]] = i;
+        for (uint32_t h = 0; h < nj; ++h)
+        {
+            uint32_t i = inv[h];
+            HitRec &hr = res->hits[done + h];
+            hr.step_off = res->steps.size();
+            hr.nsteps = ns[i];
+            res->steps.insert(res->steps.end(), got.begin() + off[i], got.begin() + off[i] + ns[i]);
+        }
+        done = end;
+    }
+    return RC_OK;
+}

@@ -1,0 +1,106 @@
+"""Shared helpers for the parity tests."""
+import numpy as np
+
+import json
+import os
+
+GOLD = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden.json")))
+SEQ32 = GOLD["seq32"]      # test/protein_profile.c:27
+SEQ1053 = GOLD["seq1053"]  # test/protein_h3reader.c:6-24
+
+AMINO = "ACDEFGHIKLMNPQRSTVWY"
+_TCAG = "TCAG"
+_AAS = "FFLLSSSSYY**CC*WLLLLPPPPHHQQRRRRIIIMTTTTNNKKSSRRVVVVAAAADDEEGGGG"
+CODONS_OF = {}
+for _i, _a in enumerate(_TCAG):
+    for _j, _b in enumerate(_TCAG):
+        for _k, _c in enumerate(_TCAG):
+            CODONS_OF.setdefault(_AAS[_i * 16 + _j * 4 + _k], []).append(_a + _b + _c)
+
+
+def frameshift(seq, rng, indel=0.02, sub=0.01):
+    out = []
+    for ch in seq:
+        r = rng.random()
+        if r < indel / 2:
+            continue
+        if r < indel:
+            out.append(ch)
+            out.append("ACGT"[rng.integers(0, 4)])
+            continue
+        if r < indel + sub:
+            out.append("ACGT"[rng.integers(0, 4)])
+            continue
+        out.append(ch)
+    return "".join(out) or "A"
+
+
+def random_seq(rng, n):
+    return "".join("ACGT"[i] for i in rng.integers(0, 4, n))
+
+
+def plan7_profile_inputs(rng, M, sharp=4.0):
+    """Pfam-shaped synthetic model inputs: peaked match distributions, Plan7-like transitions."""
+    bg = np.array([0.0787945, 0.0151600, 0.0535222, 0.0668298, 0.0397062, 0.0695071, 0.0229198, 0.0590092,
+                   0.0594422, 0.0963728, 0.0237718, 0.0414386, 0.0482904, 0.0395639, 0.0540978, 0.0683364,
+                   0.0540687, 0.0673417, 0.0114135, 0.0304133])
+    null_lp = np.log(bg / bg.sum())
+    g = rng.gamma(1.0 / sharp, 1.0, size=(M, 20)) * bg + 1e-6
+    match_lp = np.log(g / g.sum(1, keepdims=True))
+    tr = np.zeros((M + 1, 7))
+    for i in range(M + 1):
+        mm = rng.uniform(0.85, 0.97)
+        mi = (1 - mm) * rng.uniform(0.3, 0.7)
+        md = 1 - mm - mi
+        im = rng.uniform(0.4, 0.8)
+        dm = rng.uniform(0.3, 0.8)
+        t = np.log(np.array([mm, mi, md, im, 1 - im, dm, 1 - dm]))
+        if i == 0:
+            t[6] = -np.inf
+            t[5] = 0.0
+        if i == M:
+            t = np.log(np.array([mm + md, mi, 1e-300, im, 1 - im, 1.0, 1e-300]))
+            t[2] = -np.inf
+            t[6] = -np.inf
+        tr[i] = t
+    return null_lp, match_lp, tr
+
+
+def sample_read(rng, match_lp, L, indel=0.02, sub=0.01):
+    """A read carrying a frameshifted codon path drawn from the profile, padded with random nt."""
+    M = match_lp.shape[0]
+    cod = []
+    for k in range(M):
+        p = np.exp(match_lp[k])
+        aa = AMINO[rng.choice(20, p=p / p.sum())]
+        cs = CODONS_OF[aa]
+        cod.append(cs[rng.integers(0, len(cs))])
+    core = frameshift("".join(cod), rng, indel, sub)
+    if len(core) >= L:
+        s = rng.integers(0, len(core) - L + 1)
+        return core[s:s + L]
+    pad = L - len(core)
+    left = rng.integers(0, pad + 1)
+    return random_seq(rng, left) + core + random_seq(rng, pad - left)
+
+
+def oracle_twin(o, p, eps):
+    """Oracle profile holding bit-identical DP-level numbers of a product profile."""
+    M = p.core_size
+    return o.import_tables(M, float(np.float32(eps)), p.match_emission, p.insert_emission, p.null_emission,
+                           p.trans, p.entry, p.nuclt_dist(-2), p.nuclt_dist(-1),
+                           np.stack([p.nuclt_dist(k) for k in range(M)]))
+
+
+def ref_paths(ref, nprof):
+    """dict (seq, prof) -> [(state, len)] from orc.Oracle.scan output."""
+    out = {}
+    off = ref["path_off"]
+    nseq = ref["hit"].shape[0]
+    for s in range(nseq):
+        for p in range(nprof):
+            i = s * nprof + p
+            if off[i + 1] > off[i]:
+                out[(s, p)] = list(zip(ref["step_state"][off[i]:off[i + 1]].tolist(),
+                                       ref["step_len"][off[i]:off[i + 1]].tolist()))
+    return out

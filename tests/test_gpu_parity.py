@@ -1,0 +1,164 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle on identical inputs.
+Scores are compared bit for bit (same fp32 operation order), hit sets and decoded paths exactly."""
+import numpy as np
+import pytest
+
+import orc
+from common import (GOLD, SEQ32, SEQ1053, frameshift, oracle_twin, plan7_profile_inputs, random_seq, ref_paths,
+                    sample_read)
+
+pytestmark = pytest.mark.gpu
+EPS_01F = float(np.float32(0.1))
+
+
+def make_db(pkg, o, specs, eps, device=0):
+    """specs: list of (seed, M, entry_dist) sampled profiles.  Returns (db, product profiles, oracle twins)."""
+    db = pkg.Db(device)
+    twins = []
+    for seed, M, entry in specs:
+        p = pkg.ProteinProfile.sample(seed, M, pkg.protein_cfg(entry, eps), accession="PF%05d" % seed)
+        db.add(p)
+        twins.append(oracle_twin(o, p, eps))
+    db.commit()
+    return db, twins
+
+
+def check_scan(pkg, o, db, twins, seqs, multi_hits=True, hmmer3_compat=False, thr=10.0, flavour=0, rows=True):
+    res = db.scan(seqs, multi_hits, hmmer3_compat, thr, True)
+    ref = o.scan(twins, seqs, multi_hits, hmmer3_compat, thr, flavour, True)
+    assert ref["rc"] == 0
+    nprof = len(twins)
+    assert np.array_equal(res.null_loglik, ref["null"]), np.abs(res.null_loglik - ref["null"]).max()
+    assert np.array_equal(res.alt_loglik, ref["alt"]), np.abs(res.alt_loglik - ref["alt"]).max()
+    assert np.array_equal(res.hit, ref["hit"])
+    want = ref_paths(ref, nprof)
+    assert res.nhits == int(ref["hit"].sum()) == len(want)
+    order = []
+    for i in range(res.nhits):
+        si, pi, path = res.hit_at(i)
+        order.append((si, pi))
+        assert path == want[(si, pi)], (si, pi)
+        assert sum(l for _, l in path) == len(seqs[si])
+        if rows:
+            row = res.product_row(i, scan_id=7, seq_id=100 + si)
+            exp = twins[pi].product_row(7, 100 + si, "PF%05d" % 0 if False else db.profiles[pi].accession,
+                                        float(ref["alt"][si, pi]), float(ref["null"][si, pi]), seqs[si], path)
+            assert row == exp
+    assert order == sorted(order)  # (sequence, profile) order regardless of GPU scheduling
+    return res, ref
+
+
+def test_reference_golden_case_on_gpu(pkg, o32):
+    """test/protein_profile.c on the GPU path: loglik within the reference's fp32 tolerance, path shape, codons."""
+    for entry, key in ((pkg.ENTRY_DIST_UNIFORM, "uniform"), (pkg.ENTRY_DIST_OCCUPANCY, "occupancy")):
+        db, twins = make_db(pkg, o32, [(1, 2, entry)], EPS_01F)
+        res = db.scan([SEQ32], True, False, -1e30, True)
+        g = GOLD[key]
+        assert abs(float(res.null_loglik[0, 0]) - g["null_loglik"]) <= 5e-5 * abs(g["null_loglik"])
+        assert abs(float(res.alt_loglik[0, 0]) - g["alt_loglik"]) <= 5e-5 * abs(g["alt_loglik"])
+        si, pi, path = res.hit_at(0)
+        assert len(path) == g["alt_nsteps"] and path[0] == (pkg.PROTEIN_S_STATE, 0) and path[-1] == (pkg.PROTEIN_T_STATE, 0)
+        pos, cods = 0, []
+        for st, ln in path:
+            if ln:
+                cods.append(db.profiles[0].decode(SEQ32[pos:pos + ln], st)[1])
+                pos += ln
+        assert cods == GOLD["codons"]
+
+
+@pytest.mark.parametrize("eps", [EPS_01F, 0.01])
+def test_config1_sampled_profiles(pkg, o32, eps):
+    """BASELINE config 1 re-expressed: sampler profiles x the reference's test strings (+ frameshifted)."""
+    specs = [(1, 2, 1), (2, 3, 2), (3, 5, 1), (4, 17, 2), (5, 64, 2), (6, 2, 2), (7, 33, 1), (8, 64, 1)]
+    db, twins = make_db(pkg, o32, specs, eps)
+    rng = np.random.default_rng(1)
+    seqs = [SEQ32, SEQ1053, frameshift(SEQ32, rng, 0.1), frameshift(SEQ1053, rng), random_seq(rng, 77), "A", "ACGTA"]
+    for mh, h3 in ((True, False), (False, False), (True, True), (False, True)):
+        check_scan(pkg, o32, db, twins, seqs, mh, h3, thr=-1e30)
+    check_scan(pkg, o32, db, twins, seqs, thr=10.0)
+
+
+@pytest.mark.parametrize("M", [2, 31, 32, 33, 96, 128, 129, 200, 224, 255, 256])
+def test_every_lane_layout(pkg, o32, M):
+    """One profile per nodes-per-lane class boundary; short and ragged sequence lengths."""
+    db, twins = make_db(pkg, o32, [(M, M, 2)], 0.01)
+    rng = np.random.default_rng(M)
+    seqs = [random_seq(rng, n) for n in (1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 14, 15, 16, 61, 150)]
+    check_scan(pkg, o32, db, twins, seqs, thr=-1e30, rows=False)
+
+
+def test_plan7_profiles_with_real_hits(pkg, o32):
+    """Pfam-shaped profiles, frameshifted coding reads drawn from them: real hits, long D/I stretches."""
+    rng = np.random.default_rng(42)
+    db = pkg.Db(0)
+    twins, models = [], []
+    for i, M in enumerate((200, 64, 150, 37)):
+        nl, ma, tr = plan7_profile_inputs(rng, M)
+        p = pkg.ProteinProfile.from_model(nl, ma, tr, pkg.protein_cfg(pkg.ENTRY_DIST_OCCUPANCY, 0.01), "PL%d" % i)
+        db.add(p)
+        twins.append(oracle_twin(o32, p, 0.01))
+        models.append(ma)
+    db.commit()
+    seqs = []
+    for i in range(12):
+        ma = models[i % 4]
+        seqs.append(sample_read(rng, ma, int(rng.integers(300, 900)), 0.02, 0.01))
+    seqs.append(random_seq(rng, 500))
+    res, ref = check_scan(pkg, o32, db, twins, seqs, thr=10.0, flavour=1)
+    assert 6 <= res.nhits < len(seqs) * 4  # the planted reads hit, random pairs do not
+
+
+def test_multiple_hits_per_read(pkg, o32):
+    """multi_hits: two copies of a domain in one read must go through J."""
+    rng = np.random.default_rng(3)
+    nl, ma, tr = plan7_profile_inputs(rng, 50)
+    p = pkg.ProteinProfile.from_model(nl, ma, tr, pkg.protein_cfg(pkg.ENTRY_DIST_OCCUPANCY, 0.01), "TWICE")
+    db = pkg.Db(0)
+    db.add(p)
+    db.commit()
+    tw = [oracle_twin(o32, p, 0.01)]
+    read = sample_read(rng, ma, 150, 0.0, 0.0) + random_seq(rng, 40) + sample_read(rng, ma, 150, 0.01, 0.0)
+    res, ref = check_scan(pkg, o32, db, tw, [read], thr=10.0)
+    _, _, path = res.hit_at(0)
+    assert any(st == pkg.PROTEIN_J_STATE for st, _ in path)
+    res2, _ = check_scan(pkg, o32, db, tw, [read], multi_hits=False, thr=10.0)
+    assert not any(st == pkg.PROTEIN_J_STATE for st, _ in res2.hit_at(0)[2])
+
+
+def test_scores_only_and_resident_path(pkg, o32):
+    db, twins = make_db(pkg, o32, [(1, 40, 2), (2, 70, 2)], 0.01)
+    rng = np.random.default_rng(9)
+    seqs = [random_seq(rng, n) for n in (100, 333)]
+    staged = db.stage(seqs)
+    a = db.scan_resident(staged, lrt_threshold=-1e30, want_paths=False)
+    b = db.scan(seqs, lrt_threshold=-1e30, want_paths=True)
+    assert np.array_equal(a.alt_loglik, b.alt_loglik) and np.array_equal(a.null_loglik, b.null_loglik)
+    assert a.nhits == 4 and a.hit_at(0)[2] == []
+    t = b.timing
+    assert t.launches >= 5 and t.alt_cells == (40 + 70) * 433 and t.score_ms > 0
+
+
+def test_error_paths(pkg, o32):
+    db, _ = make_db(pkg, o32, [(1, 5, 2)], 0.01)
+    with pytest.raises(pkg.DcpError) as e:
+        db.scan(["ACGT", ""])
+    assert e.value.rc == pkg.RC_EINVAL  # protein_profile_setup(L=0) -> RC_EINVAL
+    with pytest.raises(pkg.DcpError) as e:
+        db.scan(["ACGN"])
+    assert e.value.rc == pkg.RC_EINVAL
+    with pytest.raises(pkg.DcpError):
+        db.add(pkg.ProteinProfile.sample(1, 5))  # already committed
+    db2 = pkg.Db(0)
+    db2.add(pkg.ProteinProfile.sample(1, 5, pkg.protein_cfg(2, 0.01)))
+    with pytest.raises(pkg.DcpError):
+        db2.add(pkg.ProteinProfile.sample(2, 5, pkg.protein_cfg(2, 0.02)))  # one epsilon per db
+
+
+def test_deterministic_across_runs(pkg, o32):
+    db, _ = make_db(pkg, o32, [(s, 100 + s, 2) for s in range(1, 9)], 0.01)
+    rng = np.random.default_rng(2)
+    seqs = [random_seq(rng, int(n)) for n in rng.integers(50, 400, 64)]
+    a = db.scan(seqs, lrt_threshold=-1e30)
+    b = db.scan(seqs, lrt_threshold=-1e30)
+    assert np.array_equal(a.alt_loglik, b.alt_loglik)
+    assert [a.hit_at(i) for i in range(0, a.nhits, 37)] == [b.hit_at(i) for i in range(0, b.nhits, 37)]

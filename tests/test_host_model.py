@@ -1,0 +1,154 @@
+"""Host model layer of libdcpgpu.so (C) against the oracle: tables, entry distribution, specials,
+decode, state names, the C-ABI export list.  No GPU needed."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import orc
+from common import GOLD, SEQ32, oracle_twin, plan7_profile_inputs
+
+EPS_01F = float(np.float32(0.1))
+
+
+def ulp_diff(a, b):
+    a = np.ascontiguousarray(a, np.float32).view(np.int32).astype(np.int64)
+    b = np.ascontiguousarray(b, np.float32).view(np.int32).astype(np.int64)
+    return np.abs(a - b)
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    lib = pkg.lib()
+    import re, os
+    hdr = open(os.path.join(os.path.dirname(pkg.__file__), "..", "include", "dcpgpu.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b((?:dcpgpu|protein|xmath)_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"protein_cfg"}
+    assert declared == set(pkg.EXPORTS)
+    for s in declared:
+        assert hasattr(lib, s), s
+
+
+@pytest.mark.parametrize("entry", [1, 2])
+@pytest.mark.parametrize("seed,M,eps", [(1, 2, EPS_01F), (2, 5, 0.01), (3, 17, 0.01), (4, 64, EPS_01F)])
+def test_sampled_profile_tables_match_oracle(pkg, o32, seed, M, eps, entry):
+    p = pkg.ProteinProfile.sample(seed, M, pkg.protein_cfg(entry, eps))
+    q = o32.sample(seed, M, entry, float(np.float32(eps)))
+    assert p.core_size == M
+    assert np.array_equal(p.trans, q.trans)
+    # tables: product sums probabilities, oracle sums in the log domain; both round once to fp32
+    for a, b in ((p.match_emission, q.emM), (p.insert_emission, q.emI), (p.null_emission, q.emN)):
+        fin = np.isfinite(b)
+        assert np.array_equal(np.isfinite(a), fin)
+        d = ulp_diff(a[fin], b[fin])
+        assert d.max() <= 1 and (d > 0).mean() < 1e-3
+    d = ulp_diff(p.entry, q.entry)
+    assert d.max() <= 1
+    for which in (-2, -1, 0, M - 1):
+        assert np.allclose(p.nuclt_dist(which), q.ndist(which), rtol=1e-12, atol=1e-12)
+
+
+def test_model_api_equals_sampler_and_oracle_build(pkg, o32):
+    nl, ma, tr = o32.sample_inputs(9, 12)
+    cfg = pkg.protein_cfg(pkg.ENTRY_DIST_OCCUPANCY, 0.01)
+    a = pkg.ProteinProfile.from_model(nl, ma, tr, cfg)
+    b = pkg.ProteinProfile.sample(9, 12, cfg)
+    assert np.array_equal(a.match_emission, b.match_emission) and np.array_equal(a.entry, b.entry)
+    q = o32.build(12, 2, float(np.float32(0.01)), nl, ma, tr)
+    assert ulp_diff(a.match_emission, q.emM).max() <= 1
+
+
+def test_model_error_paths(pkg):
+    L = pkg.lib()
+    cfg = pkg.protein_cfg()
+    nl = np.zeros(20, np.float32)
+    m = L.protein_model_new(cfg, nl.ctypes.data)
+    assert L.protein_model_add_node(m, nl.ctypes.data, b"-") == pkg.RC_EFAIL  # setup not called
+    assert L.protein_model_setup(m, 0) == pkg.RC_EINVAL
+    assert L.protein_model_setup(m, 4097) == pkg.RC_EINVAL
+    assert L.protein_model_setup(m, 1) == pkg.RC_OK
+    assert L.protein_model_add_node(m, nl.ctypes.data, b"-") == pkg.RC_OK
+    assert L.protein_model_add_node(m, nl.ctypes.data, b"-") == pkg.RC_EFAIL  # reached limit of nodes
+    L.protein_model_del(m)
+
+
+def test_profile_setup_specials(pkg, o32):
+    p = pkg.ProteinProfile.sample(1, 2)
+    rc, _ = p.setup(0)
+    assert rc == pkg.RC_EINVAL  # test/protein_profile.c:31
+    for L in (1, 2, 32, 150, 1000, 1053, 10000, 100003):
+        for mh in (True, False):
+            for h3 in (True, False):
+                rc, x = p.setup(L, mh, h3)
+                rc2, y = o32.specials(L, mh, h3)
+                assert rc == 0 and rc2 == 0
+                assert np.array_equal(x, y, equal_nan=True), (L, mh, h3, x, y)
+
+
+def test_decode_and_names(pkg, o32):
+    cfg = pkg.protein_cfg(pkg.ENTRY_DIST_UNIFORM, EPS_01F)
+    p = pkg.ProteinProfile.sample(1, 2, cfg)
+    q = o32.sample(1, 2, 1, EPS_01F)
+    rng = np.random.default_rng(0)
+    for st in (pkg.PROTEIN_N_STATE, pkg.PROTEIN_J_STATE, pkg.PROTEIN_C_STATE, pkg.PROTEIN_R_STATE, 1, 2, (1 << 14) | 1):
+        for n in range(1, 6):
+            for _ in range(12):
+                frag = "".join("ACGT"[i] for i in rng.integers(0, 4, n))
+                assert p.decode(frag, st) == q.decode(st, frag)
+    assert p.decode("ACGTAC", 1)[0] == pkg.RC_EINVAL
+    assert p.decode("ACN", 1)[0] == pkg.RC_EINVAL
+    assert p.decode("ACG", pkg.PROTEIN_B_STATE)[0] == pkg.RC_EINVAL
+    for sid in [0xC000 + i for i in range(8)] + [1, 37, 4096, (1 << 14) | 12, (2 << 14) | 255]:
+        assert pkg.protein_state_name(sid) == o32.state_name(sid)
+    assert pkg.protein_state_name(pkg.PROTEIN_R_STATE) == "R" and pkg.protein_state_name(2) == "M2"
+    assert pkg.protein_state_is_mute(pkg.PROTEIN_S_STATE) and pkg.protein_state_is_mute((2 << 14) | 3)
+    assert not pkg.protein_state_is_mute(pkg.PROTEIN_N_STATE) and not pkg.protein_state_is_mute(5)
+
+
+def test_codec_reproduces_reference_codons(pkg, o32):
+    """protein_codec_next over the oracle's golden path with the PRODUCT's decode (test/protein_profile.c:83-102)."""
+    cfg = pkg.protein_cfg(pkg.ENTRY_DIST_UNIFORM, EPS_01F)
+    p = pkg.ProteinProfile.sample(1, 2, cfg)
+    rc, _, path = oracle_twin(o32, p, EPS_01F).viterbi_alt(SEQ32)
+    pos, cods = 0, []
+    for st, ln in path:
+        if not pkg.protein_state_is_mute(st):
+            rc, cod, _ = p.decode(SEQ32[pos:pos + ln], st)
+            assert rc == 0
+            cods.append(cod)
+            pos += ln
+    assert cods == GOLD["codons"]
+
+
+def test_lrt(pkg):
+    assert pkg.xmath_lrt(-48.0, -40.0) == 16.0
+    assert pkg.xmath_lrt(np.float32(-48.927269), np.float32(-55.594276)) == np.float32(-2) * (
+        np.float32(-48.927269) - np.float32(-55.594276))
+
+
+def test_shard_profiles(pkg):
+    rng = np.random.default_rng(3)
+    sizes = np.clip(np.exp(rng.normal(np.log(130), 0.7, 5000)), 50, 2000).astype(np.uint32)
+    for n in (1, 2, 4, 8):
+        sh = pkg.shard_profiles(sizes, n)
+        loads = np.bincount(sh, weights=sizes, minlength=n)
+        assert sh.max() < n and loads.max() - loads.min() <= sizes.max()
+    with pytest.raises(pkg.DcpError):
+        pkg.shard_profiles(sizes, 0)
+
+
+def test_no_cpu_fallback(pkg):
+    """Without a CUDA device the engine refuses to exist (there is no CPU path to fall back to)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(pkg.DcpError) as e:
+        pkg.Db(0)
+    assert e.value.rc == pkg.RC_EFAIL
+
+
+def test_plan7_inputs_build(pkg, o32):
+    rng = np.random.default_rng(1)
+    nl, ma, tr = plan7_profile_inputs(rng, 40)
+    p = pkg.ProteinProfile.from_model(nl, ma, tr)
+    assert np.isfinite(p.entry).all() and abs(np.exp(p.entry.astype(np.float64)) @ np.arange(40, 0, -1) - 1) < 1e-5

@@ -1,0 +1,140 @@
+"""The oracle against every golden vector the reference's runnable tests hold for this path
+(test/protein_profile.c), plus self-consistency of its two flavours and a brute-force check."""
+import itertools
+
+import numpy as np
+import pytest
+
+import orc
+from common import GOLD, SEQ32, SEQ1053, random_seq
+
+EPS_01F = float(np.float32(0.1))  # the test passes the literal 0.1f (test/protein_profile.c:22)
+
+
+@pytest.mark.parametrize("entry,key", [(orc.ENTRY_UNIFORM, "uniform"), (orc.ENTRY_OCCUPANCY, "occupancy")])
+def test_reference_goldens_double(o64, entry, key):
+    g = GOLD[key]
+    p = o64.sample(GOLD["seed"], GOLD["core_size"], entry, EPS_01F)
+    rc, null_ll, null_path = p.viterbi_null(SEQ32)
+    assert rc == 0
+    assert abs(null_ll - g["null_loglik"]) <= 1e-9 * abs(g["null_loglik"])  # hope CLOSE, double: 1e-09
+    assert len(null_path) == g["null_nsteps"]
+    assert null_path[0] == (orc.ST_R, 3) and null_path[-1] == (orc.ST_R, 2)  # :43-54
+    rc, alt_ll, path = p.viterbi_alt(SEQ32)
+    assert rc == 0
+    assert abs(alt_ll - g["alt_loglik"]) <= 1e-9 * abs(g["alt_loglik"])
+    assert len(path) == g["alt_nsteps"]
+    assert path[0] == (orc.ST_S, 0) and path[-1] == (orc.ST_T, 0)  # :67-77
+    assert o64.state_name(path[0][0]) == "S" and o64.state_name(path[-1][0]) == "T"
+    # protein_codec_next over the path (:83-102): ten codons
+    pos, cods = 0, []
+    for st, ln in path:
+        if ln:
+            rc, cod, _ = p.decode(st, SEQ32[pos:pos + ln])
+            assert rc == 0
+            cods.append(cod)
+            pos += ln
+    assert cods == GOLD["codons"] and pos == len(SEQ32)
+
+
+@pytest.mark.parametrize("entry,key", [(orc.ENTRY_UNIFORM, "uniform"), (orc.ENTRY_OCCUPANCY, "occupancy")])
+def test_reference_goldens_float(o32, entry, key):
+    g = GOLD[key]
+    p = o32.sample(GOLD["seed"], GOLD["core_size"], entry, EPS_01F)
+    rc, null_ll, null_path = p.viterbi_null(SEQ32)
+    rc2, alt_ll, path = p.viterbi_alt(SEQ32)
+    assert rc == 0 and rc2 == 0
+    assert abs(null_ll - g["null_loglik"]) <= 5e-5 * abs(g["null_loglik"])  # hope CLOSE, float: 5e-05
+    assert abs(alt_ll - g["alt_loglik"]) <= 5e-5 * abs(g["alt_loglik"])
+    assert len(null_path) == 11 and len(path) == 14
+
+
+def test_setup_rejects_empty_sequence(o32):
+    rc, _ = o32.specials(0)
+    assert rc == 3  # RC_EINVAL, test/protein_profile.c:31
+
+
+def test_frame_tables_are_distributions(o64):
+    """Sum over all 1364 strings of exp(e) = 1 and per-length masses follow the epsilon polynomial."""
+    for eps in (EPS_01F, 0.01):
+        p = o64.sample(3, 3, orc.ENTRY_OCCUPANCY, eps)
+        e = eps
+        f = 1 - e
+        want = [e * e * f * f, 2 * e * f ** 3 + 2 * e ** 3 * f, f ** 4 + 4 * e * e * f * f + e ** 4]
+        want = want + [want[1], want[0]]
+        for tab in [p.emN, p.emI] + list(p.emM):
+            pr = np.exp(tab)
+            assert abs(pr.sum() - 1) < 1e-9
+            offs = [0, 4, 20, 84, 340, 1364]
+            for n in range(5):
+                assert abs(pr[offs[n]:offs[n + 1]].sum() - want[n]) < 1e-9
+
+
+@pytest.mark.parametrize("dbl", [False, True])
+def test_generic_equals_specialised(dbl, o32, o64):
+    """imm-shaped interpreter vs the hard-coded recurrence: bit-equal scores."""
+    o = o64 if dbl else o32
+    rng = np.random.default_rng(5)
+    for seed, M, L, entry, mh, h3 in [(1, 2, 4, 1, True, False), (2, 3, 9, 2, False, False), (3, 5, 17, 2, True, True),
+                                      (4, 8, 30, 1, False, True), (5, 17, 64, 2, True, False), (6, 33, 120, 2, True, False)]:
+        p = o.sample(seed, M, entry, 0.01)
+        s = random_seq(rng, L)
+        rc, nl, _ = p.viterbi_null(s, mh, h3)
+        rc2, al, path = p.viterbi_alt(s, mh, h3)
+        rc3, nf, af = p.scores_fast(s, mh, h3)
+        assert rc == rc2 == rc3 == 0
+        assert nl == nf and al == af
+        assert sum(l for _, l in path) == L and path[0][0] == orc.ST_S and path[-1][0] == orc.ST_T
+
+
+def test_bruteforce_tiny(o64):
+    """Enumerate every state path of a tiny model and compare the best score with Viterbi."""
+    M, L = 2, 5
+    p = o64.sample(11, M, orc.ENTRY_OCCUPANCY, 0.05)
+    seq = "ACGTA"
+    rc, x = o64.specials(L, True, False)
+    NN, CC, JJ, NB, CT, JB, RR, EJ, EC, ET, ECC, EB, EJJ = [float(v) for v in x]
+    tr, ent = p.trans, p.entry
+    emM, emI, emN = p.emM, p.emI, p.emN
+    off = [0, 0, 4, 20, 84, 340]
+
+    def code(frag):
+        v = 0
+        for ch in frag:
+            v = v * 4 + "ACGT".index(ch)
+        return off[len(frag)] + v
+
+    # graph: state -> list of (next, score); emitting states consume 1..5
+    edges = {"S": [("N", NN), ("B", NB)], "N": [("N", NN), ("B", NB)], "E": [("T", ET), ("C", ECC), ("B", EB), ("J", EJJ)],
+             "C": [("C", CC), ("T", CT)], "J": [("J", JJ), ("B", JB)], "B": [("M1", ent[0]), ("M2", ent[1])],
+             "M1": [("I1", tr[1][1]), ("M2", tr[1][0]), ("D2", tr[1][2]), ("E", 0.0)], "I1": [("I1", tr[1][4]), ("M2", tr[1][3])],
+             "M2": [("E", 0.0)], "D2": [("E", 0.0)], "T": []}
+    table = {"N": emN, "C": emN, "J": emN, "M1": emM[0], "M2": emM[1], "I1": emI}
+    best = [-np.inf]
+
+    def walk(state, pos, score, depth):
+        if depth > 14 or score == -np.inf:
+            return
+        if state == "T":
+            if pos == L:
+                best[0] = max(best[0], score)
+            return
+        for nxt, t in edges[state]:
+            if nxt in table:
+                for l in range(1, 6):
+                    if pos + l <= L:
+                        walk(nxt, pos + l, score + t + table[nxt][code(seq[pos:pos + l])], depth + 1)
+            else:
+                walk(nxt, pos, score + t, depth + 1)
+
+    walk("S", 0, 0.0, 0)
+    rc, al, _ = p.viterbi_alt(seq)
+    assert rc == 0 and abs(al - best[0]) < 1e-9
+
+
+def test_long_sequence_runs(o32):
+    p = o32.sample(7, 40, orc.ENTRY_OCCUPANCY, 0.01)
+    rc, al, path = p.viterbi_alt(SEQ1053)
+    rc2, nf, af = p.scores_fast(SEQ1053)
+    assert rc == 0 and rc2 == 0 and al == af
+    assert sum(l for _, l in path) == 1053
