@@ -23,7 +23,7 @@ PROTEIN_E_STATE, PROTEIN_J_STATE, PROTEIN_C_STATE, PROTEIN_T_STATE = 0xC004, 0xC
 # every symbol include/dcpgpu.h declares
 EXPORTS = [
     "protein_model_new", "protein_model_setup", "protein_model_add_node", "protein_model_add_trans",
-    "protein_model_del", "protein_profile_new", "protein_profile_absorb", "protein_profile_sample",
+    "protein_model_del", "protein_profile_new", "protein_profile_absorb", "protein_profile_sample", "protein_profile_build",
     "protein_profile_setup", "protein_profile_decode", "protein_profile_del", "protein_profile_core_size",
     "protein_profile_accession", "protein_profile_match_emission", "protein_profile_insert_emission",
     "protein_profile_null_emission", "protein_profile_trans", "protein_profile_entry",
@@ -33,7 +33,7 @@ EXPORTS = [
     "dcpgpu_result_nseqs", "dcpgpu_result_nprofiles", "dcpgpu_result_null_loglik", "dcpgpu_result_alt_loglik",
     "dcpgpu_result_hit", "dcpgpu_result_nhits", "dcpgpu_result_hit_at", "dcpgpu_result_timing",
     "dcpgpu_result_del", "dcpgpu_shard_profiles", "dcpgpu_prod_fwrite_header", "dcpgpu_prod_fwrite",
-    "dcpgpu_prod_row", "dcpgpu_last_error",
+    "dcpgpu_prod_row", "dcpgpu_microbench_alu", "dcpgpu_last_error",
 ]
 
 
@@ -88,6 +88,7 @@ def lib():
     L.protein_profile_new.argtypes = [C.c_char_p, _Cfg]
     L.protein_profile_absorb.argtypes = [vp, vp]
     L.protein_profile_sample.argtypes = [vp, u, u]
+    L.protein_profile_build.argtypes = [vp, u, vp, vp, vp, C.c_char_p]
     L.protein_profile_setup.argtypes = [vp, u, C.c_bool, C.c_bool, vp]
     L.protein_profile_decode.argtypes = [vp, C.c_char_p, u, u, C.c_char_p, C.c_char_p]
     L.protein_profile_del.argtypes = [vp]
@@ -132,6 +133,7 @@ def lib():
     L.dcpgpu_shard_profiles.argtypes = [u, vp, u, vp]
     L.dcpgpu_prod_row.restype = C.c_long
     L.dcpgpu_prod_row.argtypes = [vp, vp, C.c_uint64, C.c_int64, C.c_int64, C.c_char_p, C.c_char_p, C.c_long]
+    L.dcpgpu_microbench_alu.argtypes = [i, vp]
     L.dcpgpu_last_error.restype = C.c_char_p
     _lib = L
     return L
@@ -158,6 +160,13 @@ def protein_state_is_mute(state_id):
 
 def xmath_lrt(null, alt):
     return lib().xmath_lrt_f32(null, alt)
+
+
+def microbench_alu(device=0):
+    """Measured FP32 issue peaks: dict of 1e9 lane-instructions/s for FADD, FMNMX3 and the DP-cell mix."""
+    out = np.zeros(4)
+    _check(lib().dcpgpu_microbench_alu(device, out.ctypes.data))
+    return {"fadd_ginst": out[0], "fmnmx3_ginst": out[1], "mix_ginst": out[2], "sms": int(out[3])}
 
 
 def shard_profiles(core_sizes, nshards):
@@ -213,6 +222,19 @@ class ProteinProfile:
             _check(L.protein_profile_absorb(p.h, m))
         finally:
             L.protein_model_del(m)
+        return p
+
+    @classmethod
+    def build(cls, null_lprobs, match_lprobs, trans, cfg=None, accession="accession", consensus=None):
+        """Same as from_model in one C call (releases the GIL; used to build large synthetic databases)."""
+        nl = np.ascontiguousarray(null_lprobs, np.float32)
+        ml = np.ascontiguousarray(match_lprobs, np.float32)
+        tr = np.ascontiguousarray(trans, np.float32)
+        M = ml.shape[0]
+        assert nl.shape == (20,) and ml.shape == (M, 20) and tr.shape == (M + 1, 7)
+        p = cls(accession, cfg)
+        _check(lib().protein_profile_build(p.h, M, nl.ctypes.data, ml.ctypes.data, tr.ctypes.data,
+                                           consensus.encode() if consensus else None))
         return p
 
     core_size = property(lambda s: lib().protein_profile_core_size(s.h))

@@ -151,29 +151,23 @@ static double frame_prob(struct frame_ctx const *fc, int const *z, int n)
         return fc->c3a * keep + fc->c3b * sub + fc->c3c * rare;
     }
     case 4: {
+        /* one inserted base i: codon = the other three; two inserted bases i<j plus one deletion */
+        static const unsigned char pair4[6][4] = {{0, 1, 2, 3}, {0, 2, 1, 3}, {0, 3, 1, 2},
+                                                  {1, 2, 0, 3}, {1, 3, 0, 2}, {2, 3, 0, 1}};
         double ins1 = B[z[0]] * MM_(z[1], z[2], z[3]) + B[z[1]] * MM_(z[0], z[2], z[3]) +
                       B[z[2]] * MM_(z[0], z[1], z[3]) + B[z[3]] * MM_(z[0], z[1], z[2]);
         double mix = 0.0;
-        for (int i = 0; i < 4; ++i)
-            for (int j = i + 1; j < 4; ++j)
-            {
-                int r[2], k = 0;
-                for (int q = 0; q < 4; ++q)
-                    if (q != i && q != j) r[k++] = z[q];
-                mix += B[z[i]] * B[z[j]] * fc->two[4 * r[0] + r[1]];
-            }
+        for (int q = 0; q < 6; ++q)
+            mix += B[z[pair4[q][0]]] * B[z[pair4[q][1]]] * fc->two[4 * z[pair4[q][2]] + z[pair4[q][3]]];
         return fc->c4a * ins1 + fc->c4b * mix;
     }
     default: {
+        static const unsigned char pair5[10][5] = {{0, 1, 2, 3, 4}, {0, 2, 1, 3, 4}, {0, 3, 1, 2, 4}, {0, 4, 1, 2, 3},
+                                                   {1, 2, 0, 3, 4}, {1, 3, 0, 2, 4}, {1, 4, 0, 2, 3}, {2, 3, 0, 1, 4},
+                                                   {2, 4, 0, 1, 3}, {3, 4, 0, 1, 2}};
         double ins2 = 0.0;
-        for (int i = 0; i < 5; ++i)
-            for (int j = i + 1; j < 5; ++j)
-            {
-                int r[3], k = 0;
-                for (int q = 0; q < 5; ++q)
-                    if (q != i && q != j) r[k++] = z[q];
-                ins2 += B[z[i]] * B[z[j]] * MM_(r[0], r[1], r[2]);
-            }
+        for (int q = 0; q < 10; ++q)
+            ins2 += B[z[pair5[q][0]]] * B[z[pair5[q][1]]] * MM_(z[pair5[q][2]], z[pair5[q][3]], z[pair5[q][4]]);
         return fc->c5 * ins2;
     }
     }
@@ -472,7 +466,6 @@ enum rc protein_profile_absorb(struct protein_profile *p, struct protein_model c
     double eps = (double)m->cfg.epsilon;
     dcp_frame_table(&p->null_ndist, eps, p->null_emission);
     dcp_frame_table(&p->insert_ndist, eps, p->insert_emission);
-#pragma omp parallel for schedule(dynamic, 4) if (n >= 32)
     for (unsigned k = 0; k < n; ++k)
         dcp_frame_table(&p->match_ndists[k], eps, p->match_emission + (size_t)k * DCP_FRAME_TABLE_SIZE);
     entry_distribution(m, p->entry);
@@ -509,6 +502,33 @@ enum rc protein_profile_sample(struct protein_profile *p, unsigned seed, unsigne
         struct protein_trans tr;
         for (int i = 0; i < PROTEIN_TRANS_SIZE; ++i) tr.data[i] = (float)(t[i] - z);
         rc = protein_model_add_trans(m, tr);
+    }
+    if (!rc) rc = protein_profile_absorb(p, m);
+    protein_model_del(m);
+    return rc;
+}
+
+/* The loop body of protein_h3reader_next (src/model/protein_h3reader.c:18-72) for arrays that are
+ * already in memory: trans[0], then per node (match lprobs, trans[k]); then absorb. */
+enum rc protein_profile_build(struct protein_profile *p, unsigned core_size,
+                              float const null_lprobs[DCP_AMINO_SIZE], float const *match_lprobs,
+                              float const *trans, char const *consensus)
+{
+    struct protein_model *m = protein_model_new(p->cfg, null_lprobs);
+    if (!m) return dcp_error(RC_ENOMEM, "alloc model");
+    enum rc rc = protein_model_setup(m, core_size);
+    struct protein_trans t;
+    if (!rc)
+    {
+        memcpy(t.data, trans, sizeof t.data);
+        rc = protein_model_add_trans(m, t);
+    }
+    for (unsigned k = 0; !rc && k < core_size; ++k)
+    {
+        rc = protein_model_add_node(m, match_lprobs + (size_t)k * DCP_AMINO_SIZE, consensus ? consensus[k] : '-');
+        if (rc) break;
+        memcpy(t.data, trans + (size_t)(k + 1) * PROTEIN_TRANS_SIZE, sizeof t.data);
+        rc = protein_model_add_trans(m, t);
     }
     if (!rc) rc = protein_profile_absorb(p, m);
     protein_model_del(m);

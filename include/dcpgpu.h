@@ -127,6 +127,12 @@ void protein_model_del(struct protein_model *);
 struct protein_profile *protein_profile_new(char const *accession, struct protein_cfg cfg);
 /* protein_profile_absorb (protein_profile.c:218-257): compiles the model into DP tables */
 enum rc protein_profile_absorb(struct protein_profile *, struct protein_model const *);
+/* protein_h3reader_next's loop body (src/model/protein_h3reader.c:18-72) over in-memory arrays:
+ * trans[0], then (match_lprobs[k], trans[k+1]) per node, then absorb.  match_lprobs: [core_size][20],
+ * trans: [core_size+1][7], consensus: core_size chars or NULL. */
+enum rc protein_profile_build(struct protein_profile *, unsigned core_size,
+                              float const null_lprobs[DCP_AMINO_SIZE], float const *match_lprobs,
+                              float const *trans, char const *consensus);
 /* protein_profile_sample (protein_profile.c:259-304): imm_rnd(seed) driven random profile */
 enum rc protein_profile_sample(struct protein_profile *, unsigned seed, unsigned core_size);
 /* protein_profile_setup (protein_profile.c:155-216): length-dependent special transitions.
@@ -247,6 +253,11 @@ enum rc dcpgpu_prod_fwrite(struct dcpgpu_result const *, struct dcpgpu_db const 
 /* Row for a single hit into a caller buffer; returns length or -1 if it does not fit. */
 long dcpgpu_prod_row(struct dcpgpu_result const *, struct dcpgpu_db const *, uint64_t hit,
                      int64_t scan_id, int64_t seq_id, char const *seq, char *out, long cap);
+
+/* Measured FP32 issue peaks of `device` (the roofline denominators of the score kernel):
+ * out[0] FADD, out[1] FMNMX3, out[2] the DP cell's 2:1 FADD:FMNMX3 mix, in 1e9 lane-instructions/s;
+ * out[3] = SM count. */
+enum rc dcpgpu_microbench_alu(int device, double out[4]);
 
 char const *dcpgpu_last_error(void); /* thread-local message of the last failure */
 
