@@ -37,30 +37,38 @@ namespace
 /* ----------------------------------------------------------------------------------------- */
 __constant__ uint32_t c_frame_off[6] = {0, 0, 4, 20, 84, 340};
 
+/* frame-table codes of the windows seq[j-l:j], l = 1..5 (0 where the window does not exist) */
+__device__ __forceinline__ void window_codes(const uint8_t *__restrict__ b, uint32_t j, uint32_t len,
+                                             uint32_t (&code)[5])
+{
+    uint32_t w = 0;
+#pragma unroll
+    for (int l = 1; l <= 5; ++l)
+    {
+        /* window grows to the left: seq[j-l] becomes the most significant base */
+        if (j >= (uint32_t)l && j <= len)
+        {
+            w |= (uint32_t)b[j - l] << (2 * (l - 1));
+            code[l - 1] = c_frame_off[l] + w;
+        }
+        else
+            code[l - 1] = 0; /* unused: Tin of a negative row is -inf */
+    }
+}
+
 __global__ void k_rows(const uint8_t *__restrict__ bases, const SeqMeta *__restrict__ seqs, uint32_t nseq,
                        const float *__restrict__ null_tabs, const float *__restrict__ ins_tab,
-                       uint32_t n_null, uint64_t total_rows, RowRec *__restrict__ rows)
+                       uint32_t n_null, uint64_t total_recs, RowRec *__restrict__ rows)
 {
     uint32_t s = blockIdx.x;
     if (s >= nseq) return;
     SeqMeta sm = seqs[s];
     const uint8_t *b = bases + sm.row_off;
-    for (uint32_t j = 1 + threadIdx.x; j <= sm.len; j += blockDim.x)
+    for (uint32_t j = threadIdx.x; j <= sm.len; j += blockDim.x)
     {
-        uint32_t code[5];
-        uint32_t w = 0;
-#pragma unroll
-        for (int l = 1; l <= 5; ++l)
-        {
-            /* window grows to the left: seq[j-l] becomes the most significant base */
-            if (j >= (uint32_t)l)
-            {
-                w |= (uint32_t)b[j - l] << (2 * (l - 1));
-                code[l - 1] = c_frame_off[l] + w;
-            }
-            else
-                code[l - 1] = 0; /* unused: Tin of a negative row is -inf */
-        }
+        uint32_t code[5], next[5];
+        window_codes(b, j, sm.len, code);
+        window_codes(b, j + 1, sm.len, next);
         for (uint32_t t = 0; t < n_null; ++t)
         {
             RowRec r;
@@ -69,16 +77,17 @@ __global__ void k_rows(const uint8_t *__restrict__ bases, const SeqMeta *__restr
             {
                 r.eN[l] = null_tabs[(size_t)t * kTab + code[l]];
                 r.eI[l] = ins_tab[code[l]];
-                r.code[l] = code[l];
+                r.code[l] = (uint16_t)code[l];
+                r.code_next[l] = (uint16_t)next[l];
             }
-            r.pad = 0;
-            rows[(size_t)t * total_rows + sm.row_off + (j - 1)] = r;
+            r.code[5] = r.code_next[5] = 0;
+            rows[(size_t)t * total_recs + sm.rec_off + j] = r;
         }
     }
 }
 
 /* imm_dp_viterbi on the null dp (scan_thread.c:115): V_R[j] = max_l Tin_R[j-l] + e_R(seq[j-l:j]) */
-__global__ void k_null(const SeqMeta *__restrict__ seqs, uint32_t nseq, uint32_t n_null, uint64_t total_rows,
+__global__ void k_null(const SeqMeta *__restrict__ seqs, uint32_t nseq, uint32_t n_null, uint64_t total_recs,
                        const RowRec *__restrict__ rows, const float *__restrict__ spec,
                        float *__restrict__ null_out)
 {
@@ -87,16 +96,15 @@ __global__ void k_null(const SeqMeta *__restrict__ seqs, uint32_t nseq, uint32_t
     uint32_t s = tid / n_null, t = tid % n_null;
     SeqMeta sm = seqs[s];
     const float RR = spec[(size_t)s * 16 + 6];
-    const RowRec *r = rows + (size_t)t * total_rows + sm.row_off;
+    const RowRec *r = rows + (size_t)t * total_recs + sm.rec_off;
     /* ring of Tin_R for the last five rows; Tin_R[0] = start lprob 0 */
     float tin[5] = {NEG_INF, NEG_INF, NEG_INF, NEG_INF, 0.0f};
     float v = NEG_INF;
     for (uint32_t j = 1; j <= sm.len; ++j)
     {
-        const float4 *q = reinterpret_cast<const float4 *>(r + (j - 1));
-        float4 a = __ldg(q);
-        float e5 = __ldg(reinterpret_cast<const float *>(q + 1));
-        v = fmaxf(fmaxf(fmaxf(tin[4] + a.x, tin[3] + a.y), fmaxf(tin[2] + a.z, tin[1] + a.w)), tin[0] + e5);
+        float e[5];
+        load_row_special(r + j, e);
+        v = fmaxf(fmaxf(fmaxf(tin[4] + e[0], tin[3] + e[1]), fmaxf(tin[2] + e[2], tin[1] + e[3])), tin[0] + e[4]);
         tin[0] = tin[1], tin[1] = tin[2], tin[2] = tin[3], tin[3] = tin[4];
         tin[4] = v + RR;
     }
@@ -106,35 +114,49 @@ __global__ void k_null(const SeqMeta *__restrict__ seqs, uint32_t nseq, uint32_t
 /* ----------------------------------------------------------------------------------------- */
 /* alt Viterbi, score pass                                                                   */
 /* ----------------------------------------------------------------------------------------- */
+/* loads in flight for the next row: match emissions, insert/special emissions, codes after that */
+template <int Q>
+struct RowState
+{
+    float em[5][Q];
+    float eI[5], eN[5];
+    uint32_t next[5];
+};
+
 /*
  * One DP row.  R = ring slot this row writes ((j-1) % 5); the slot holding row j-l is
  * (R - l + 5) % 5, so slot R still holds row j-5 while it is read.
  * Lanes 0,1,2 also carry the N, J, C special states (tx ring); cE/cX are their lane-specific
  * E->X and X->X scores.  Returns E[j] and this lane's V_X[j].
+ *
+ * Software pipeline: `rs` arrives holding row j's emissions (issued one row earlier); as soon as
+ * they are consumed the loads of row j+1 are issued into the same registers, so their L1/L2
+ * latency is covered by the D chain, the specials and the Tin updates of row j.
  */
 template <int Q, int R>
 __device__ __forceinline__ void score_row(float (&tm)[5][Q], float (&ti)[5][Q], float (&tx)[5],
-                                          const NodeParams<Q> &p, const float *__restrict__ emis_lane,
-                                          const RowRec *__restrict__ rec, int lane, float NB, float JB,
+                                          const NodeParams<Q> &p, RowState<Q> &rs,
+                                          const float *__restrict__ emis_lane,
+                                          const RowRec *__restrict__ rec_next, int lane, float NB, float JB,
                                           float EB, float cE, float cX, float &E_out, float &vx_out)
 {
     constexpr int S1 = (R + 4) % 5, S2 = (R + 3) % 5, S3 = (R + 2) % 5, S4 = (R + 1) % 5, S5 = R;
-    RowIn in = load_row(rec);
-    float em[5][Q];
-    load_emis<Q>(em, emis_lane, in.code);
 
     float vm[Q], vi[Q];
 #pragma unroll
     for (int i = 0; i < Q; ++i)
-    {
-        vm[i] = fmaxf(max3(tm[S1][i] + em[0][i], tm[S2][i] + em[1][i], tm[S3][i] + em[2][i]),
-                      fmaxf(tm[S4][i] + em[3][i], tm[S5][i] + em[4][i]));
-        vi[i] = fmaxf(max3(ti[S1][i] + in.eI[0], ti[S2][i] + in.eI[1], ti[S3][i] + in.eI[2]),
-                      fmaxf(ti[S4][i] + in.eI[3], ti[S5][i] + in.eI[4]));
-    }
+        vm[i] = fmaxf(max3(tm[S1][i] + rs.em[0][i], tm[S2][i] + rs.em[1][i], tm[S3][i] + rs.em[2][i]),
+                      fmaxf(tm[S4][i] + rs.em[3][i], tm[S5][i] + rs.em[4][i]));
+#pragma unroll
+    for (int i = 0; i < Q; ++i)
+        vi[i] = fmaxf(max3(ti[S1][i] + rs.eI[0], ti[S2][i] + rs.eI[1], ti[S3][i] + rs.eI[2]),
+                      fmaxf(ti[S4][i] + rs.eI[3], ti[S5][i] + rs.eI[4]));
     /* special state carried by this lane */
-    float vx = fmaxf(max3(tx[S1] + in.eN[0], tx[S2] + in.eN[1], tx[S3] + in.eN[2]),
-                     fmaxf(tx[S4] + in.eN[3], tx[S5] + in.eN[4]));
+    float vx = fmaxf(max3(tx[S1] + rs.eN[0], tx[S2] + rs.eN[1], tx[S3] + rs.eN[2]),
+                     fmaxf(tx[S4] + rs.eN[3], tx[S5] + rs.eN[4]));
+
+    /* issue row j+1, part 1: the 4- and 5-nt lines (256 and 1024 codes: the likely L1 misses) */
+    load_emis_part<Q, 3, 5>(rs.em, emis_lane, rs.next);
 
     /* E[j]: every M_k -> E is 0 and D_k <= max V_M because MD, DD <= 0 (checked at commit) */
     float eloc = vm[0];
@@ -169,6 +191,11 @@ __device__ __forceinline__ void score_row(float (&tm)[5][Q], float (&ti)[5][Q], 
         if (!__any_sync(FULL, d[Q - 1] > old)) break;
     }
 
+    /* issue row j+1, part 2: the short lines (L1 resident) and the row record */
+    load_emis_part<Q, 0, 3>(rs.em, emis_lane, rs.next);
+    load_row_common(rec_next, rs.eI, rs.next);
+    if (lane < 3) load_row_special(rec_next, rs.eN);
+
     /* B[j] = max(V_N + NB, V_J + JB, E + (EJ+JB)) */
     float vN = __shfl_sync(FULL, vx, 0);
     float vJ = __shfl_sync(FULL, vx, 1);
@@ -188,9 +215,10 @@ __device__ __forceinline__ void score_row(float (&tm)[5][Q], float (&ti)[5][Q], 
     vx_out = vx;
 }
 
+/* recs = record of row 0 of this sequence (L+1 records) */
 template <int Q>
 __device__ __forceinline__ float score_pair(const NodeParams<Q> &p, const float *__restrict__ emis_lane,
-                                            const RowRec *__restrict__ rows, uint32_t L,
+                                            const RowRec *__restrict__ recs, uint32_t L,
                                             const float *__restrict__ sp, int lane)
 {
     const float NN = sp[0], CC = sp[1], JJ = sp[2], NB = sp[3], CT = sp[4], JB = sp[5];
@@ -211,20 +239,31 @@ __device__ __forceinline__ float score_pair(const NodeParams<Q> &p, const float 
     for (int i = 0; i < Q; ++i) tm[4][i] = NB + p.ent[i];
     tx[4] = lane == 0 ? NN : NEG_INF;
 
+    /* pipeline prologue: row 1's loads */
+    RowState<Q> rs;
+#pragma unroll
+    for (int l = 0; l < 5; ++l) rs.eN[l] = NEG_INF;
+    load_row_common(recs, rs.eI, rs.next); /* record 0: codes of row 1 */
+    load_emis<Q>(rs.em, emis_lane, rs.next);
+    load_row_common(recs + 1, rs.eI, rs.next);
+    if (lane < 3) load_row_special(recs + 1, rs.eN);
+
     float E = NEG_INF, vx = NEG_INF;
     uint32_t j = 1;
+#define NEXT(jj) (recs + min((uint32_t)(jj) + 1u, L))
     for (; j + 4 <= L; j += 5)
     {
-        score_row<Q, 0>(tm, ti, tx, p, emis_lane, rows + (j - 1), lane, NB, JB, EB, cE, cX, E, vx);
-        score_row<Q, 1>(tm, ti, tx, p, emis_lane, rows + j, lane, NB, JB, EB, cE, cX, E, vx);
-        score_row<Q, 2>(tm, ti, tx, p, emis_lane, rows + (j + 1), lane, NB, JB, EB, cE, cX, E, vx);
-        score_row<Q, 3>(tm, ti, tx, p, emis_lane, rows + (j + 2), lane, NB, JB, EB, cE, cX, E, vx);
-        score_row<Q, 4>(tm, ti, tx, p, emis_lane, rows + (j + 3), lane, NB, JB, EB, cE, cX, E, vx);
+        score_row<Q, 0>(tm, ti, tx, p, rs, emis_lane, NEXT(j), lane, NB, JB, EB, cE, cX, E, vx);
+        score_row<Q, 1>(tm, ti, tx, p, rs, emis_lane, NEXT(j + 1), lane, NB, JB, EB, cE, cX, E, vx);
+        score_row<Q, 2>(tm, ti, tx, p, rs, emis_lane, NEXT(j + 2), lane, NB, JB, EB, cE, cX, E, vx);
+        score_row<Q, 3>(tm, ti, tx, p, rs, emis_lane, NEXT(j + 3), lane, NB, JB, EB, cE, cX, E, vx);
+        score_row<Q, 4>(tm, ti, tx, p, rs, emis_lane, NEXT(j + 4), lane, NB, JB, EB, cE, cX, E, vx);
     }
-    if (j <= L) score_row<Q, 0>(tm, ti, tx, p, emis_lane, rows + (j - 1), lane, NB, JB, EB, cE, cX, E, vx);
-    if (j + 1 <= L) score_row<Q, 1>(tm, ti, tx, p, emis_lane, rows + j, lane, NB, JB, EB, cE, cX, E, vx);
-    if (j + 2 <= L) score_row<Q, 2>(tm, ti, tx, p, emis_lane, rows + (j + 1), lane, NB, JB, EB, cE, cX, E, vx);
-    if (j + 3 <= L) score_row<Q, 3>(tm, ti, tx, p, emis_lane, rows + (j + 2), lane, NB, JB, EB, cE, cX, E, vx);
+    if (j <= L) score_row<Q, 0>(tm, ti, tx, p, rs, emis_lane, NEXT(j), lane, NB, JB, EB, cE, cX, E, vx);
+    if (j + 1 <= L) score_row<Q, 1>(tm, ti, tx, p, rs, emis_lane, NEXT(j + 1), lane, NB, JB, EB, cE, cX, E, vx);
+    if (j + 2 <= L) score_row<Q, 2>(tm, ti, tx, p, rs, emis_lane, NEXT(j + 2), lane, NB, JB, EB, cE, cX, E, vx);
+    if (j + 3 <= L) score_row<Q, 3>(tm, ti, tx, p, rs, emis_lane, NEXT(j + 3), lane, NB, JB, EB, cE, cX, E, vx);
+#undef NEXT
     /* T[L] = max(E[L] + (EC+CT), V_C[L] + CT); V_C lives in lane 2 */
     float vC = __shfl_sync(FULL, vx, 2);
     return fmaxf(E + ET, vC + CT);
@@ -234,10 +273,9 @@ template <int Q>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 1)
 k_score(const float *__restrict__ emis, const float *__restrict__ trans, const ProfMeta *__restrict__ metas,
         const uint32_t *__restrict__ class_profs, uint32_t n_class_profs, const SeqMeta *__restrict__ seqs,
-        uint32_t nseq, uint64_t total_rows, const RowRec *__restrict__ rows, const float *__restrict__ spec,
+        uint32_t nseq, uint64_t total_recs, const RowRec *__restrict__ rows, const float *__restrict__ spec,
         float *__restrict__ alt_out, uint32_t nprof, unsigned long long *__restrict__ counter)
 {
-    constexpr int QP = Q <= 4 ? 4 : 8;
     const int lane = threadIdx.x & 31;
     const uint32_t nchunks = (nseq + kSeqChunk - 1) / kSeqChunk;
     const unsigned long long n_items = (unsigned long long)n_class_profs * nchunks;
@@ -252,13 +290,13 @@ k_score(const float *__restrict__ emis, const float *__restrict__ trans, const P
         ProfMeta pm = metas[prof];
         NodeParams<Q> p;
         load_params<Q>(p, trans + pm.trans_off, lane);
-        const float *emis_lane = emis + pm.emis_off + lane * QP;
-        const RowRec *rows_t = rows + (size_t)pm.null_id * total_rows;
+        const float *emis_lane = emis + pm.emis_off + lane * 4;
+        const RowRec *rows_t = rows + (size_t)pm.null_id * total_recs;
         uint32_t s_end = min(nseq, (ci + 1) * kSeqChunk);
         for (uint32_t s = ci * kSeqChunk; s < s_end; ++s)
         {
             SeqMeta sm = seqs[s];
-            float T = score_pair<Q>(p, emis_lane, rows_t + sm.row_off, sm.len, spec + (size_t)s * 16, lane);
+            float T = score_pair<Q>(p, emis_lane, rows_t + sm.rec_off, sm.len, spec + (size_t)s * 16, lane);
             if (lane == 0) alt_out[(size_t)s * nprof + prof] = T;
         }
     }
@@ -437,7 +475,9 @@ extern "C" enum rc dcpgpu_db_commit(struct dcpgpu_db *db)
         {
             uint32_t lane = k / m.Q, sub = k % m.Q;
             const float *src = p->match_emission + (size_t)k * kTab;
-            for (int c = 0; c < kTab; ++c) stage[(size_t)c * ROW + lane * m.QP + sub] = src[c];
+            /* [code][half][lane][4]: node k = lane*Q + sub sits in half sub/4 at float sub%4 */
+            const size_t at = (size_t)(sub / 4) * 128 + (size_t)lane * 4 + (sub % 4);
+            for (int c = 0; c < kTab; ++c) stage[(size_t)c * ROW + at] = src[c];
         }
         CU_TRY(cudaMemcpyAsync(db->d_emis + m.emis_off, stage, (size_t)kTab * ROW * sizeof(float),
                                cudaMemcpyHostToDevice, db->stream));
@@ -516,6 +556,7 @@ extern "C" enum rc dcpgpu_seqs_new(struct dcpgpu_seqs **out, struct dcpgpu_db *d
             return dcp_error(RC_EINVAL, "sequence cannot be empty"); /* protein_profile.c:158 */
         }
         sq->metas[i].len = lens[i], sq->metas[i].pad = 0, sq->metas[i].row_off = total;
+        sq->metas[i].rec_off = total + i; /* L+1 records per sequence */
         total += lens[i];
     }
     sq->total = total;
@@ -623,7 +664,8 @@ extern "C" enum rc dcpgpu_scan_resident(struct dcpgpu_db *db, struct dcpgpu_seqs
     }
     DevBuf b_spec, b_rows, b_counter, b_nhits;
     CU_TRY(cudaMalloc(&b_spec.p, spec.size() * sizeof(float)));
-    CU_TRY(cudaMalloc(&b_rows.p, (size_t)n_null * sq->total * sizeof(RowRec)));
+    const uint64_t total_recs = sq->total + nseq;
+    CU_TRY(cudaMalloc(&b_rows.p, (size_t)n_null * total_recs * sizeof(RowRec)));
     CU_TRY(cudaMalloc(&b_counter.p, (kMaxQ + 1) * sizeof(unsigned long long)));
     CU_TRY(cudaMalloc(&b_nhits.p, 2 * sizeof(unsigned long long)));
     CU_TRY(cudaMalloc(&res->d_alt, npairs * sizeof(float)));
@@ -638,9 +680,9 @@ extern "C" enum rc dcpgpu_scan_resident(struct dcpgpu_db *db, struct dcpgpu_seqs
     CU_TRY(cudaMemcpyAsync(b_spec.p, spec.data(), spec.size() * sizeof(float), cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemsetAsync(b_counter.p, 0, (kMaxQ + 1) * sizeof(unsigned long long), st));
     CU_TRY(cudaMemsetAsync(b_nhits.p, 0, 2 * sizeof(unsigned long long), st));
-    k_rows<<<nseq, 128, 0, st>>>(sq->d_bases, sq->d_metas, nseq, db->d_null_tabs, db->d_ins_tab, n_null, sq->total,
+    k_rows<<<nseq, 128, 0, st>>>(sq->d_bases, sq->d_metas, nseq, db->d_null_tabs, db->d_ins_tab, n_null, total_recs,
                                  b_rows.as<RowRec>());
-    k_null<<<(nseq * n_null + 127) / 128, 128, 0, st>>>(sq->d_metas, nseq, n_null, sq->total, b_rows.as<RowRec>(),
+    k_null<<<(nseq * n_null + 127) / 128, 128, 0, st>>>(sq->d_metas, nseq, n_null, total_recs, b_rows.as<RowRec>(),
                                                         b_spec.as<float>(), res->d_null);
     launches += 2;
     CU_TRY(cudaEventRecord(ev[1], st));
@@ -655,7 +697,7 @@ extern "C" enum rc dcpgpu_scan_resident(struct dcpgpu_db *db, struct dcpgpu_seqs
 #define LAUNCH(QQ)                                                                                         \
     case QQ:                                                                                               \
         launch_score<QQ>(nblocks, st, db->d_emis, db->d_trans, db->d_metas, db->d_class[q], n_class,       \
-                         sq->d_metas, nseq, sq->total, b_rows.as<RowRec>(), b_spec.as<float>(), res->d_alt, \
+                         sq->d_metas, nseq, total_recs, b_rows.as<RowRec>(), b_spec.as<float>(), res->d_alt,  \
                          nprof, ctr);                                                                      \
         break;
         switch (q)

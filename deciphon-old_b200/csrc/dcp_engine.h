@@ -29,13 +29,16 @@ constexpr int kSeqChunk = 4;      /* sequences per work item */
         }                                                                                      \
     } while (0)
 
-/* one DP row of one sequence under one null table: 64 bytes */
+/*
+ * One DP row of one sequence under one null table: 64 bytes.  A sequence of L nucleotides owns
+ * L+1 records (rows 0..L); record 0 only carries the codes of row 1.
+ */
 struct __align__(16) RowRec
 {
-    float eN[5];      /* N/J/C/R emission of seq[j-l:j], l = 1..5 */
-    float eI[5];      /* insert emission */
-    uint32_t code[5]; /* frame-table code of seq[j-l:j] */
-    uint32_t pad;
+    float eI[5];           /* insert emission of seq[j-l:j], l = 1..5 */
+    uint16_t code_next[6]; /* frame-table codes of row j+1 (0 past the end), [5] pads */
+    float eN[5];           /* N/J/C/R emission of seq[j-l:j] */
+    uint16_t code[6];      /* frame-table codes of this row, [5] pads */
 };
 static_assert(sizeof(RowRec) == 64, "row record is one 64-byte line");
 
@@ -50,7 +53,8 @@ struct SeqMeta
 {
     uint32_t len;
     uint32_t pad;
-    uint64_t row_off; /* first row record (row j=1) / first base */
+    uint64_t row_off; /* first base */
+    uint64_t rec_off; /* record of row 0 (= row_off + sequence index) */
 };
 
 

@@ -210,7 +210,6 @@ __global__ void __launch_bounds__(128) k_trace(const float *__restrict__ emis, c
                                                uint16_t *__restrict__ cell_bp, uint32_t *__restrict__ row_bp,
                                                float *__restrict__ alt_out)
 {
-    constexpr int QP = Q <= 4 ? 4 : 8;
     const int lane = threadIdx.x & 31;
     uint32_t job = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (job >= njobs) return;
@@ -219,8 +218,8 @@ __global__ void __launch_bounds__(128) k_trace(const float *__restrict__ emis, c
     SeqMeta sm = seqs[tj_.seq];
     NodeParams<Q> p;
     load_params<Q>(p, trans + pm.trans_off, lane);
-    const float *emis_lane = emis + pm.emis_off + lane * QP;
-    const RowRec *r = rows + (size_t)pm.null_id * total_rows + sm.row_off;
+    const float *emis_lane = emis + pm.emis_off + lane * 4;
+    const RowRec *r = rows + (size_t)pm.null_id * total_rows + sm.rec_off + 1; /* record of row 1 */
     const float *sp = spec + (size_t)tj_.seq * 16;
     uint16_t *cb = cell_bp + tj_.cell_off;
     uint32_t *rb = row_bp + tj_.row_off;
@@ -411,7 +410,7 @@ template <int Q>
 void launch_trace(cudaStream_t st, uint32_t njobs, const dcpgpu_db *db, const dcpgpu_seqs *sq, const RowRec *rows,
                   const float *spec, const TraceJob *jobs, uint16_t *cell_bp, uint32_t *row_bp, float *alt)
 {
-    k_trace<Q><<<(njobs + 3) / 4, 128, 0, st>>>(db->d_emis, db->d_trans, db->d_metas, sq->d_metas, sq->total, rows,
+    k_trace<Q><<<(njobs + 3) / 4, 128, 0, st>>>(db->d_emis, db->d_trans, db->d_metas, sq->d_metas, sq->total + sq->nseq, rows,
                                                 spec, jobs, njobs, cell_bp, row_bp, alt);
 }
 
