@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdcpgpu.so")
+LIB_PATH = os.environ.get("DCPGPU_LIB") or os.path.join(_HERE, "libdcpgpu.so")  # override: kernel-variant experiments
 
 RC_OK, RC_END, RC_EFAIL, RC_EINVAL, RC_EIO, RC_ENOMEM, RC_EPARSE, RC_EAPI, RC_EHTTP = range(9)
 ENTRY_DIST_NULL, ENTRY_DIST_UNIFORM, ENTRY_DIST_OCCUPANCY = range(3)

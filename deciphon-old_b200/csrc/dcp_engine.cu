@@ -35,30 +35,10 @@ namespace
 /* ----------------------------------------------------------------------------------------- */
 /* prep kernels                                                                              */
 /* ----------------------------------------------------------------------------------------- */
-__constant__ uint32_t c_frame_off[6] = {0, 0, 4, 20, 84, 340};
-
-/* frame-table codes of the windows seq[j-l:j], l = 1..5 (0 where the window does not exist) */
-__device__ __forceinline__ void window_codes(const uint8_t *__restrict__ b, uint32_t j, uint32_t len,
-                                             uint32_t (&code)[5])
-{
-    uint32_t w = 0;
-#pragma unroll
-    for (int l = 1; l <= 5; ++l)
-    {
-        /* window grows to the left: seq[j-l] becomes the most significant base */
-        if (j >= (uint32_t)l && j <= len)
-        {
-            w |= (uint32_t)b[j - l] << (2 * (l - 1));
-            code[l - 1] = c_frame_off[l] + w;
-        }
-        else
-            code[l - 1] = 0; /* unused: Tin of a negative row is -inf */
-    }
-}
-
 __global__ void k_rows(const uint8_t *__restrict__ bases, const SeqMeta *__restrict__ seqs, uint32_t nseq,
                        const float *__restrict__ null_tabs, const float *__restrict__ ins_tab,
-                       uint32_t n_null, uint64_t total_recs, RowRec *__restrict__ rows)
+                       uint32_t n_null, uint64_t total_recs, RowRec *__restrict__ rows,
+                       uint16_t *__restrict__ wcodes)
 {
     uint32_t s = blockIdx.x;
     if (s >= nseq) return;
@@ -66,9 +46,14 @@ __global__ void k_rows(const uint8_t *__restrict__ bases, const SeqMeta *__restr
     const uint8_t *b = bases + sm.row_off;
     for (uint32_t j = threadIdx.x; j <= sm.len; j += blockDim.x)
     {
-        uint32_t code[5], next[5];
-        window_codes(b, j, sm.len, code);
-        window_codes(b, j + 1, sm.len, next);
+        /* seq[j-l] is the l-th least significant base pair of the window */
+        uint32_t w = 0;
+#pragma unroll
+        for (int l = 1; l <= 5; ++l)
+            if (j >= (uint32_t)l) w |= (uint32_t)b[j - l] << (2 * (l - 1));
+        wcodes[sm.rec_off + j] = (uint16_t)w;
+        uint32_t code[5];
+        codes_of(w, code);
         for (uint32_t t = 0; t < n_null; ++t)
         {
             RowRec r;
@@ -77,10 +62,8 @@ __global__ void k_rows(const uint8_t *__restrict__ bases, const SeqMeta *__restr
             {
                 r.eN[l] = null_tabs[(size_t)t * kTab + code[l]];
                 r.eI[l] = ins_tab[code[l]];
-                r.code[l] = (uint16_t)code[l];
-                r.code_next[l] = (uint16_t)next[l];
             }
-            r.code[5] = r.code_next[5] = 0;
+            r.pad0[0] = r.pad0[1] = r.pad0[2] = r.pad1[0] = r.pad1[1] = r.pad1[2] = 0.0f;
             rows[(size_t)t * total_recs + sm.rec_off + j] = r;
         }
     }
@@ -114,13 +97,14 @@ __global__ void k_null(const SeqMeta *__restrict__ seqs, uint32_t nseq, uint32_t
 /* ----------------------------------------------------------------------------------------- */
 /* alt Viterbi, score pass                                                                   */
 /* ----------------------------------------------------------------------------------------- */
-/* loads in flight for the next row: match emissions, insert/special emissions, codes after that */
+/* loads in flight for the next row(s) */
 template <int Q>
 struct RowState
 {
-    float em[5][Q];
+    float em[5][Q];    /* match emissions of the row about to be processed */
     float eI[5], eN[5];
-    uint32_t next[5];
+    uint32_t w1;       /* window of the row after it (addresses of the next emission loads) */
+    uint32_t w2;       /* window two rows ahead, in flight */
 };
 
 /*
@@ -129,15 +113,18 @@ struct RowState
  * Lanes 0,1,2 also carry the N, J, C special states (tx ring); cE/cX are their lane-specific
  * E->X and X->X scores.  Returns E[j] and this lane's V_X[j].
  *
- * Software pipeline: `rs` arrives holding row j's emissions (issued one row earlier); as soon as
- * they are consumed the loads of row j+1 are issued into the same registers, so their L1/L2
- * latency is covered by the D chain, the specials and the Tin updates of row j.
+ * Software pipeline (no load is consumed in the row that issues it):
+ *   rs.em            row j's match emissions, issued during row j-1
+ *   rs.eI / rs.eN    row j's shared emissions, issued early in row j-1
+ *   rs.w1            window of row j+1, loaded during row j-1: addresses of row j+1's emission loads
+ *   rs.w2            window of row j+2, loaded here
  */
 template <int Q, int R>
 __device__ __forceinline__ void score_row(float (&tm)[5][Q], float (&ti)[5][Q], float (&tx)[5],
                                           const NodeParams<Q> &p, RowState<Q> &rs,
                                           const float *__restrict__ emis_lane,
-                                          const RowRec *__restrict__ rec_next, int lane, float NB, float JB,
+                                          const RowRec *__restrict__ rec_next,
+                                          const uint16_t *__restrict__ w_next2, int lane, float NB, float JB,
                                           float EB, float cE, float cX, float &E_out, float &vx_out)
 {
     constexpr int S1 = (R + 4) % 5, S2 = (R + 3) % 5, S3 = (R + 2) % 5, S4 = (R + 1) % 5, S5 = R;
@@ -147,6 +134,7 @@ __device__ __forceinline__ void score_row(float (&tm)[5][Q], float (&ti)[5][Q], 
     for (int i = 0; i < Q; ++i)
         vm[i] = fmaxf(max3(tm[S1][i] + rs.em[0][i], tm[S2][i] + rs.em[1][i], tm[S3][i] + rs.em[2][i]),
                       fmaxf(tm[S4][i] + rs.em[3][i], tm[S5][i] + rs.em[4][i]));
+
 #pragma unroll
     for (int i = 0; i < Q; ++i)
         vi[i] = fmaxf(max3(ti[S1][i] + rs.eI[0], ti[S2][i] + rs.eI[1], ti[S3][i] + rs.eI[2]),
@@ -155,8 +143,15 @@ __device__ __forceinline__ void score_row(float (&tm)[5][Q], float (&ti)[5][Q], 
     float vx = fmaxf(max3(tx[S1] + rs.eN[0], tx[S2] + rs.eN[1], tx[S3] + rs.eN[2]),
                      fmaxf(tx[S4] + rs.eN[3], tx[S5] + rs.eN[4]));
 
-    /* issue row j+1, part 1: the 4- and 5-nt lines (256 and 1024 codes: the likely L1 misses) */
-    load_emis_part<Q, 3, 5>(rs.em, emis_lane, rs.next);
+    /* issue row j+1, part 1: the 4- and 5-nt lines (256 and 1024 codes: the likely L1 misses),
+     * the shared emissions (their registers were just consumed) and the window two rows ahead */
+    uint32_t code[5];
+    codes_of(rs.w1, code);
+    load_emis_part<Q, 3, 5>(rs.em, emis_lane, code);
+    load_row_insert(rec_next, rs.eI);
+    if (lane < 3) load_row_special(rec_next, rs.eN);
+    rs.w1 = rs.w2;
+    rs.w2 = __ldg(w_next2);
 
     /* E[j]: every M_k -> E is 0 and D_k <= max V_M because MD, DD <= 0 (checked at commit) */
     float eloc = vm[0];
@@ -166,8 +161,7 @@ __device__ __forceinline__ void score_row(float (&tm)[5][Q], float (&ti)[5][Q], 
 
     /* node k0-1 lives in the previous lane */
     float vm_prev = __shfl_up_sync(FULL, vm[Q - 1], 1);
-    float vi_prev = __shfl_up_sync(FULL, vi[Q - 1], 1);
-    if (lane == 0) vm_prev = NEG_INF, vi_prev = NEG_INF;
+    if (lane == 0) vm_prev = NEG_INF;
 
     /* D chain: local pass with no carry-in, then exact lazy propagation across lanes */
     float d[Q];
@@ -191,10 +185,11 @@ __device__ __forceinline__ void score_row(float (&tm)[5][Q], float (&ti)[5][Q], 
         if (!__any_sync(FULL, d[Q - 1] > old)) break;
     }
 
-    /* issue row j+1, part 2: the short lines (L1 resident) and the row record */
-    load_emis_part<Q, 0, 3>(rs.em, emis_lane, rs.next);
-    load_row_common(rec_next, rs.eI, rs.next);
-    if (lane < 3) load_row_special(rec_next, rs.eN);
+    float vi_prev = __shfl_up_sync(FULL, vi[Q - 1], 1);
+    if (lane == 0) vi_prev = NEG_INF;
+
+    /* issue row j+1, part 2: the short lines (L1 resident) */
+    load_emis_part<Q, 0, 3>(rs.em, emis_lane, code);
 
     /* B[j] = max(V_N + NB, V_J + JB, E + (EJ+JB)) */
     float vN = __shfl_sync(FULL, vx, 0);
@@ -215,11 +210,11 @@ __device__ __forceinline__ void score_row(float (&tm)[5][Q], float (&ti)[5][Q], 
     vx_out = vx;
 }
 
-/* recs = record of row 0 of this sequence (L+1 records) */
+/* recs / wc = record and window of row 0 of this sequence (L+1 of each) */
 template <int Q>
 __device__ __forceinline__ float score_pair(const NodeParams<Q> &p, const float *__restrict__ emis_lane,
-                                            const RowRec *__restrict__ recs, uint32_t L,
-                                            const float *__restrict__ sp, int lane)
+                                            const RowRec *__restrict__ recs, const uint16_t *__restrict__ wc,
+                                            uint32_t L, const float *__restrict__ sp, int lane)
 {
     const float NN = sp[0], CC = sp[1], JJ = sp[2], NB = sp[3], CT = sp[4], JB = sp[5];
     const float ET = sp[9], ECC = sp[10], EB = sp[11], EJJ = sp[12];
@@ -239,31 +234,36 @@ __device__ __forceinline__ float score_pair(const NodeParams<Q> &p, const float 
     for (int i = 0; i < Q; ++i) tm[4][i] = NB + p.ent[i];
     tx[4] = lane == 0 ? NN : NEG_INF;
 
-    /* pipeline prologue: row 1's loads */
+    /* pipeline prologue: row 1's loads, windows of rows 2 and 3 */
     RowState<Q> rs;
 #pragma unroll
     for (int l = 0; l < 5; ++l) rs.eN[l] = NEG_INF;
-    load_row_common(recs, rs.eI, rs.next); /* record 0: codes of row 1 */
-    load_emis<Q>(rs.em, emis_lane, rs.next);
-    load_row_common(recs + 1, rs.eI, rs.next);
+    {
+        uint32_t code[5];
+        codes_of(__ldg(wc + 1), code);
+        load_emis<Q>(rs.em, emis_lane, code);
+    }
+    load_row_insert(recs + 1, rs.eI);
     if (lane < 3) load_row_special(recs + 1, rs.eN);
+    rs.w1 = __ldg(wc + min(2u, L));
+    rs.w2 = __ldg(wc + min(3u, L));
 
     float E = NEG_INF, vx = NEG_INF;
     uint32_t j = 1;
-#define NEXT(jj) (recs + min((uint32_t)(jj) + 1u, L))
+#define ROW_ARGS(jj) recs + min((uint32_t)(jj) + 1u, L), wc + min((uint32_t)(jj) + 3u, L)
     for (; j + 4 <= L; j += 5)
     {
-        score_row<Q, 0>(tm, ti, tx, p, rs, emis_lane, NEXT(j), lane, NB, JB, EB, cE, cX, E, vx);
-        score_row<Q, 1>(tm, ti, tx, p, rs, emis_lane, NEXT(j + 1), lane, NB, JB, EB, cE, cX, E, vx);
-        score_row<Q, 2>(tm, ti, tx, p, rs, emis_lane, NEXT(j + 2), lane, NB, JB, EB, cE, cX, E, vx);
-        score_row<Q, 3>(tm, ti, tx, p, rs, emis_lane, NEXT(j + 3), lane, NB, JB, EB, cE, cX, E, vx);
-        score_row<Q, 4>(tm, ti, tx, p, rs, emis_lane, NEXT(j + 4), lane, NB, JB, EB, cE, cX, E, vx);
+        score_row<Q, 0>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j), lane, NB, JB, EB, cE, cX, E, vx);
+        score_row<Q, 1>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 1), lane, NB, JB, EB, cE, cX, E, vx);
+        score_row<Q, 2>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 2), lane, NB, JB, EB, cE, cX, E, vx);
+        score_row<Q, 3>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 3), lane, NB, JB, EB, cE, cX, E, vx);
+        score_row<Q, 4>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 4), lane, NB, JB, EB, cE, cX, E, vx);
     }
-    if (j <= L) score_row<Q, 0>(tm, ti, tx, p, rs, emis_lane, NEXT(j), lane, NB, JB, EB, cE, cX, E, vx);
-    if (j + 1 <= L) score_row<Q, 1>(tm, ti, tx, p, rs, emis_lane, NEXT(j + 1), lane, NB, JB, EB, cE, cX, E, vx);
-    if (j + 2 <= L) score_row<Q, 2>(tm, ti, tx, p, rs, emis_lane, NEXT(j + 2), lane, NB, JB, EB, cE, cX, E, vx);
-    if (j + 3 <= L) score_row<Q, 3>(tm, ti, tx, p, rs, emis_lane, NEXT(j + 3), lane, NB, JB, EB, cE, cX, E, vx);
-#undef NEXT
+    if (j <= L) score_row<Q, 0>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j), lane, NB, JB, EB, cE, cX, E, vx);
+    if (j + 1 <= L) score_row<Q, 1>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 1), lane, NB, JB, EB, cE, cX, E, vx);
+    if (j + 2 <= L) score_row<Q, 2>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 2), lane, NB, JB, EB, cE, cX, E, vx);
+    if (j + 3 <= L) score_row<Q, 3>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 3), lane, NB, JB, EB, cE, cX, E, vx);
+#undef ROW_ARGS
     /* T[L] = max(E[L] + (EC+CT), V_C[L] + CT); V_C lives in lane 2 */
     float vC = __shfl_sync(FULL, vx, 2);
     return fmaxf(E + ET, vC + CT);
@@ -273,8 +273,9 @@ template <int Q>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 1)
 k_score(const float *__restrict__ emis, const float *__restrict__ trans, const ProfMeta *__restrict__ metas,
         const uint32_t *__restrict__ class_profs, uint32_t n_class_profs, const SeqMeta *__restrict__ seqs,
-        uint32_t nseq, uint64_t total_recs, const RowRec *__restrict__ rows, const float *__restrict__ spec,
-        float *__restrict__ alt_out, uint32_t nprof, unsigned long long *__restrict__ counter)
+        uint32_t nseq, uint64_t total_recs, const RowRec *__restrict__ rows, const uint16_t *__restrict__ wcodes,
+        const float *__restrict__ spec, float *__restrict__ alt_out, uint32_t nprof,
+        unsigned long long *__restrict__ counter)
 {
     const int lane = threadIdx.x & 31;
     const uint32_t nchunks = (nseq + kSeqChunk - 1) / kSeqChunk;
@@ -296,7 +297,8 @@ k_score(const float *__restrict__ emis, const float *__restrict__ trans, const P
         for (uint32_t s = ci * kSeqChunk; s < s_end; ++s)
         {
             SeqMeta sm = seqs[s];
-            float T = score_pair<Q>(p, emis_lane, rows_t + sm.rec_off, sm.len, spec + (size_t)s * 16, lane);
+            float T = score_pair<Q>(p, emis_lane, rows_t + sm.rec_off, wcodes + sm.rec_off, sm.len,
+                                    spec + (size_t)s * 16, lane);
             if (lane == 0) alt_out[(size_t)s * nprof + prof] = T;
         }
     }
@@ -342,11 +344,12 @@ __global__ void k_gather(const unsigned long long *__restrict__ list, size_t nhi
 template <int Q>
 void launch_score(int nblocks, cudaStream_t st, const float *emis, const float *trans, const ProfMeta *metas,
                   const uint32_t *class_profs, uint32_t n_class, const SeqMeta *seqs, uint32_t nseq,
-                  uint64_t total_rows, const RowRec *rows, const float *spec, float *alt, uint32_t nprof,
+                  uint64_t total_rows, const RowRec *rows, const uint16_t *wcodes, const float *spec, float *alt,
+                  uint32_t nprof,
                   unsigned long long *counter)
 {
     k_score<Q><<<nblocks, kWarpsPerBlock * 32, 0, st>>>(emis, trans, metas, class_profs, n_class, seqs, nseq,
-                                                        total_rows, rows, spec, alt, nprof, counter);
+                                                        total_rows, rows, wcodes, spec, alt, nprof, counter);
 }
 
 } // namespace
@@ -662,10 +665,11 @@ extern "C" enum rc dcpgpu_scan_resident(struct dcpgpu_db *db, struct dcpgpu_seqs
             memcpy(&spec[(size_t)e.second * 16], x, sizeof x);
         }
     }
-    DevBuf b_spec, b_rows, b_counter, b_nhits;
+    DevBuf b_spec, b_rows, b_wcodes, b_counter, b_nhits;
     CU_TRY(cudaMalloc(&b_spec.p, spec.size() * sizeof(float)));
     const uint64_t total_recs = sq->total + nseq;
     CU_TRY(cudaMalloc(&b_rows.p, (size_t)n_null * total_recs * sizeof(RowRec)));
+    CU_TRY(cudaMalloc(&b_wcodes.p, total_recs * sizeof(uint16_t)));
     CU_TRY(cudaMalloc(&b_counter.p, (kMaxQ + 1) * sizeof(unsigned long long)));
     CU_TRY(cudaMalloc(&b_nhits.p, 2 * sizeof(unsigned long long)));
     CU_TRY(cudaMalloc(&res->d_alt, npairs * sizeof(float)));
@@ -681,7 +685,7 @@ extern "C" enum rc dcpgpu_scan_resident(struct dcpgpu_db *db, struct dcpgpu_seqs
     CU_TRY(cudaMemsetAsync(b_counter.p, 0, (kMaxQ + 1) * sizeof(unsigned long long), st));
     CU_TRY(cudaMemsetAsync(b_nhits.p, 0, 2 * sizeof(unsigned long long), st));
     k_rows<<<nseq, 128, 0, st>>>(sq->d_bases, sq->d_metas, nseq, db->d_null_tabs, db->d_ins_tab, n_null, total_recs,
-                                 b_rows.as<RowRec>());
+                                 b_rows.as<RowRec>(), b_wcodes.as<uint16_t>());
     k_null<<<(nseq * n_null + 127) / 128, 128, 0, st>>>(sq->d_metas, nseq, n_null, total_recs, b_rows.as<RowRec>(),
                                                         b_spec.as<float>(), res->d_null);
     launches += 2;
@@ -697,7 +701,8 @@ extern "C" enum rc dcpgpu_scan_resident(struct dcpgpu_db *db, struct dcpgpu_seqs
 #define LAUNCH(QQ)                                                                                         \
     case QQ:                                                                                               \
         launch_score<QQ>(nblocks, st, db->d_emis, db->d_trans, db->d_metas, db->d_class[q], n_class,       \
-                         sq->d_metas, nseq, total_recs, b_rows.as<RowRec>(), b_spec.as<float>(), res->d_alt,  \
+                         sq->d_metas, nseq, total_recs, b_rows.as<RowRec>(), b_wcodes.as<uint16_t>(), b_spec.as<float>(), \
+                         res->d_alt,                                                                       \
                          nprof, ctr);                                                                      \
         break;
         switch (q)
@@ -757,7 +762,8 @@ extern "C" enum rc dcpgpu_scan_resident(struct dcpgpu_db *db, struct dcpgpu_seqs
     CU_TRY(cudaEventRecord(ev[3], st));
     if (nhits && prm->want_paths)
     {
-        enum rc rc = dcp_trace_hits(db, sq, res, b_rows.as<RowRec>(), b_spec.as<float>(), &launches);
+        enum rc rc = dcp_trace_hits(db, sq, res, b_rows.as<RowRec>(), b_wcodes.as<uint16_t>(), b_spec.as<float>(),
+                                    &launches);
         if (rc) return rc;
         res->have_paths = true;
     }

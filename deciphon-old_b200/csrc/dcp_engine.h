@@ -30,15 +30,18 @@ constexpr int kSeqChunk = 4;      /* sequences per work item */
     } while (0)
 
 /*
- * One DP row of one sequence under one null table: 64 bytes.  A sequence of L nucleotides owns
- * L+1 records (rows 0..L); record 0 only carries the codes of row 1.
+ * Per-row inputs of the DP besides the match emissions.  A sequence of L nucleotides owns L+1
+ * records (rows 0..L).  wcode[row] (one uint16 per record, independent of the null table) is the
+ * 2-bit packed window of the last five nucleotides ending at that row; the frame-table code of
+ * seq[j-l:j] is frame_off[l] + (w & (4^l - 1)).  RowRec holds the emissions that are shared by
+ * all core nodes: insert (eI) and N/J/C/R (eN), one record per (null table, row).
  */
 struct __align__(16) RowRec
 {
-    float eI[5];           /* insert emission of seq[j-l:j], l = 1..5 */
-    uint16_t code_next[6]; /* frame-table codes of row j+1 (0 past the end), [5] pads */
-    float eN[5];           /* N/J/C/R emission of seq[j-l:j] */
-    uint16_t code[6];      /* frame-table codes of this row, [5] pads */
+    float eI[5]; /* insert emission of seq[j-l:j], l = 1..5 */
+    float pad0[3];
+    float eN[5]; /* N/J/C/R emission of seq[j-l:j] */
+    float pad1[3];
 };
 static_assert(sizeof(RowRec) == 64, "row record is one 64-byte line");
 
@@ -113,7 +116,7 @@ struct dcpgpu_result
 
 /* dcp_trace.cu */
 enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const RowRec *d_rows,
-                       const float *d_spec, uint64_t *launches);
+                       const uint16_t *d_wcodes, const float *d_spec, uint64_t *launches);
 const protein_profile *dcp_db_profile(struct dcpgpu_db const *db, unsigned i);
 
 #endif

@@ -4,6 +4,10 @@
 
 #include "dcp_engine.h"
 
+#ifndef DCP_HINTS
+#define DCP_HINTS 0
+#endif
+
 template <int Q>
 struct NodeParams
 {
@@ -41,30 +45,24 @@ __device__ __forceinline__ void load_params(NodeParams<Q> &p, const float *__res
     }
 }
 
-/* everything one DP row needs besides the match emissions */
-struct RowIn
+/* frame-table codes of the windows ending at a row, from its packed 10-bit window */
+__device__ __forceinline__ void codes_of(uint32_t w, uint32_t (&c)[5])
 {
-    float eI[5];        /* insert emission of seq[j-l:j] */
-    float eN[5];        /* N/J/C emission of seq[j-l:j] */
-    uint32_t code[5];   /* frame-table code of seq[j-l:j] */
-    uint32_t next[5];   /* the same for row j+1 (0 past the end) */
-};
-
-__device__ __forceinline__ void unpack_codes(uint32_t (&c)[5], uint32_t w0, uint32_t w1, uint32_t w2)
-{
-    c[0] = w0 & 0xffffu, c[1] = w0 >> 16, c[2] = w1 & 0xffffu, c[3] = w1 >> 16, c[4] = w2 & 0xffffu;
+    c[0] = w & 3u;
+    c[1] = 4u + (w & 15u);
+    c[2] = 20u + (w & 63u);
+    c[3] = 84u + (w & 255u);
+    c[4] = 340u + (w & 1023u);
 }
 
-/* first 32 bytes of a record: what every lane needs (eI of this row, codes of the next) */
-__device__ __forceinline__ void load_row_common(const RowRec *__restrict__ r, float (&eI)[5], uint32_t (&next)[5])
+__device__ __forceinline__ void load_row_insert(const RowRec *__restrict__ r, float (&eI)[5])
 {
     const float4 *q = reinterpret_cast<const float4 *>(r);
-    float4 a = __ldg(q), b = __ldg(q + 1);
-    eI[0] = a.x, eI[1] = a.y, eI[2] = a.z, eI[3] = a.w, eI[4] = b.x;
-    unpack_codes(next, __float_as_uint(b.y), __float_as_uint(b.z), __float_as_uint(b.w));
+    float4 a = __ldg(q);
+    float e4 = __ldg(reinterpret_cast<const float *>(q + 1));
+    eI[0] = a.x, eI[1] = a.y, eI[2] = a.z, eI[3] = a.w, eI[4] = e4;
 }
 
-/* second 32 bytes: eN (used by the lanes that carry N, J, C) and this row's own codes */
 __device__ __forceinline__ void load_row_special(const RowRec *__restrict__ r, float (&eN)[5])
 {
     const float4 *q = reinterpret_cast<const float4 *>(r) + 2;
@@ -73,21 +71,27 @@ __device__ __forceinline__ void load_row_special(const RowRec *__restrict__ r, f
     eN[0] = a.x, eN[1] = a.y, eN[2] = a.z, eN[3] = a.w, eN[4] = e4;
 }
 
-__device__ __forceinline__ RowIn load_row(const RowRec *__restrict__ r)
+/* 128-bit read-only loads with an L1 eviction hint (PTX ld.global.nc.L1::*) */
+__device__ __forceinline__ float4 ldg_keep(const float4 *p)
 {
-    RowIn o;
-    load_row_common(r, o.eI, o.next);
-    load_row_special(r, o.eN);
-    const float4 *q = reinterpret_cast<const float4 *>(r) + 3;
-    float4 d = __ldg(q);
-    unpack_codes(o.code, __float_as_uint(d.y), __float_as_uint(d.z), __float_as_uint(d.w));
-    return o;
+    float4 v;
+    asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ldg_stream(const float4 *p)
+{
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
 }
 
 /*
- * Match emissions of one row: for each of the five lengths one line of the transposed table,
- * [code][half][lane][4] -- every LDG.128 of a warp covers 512 contiguous bytes.
- * emis_lane = table base + lane * 4.
+ * Lines of the 1-, 2- and 3-nt windows (84 codes, 84 KB per profile at QP = 8) are reused by
+ * every row of every warp working on the profile: keep them in L1 (evict_last).  The 5-nt lines
+ * (1024 codes, 1 MB) are a stream with almost no reuse inside one SM: do not allocate them in L1,
+ * L2 serves them.  4-nt lines (256 codes) take the default policy.
  */
 template <int Q, int L0, int L1>
 __device__ __forceinline__ void load_emis_part(float (&em)[5][Q], const float *__restrict__ emis_lane,
@@ -99,12 +103,21 @@ __device__ __forceinline__ void load_emis_part(float (&em)[5][Q], const float *_
     for (int l = L0; l < L1; ++l)
     {
         const float4 *src = reinterpret_cast<const float4 *>(emis_lane + (size_t)code[l] * ROW);
+#if DCP_HINTS
+        float4 a = l < 3 ? ldg_keep(src) : (l == 4 ? ldg_stream(src) : __ldg(src));
+#else
         float4 a = __ldg(src);
+#endif
         float tmp[8];
         tmp[0] = a.x, tmp[1] = a.y, tmp[2] = a.z, tmp[3] = a.w;
         if (Q > 4)
         {
-            float4 b = __ldg(src + 32); /* second half: +128 floats */
+            /* second half: +128 floats */
+#if DCP_HINTS
+            float4 b = l < 3 ? ldg_keep(src + 32) : (l == 4 ? ldg_stream(src + 32) : __ldg(src + 32));
+#else
+            float4 b = __ldg(src + 32);
+#endif
             tmp[4] = b.x, tmp[5] = b.y, tmp[6] = b.z, tmp[7] = b.w;
         }
 #pragma unroll

@@ -47,15 +47,19 @@ template <int Q, int R>
 __device__ __forceinline__ void trace_row(float (&tm)[5][Q], float (&ti)[5][Q], float (&tn)[5], float (&tj)[5],
                                           float (&tc)[5], const NodeParams<Q> &p,
                                           const float *__restrict__ emis_lane, const RowRec *__restrict__ rec,
-                                          int lane, const float *__restrict__ sp, uint16_t *__restrict__ cell_bp,
+                                          uint32_t wcode, int lane, const float *__restrict__ sp, uint16_t *__restrict__ cell_bp,
                                           uint32_t *__restrict__ row_bp, float &T_out)
 {
     constexpr int S[5] = {(R + 4) % 5, (R + 3) % 5, (R + 2) % 5, (R + 1) % 5, R};
     const float NN = sp[0], CC = sp[1], JJ = sp[2], NB = sp[3], CT = sp[4], JB = sp[5];
     const float ET = sp[9], ECC = sp[10], EB = sp[11], EJJ = sp[12];
-    RowIn in = load_row(rec);
+    struct { float eI[5], eN[5]; } in;
+    load_row_insert(rec, in.eI);
+    load_row_special(rec, in.eN);
+    uint32_t code[5];
+    codes_of(wcode, code);
     float em[5][Q];
-    load_emis<Q>(em, emis_lane, in.code);
+    load_emis<Q>(em, emis_lane, code);
 
     /* W[j-l][X][l] for every emitting state: the five candidate sums per state */
     float sM[Q][5], sI[Q][5], vm[Q], vi[Q];
@@ -205,8 +209,8 @@ template <int Q>
 __global__ void __launch_bounds__(128) k_trace(const float *__restrict__ emis, const float *__restrict__ trans,
                                                const ProfMeta *__restrict__ metas,
                                                const SeqMeta *__restrict__ seqs, uint64_t total_rows,
-                                               const RowRec *__restrict__ rows, const float *__restrict__ spec,
-                                               const TraceJob *__restrict__ jobs, uint32_t njobs,
+                                               const RowRec *__restrict__ rows, const uint16_t *__restrict__ wcodes,
+                                               const float *__restrict__ spec, const TraceJob *__restrict__ jobs, uint32_t njobs,
                                                uint16_t *__restrict__ cell_bp, uint32_t *__restrict__ row_bp,
                                                float *__restrict__ alt_out)
 {
@@ -220,6 +224,7 @@ __global__ void __launch_bounds__(128) k_trace(const float *__restrict__ emis, c
     load_params<Q>(p, trans + pm.trans_off, lane);
     const float *emis_lane = emis + pm.emis_off + lane * 4;
     const RowRec *r = rows + (size_t)pm.null_id * total_rows + sm.rec_off + 1; /* record of row 1 */
+    const uint16_t *wc = wcodes + sm.rec_off; /* wc[j] = window of row j */
     const float *sp = spec + (size_t)tj_.seq * 16;
     uint16_t *cb = cell_bp + tj_.cell_off;
     uint32_t *rb = row_bp + tj_.row_off;
@@ -249,16 +254,16 @@ __global__ void __launch_bounds__(128) k_trace(const float *__restrict__ emis, c
     constexpr uint32_t CS = Q * 32; /* cell backpointers per row */
     for (; j + 4 <= L; j += 5)
     {
-        trace_row<Q, 0>(tm, ti, tn, tjr, tc, p, emis_lane, r + (j - 1), lane, sp, cb + (size_t)j * CS, rb + j, T);
-        trace_row<Q, 1>(tm, ti, tn, tjr, tc, p, emis_lane, r + j, lane, sp, cb + (size_t)(j + 1) * CS, rb + j + 1, T);
-        trace_row<Q, 2>(tm, ti, tn, tjr, tc, p, emis_lane, r + (j + 1), lane, sp, cb + (size_t)(j + 2) * CS, rb + j + 2, T);
-        trace_row<Q, 3>(tm, ti, tn, tjr, tc, p, emis_lane, r + (j + 2), lane, sp, cb + (size_t)(j + 3) * CS, rb + j + 3, T);
-        trace_row<Q, 4>(tm, ti, tn, tjr, tc, p, emis_lane, r + (j + 3), lane, sp, cb + (size_t)(j + 4) * CS, rb + j + 4, T);
+        trace_row<Q, 0>(tm, ti, tn, tjr, tc, p, emis_lane, r + (j - 1), wc[(j - 1) + 1], lane, sp, cb + (size_t)j * CS, rb + j, T);
+        trace_row<Q, 1>(tm, ti, tn, tjr, tc, p, emis_lane, r + j, wc[j + 1], lane, sp, cb + (size_t)(j + 1) * CS, rb + j + 1, T);
+        trace_row<Q, 2>(tm, ti, tn, tjr, tc, p, emis_lane, r + (j + 1), wc[(j + 1) + 1], lane, sp, cb + (size_t)(j + 2) * CS, rb + j + 2, T);
+        trace_row<Q, 3>(tm, ti, tn, tjr, tc, p, emis_lane, r + (j + 2), wc[(j + 2) + 1], lane, sp, cb + (size_t)(j + 3) * CS, rb + j + 3, T);
+        trace_row<Q, 4>(tm, ti, tn, tjr, tc, p, emis_lane, r + (j + 3), wc[(j + 3) + 1], lane, sp, cb + (size_t)(j + 4) * CS, rb + j + 4, T);
     }
-    if (j <= L) trace_row<Q, 0>(tm, ti, tn, tjr, tc, p, emis_lane, r + (j - 1), lane, sp, cb + (size_t)j * CS, rb + j, T);
-    if (j + 1 <= L) trace_row<Q, 1>(tm, ti, tn, tjr, tc, p, emis_lane, r + j, lane, sp, cb + (size_t)(j + 1) * CS, rb + j + 1, T);
-    if (j + 2 <= L) trace_row<Q, 2>(tm, ti, tn, tjr, tc, p, emis_lane, r + (j + 1), lane, sp, cb + (size_t)(j + 2) * CS, rb + j + 2, T);
-    if (j + 3 <= L) trace_row<Q, 3>(tm, ti, tn, tjr, tc, p, emis_lane, r + (j + 2), lane, sp, cb + (size_t)(j + 3) * CS, rb + j + 3, T);
+    if (j <= L) trace_row<Q, 0>(tm, ti, tn, tjr, tc, p, emis_lane, r + (j - 1), wc[(j - 1) + 1], lane, sp, cb + (size_t)j * CS, rb + j, T);
+    if (j + 1 <= L) trace_row<Q, 1>(tm, ti, tn, tjr, tc, p, emis_lane, r + j, wc[j + 1], lane, sp, cb + (size_t)(j + 1) * CS, rb + j + 1, T);
+    if (j + 2 <= L) trace_row<Q, 2>(tm, ti, tn, tjr, tc, p, emis_lane, r + (j + 1), wc[(j + 1) + 1], lane, sp, cb + (size_t)(j + 2) * CS, rb + j + 2, T);
+    if (j + 3 <= L) trace_row<Q, 3>(tm, ti, tn, tjr, tc, p, emis_lane, r + (j + 2), wc[(j + 2) + 1], lane, sp, cb + (size_t)(j + 3) * CS, rb + j + 3, T);
     if (lane == 0) alt_out[job] = T;
 }
 
@@ -408,16 +413,16 @@ struct DevBuf
 
 template <int Q>
 void launch_trace(cudaStream_t st, uint32_t njobs, const dcpgpu_db *db, const dcpgpu_seqs *sq, const RowRec *rows,
-                  const float *spec, const TraceJob *jobs, uint16_t *cell_bp, uint32_t *row_bp, float *alt)
+                  const uint16_t *wcodes, const float *spec, const TraceJob *jobs, uint16_t *cell_bp, uint32_t *row_bp, float *alt)
 {
     k_trace<Q><<<(njobs + 3) / 4, 128, 0, st>>>(db->d_emis, db->d_trans, db->d_metas, sq->d_metas, sq->total + sq->nseq, rows,
-                                                spec, jobs, njobs, cell_bp, row_bp, alt);
+                                                wcodes, spec, jobs, njobs, cell_bp, row_bp, alt);
 }
 
 } // namespace
 
 enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const RowRec *d_rows,
-                       const float *d_spec, uint64_t *launches)
+                       const uint16_t *d_wcodes, const float *d_spec, uint64_t *launches)
 {
     cudaStream_t st = db->stream;
     const size_t nhits = res->hits.size();
@@ -472,7 +477,7 @@ enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const
             while (b < nj && db->metas[sorted[b].prof].Q == Q) ++b;
 #define LT(QQ)                                                                                                   \
     case QQ:                                                                                                     \
-        launch_trace<QQ>(st, b - a, db, sq, d_rows, d_spec, b_jobs.as<TraceJob>() + a, b_cells.as<uint16_t>(),   \
+        launch_trace<QQ>(st, b - a, db, sq, d_rows, d_wcodes, d_spec, b_jobs.as<TraceJob>() + a, b_cells.as<uint16_t>(),   \
                          b_rows.as<uint32_t>(), b_alt.as<float>() + a);                                          \
         break;
             switch (Q)
