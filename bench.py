@@ -145,9 +145,11 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--profiles", type=int, default=1000, help="profiles per GPU")
     ap.add_argument("--reads", type=int, default=10000)
+    ap.add_argument("--core", type=int, default=CORE, help="profile core length (experiments; the metric is quoted at 200)")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
+    globals()["CORE"] = a.core
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -4,10 +4,6 @@
 
 #include "dcp_engine.h"
 
-#ifndef DCP_HINTS
-#define DCP_HINTS 0
-#endif
-
 template <int Q>
 struct NodeParams
 {
@@ -71,27 +67,11 @@ __device__ __forceinline__ void load_row_special(const RowRec *__restrict__ r, f
     eN[0] = a.x, eN[1] = a.y, eN[2] = a.z, eN[3] = a.w, eN[4] = e4;
 }
 
-/* 128-bit read-only loads with an L1 eviction hint (PTX ld.global.nc.L1::*) */
-__device__ __forceinline__ float4 ldg_keep(const float4 *p)
-{
-    float4 v;
-    asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ float4 ldg_stream(const float4 *p)
-{
-    float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-}
-
 /*
- * Lines of the 1-, 2- and 3-nt windows (84 codes, 84 KB per profile at QP = 8) are reused by
- * every row of every warp working on the profile: keep them in L1 (evict_last).  The 5-nt lines
- * (1024 codes, 1 MB) are a stream with almost no reuse inside one SM: do not allocate them in L1,
- * L2 serves them.  4-nt lines (256 codes) take the default policy.
+ * Match emissions of one row: for each of the five lengths one line of the transposed table,
+ * [code][half][lane][4] -- every LDG.128 of a warp covers 512 contiguous bytes.
+ * emis_lane = table base + lane * 4.  (L1 eviction hints -- evict_last on the 1-3 nt lines,
+ * no_allocate on the 5 nt lines -- were measured and did not help: 381 vs 399 GCUPS.)
  */
 template <int Q, int L0, int L1>
 __device__ __forceinline__ void load_emis_part(float (&em)[5][Q], const float *__restrict__ emis_lane,
@@ -102,26 +82,41 @@ __device__ __forceinline__ void load_emis_part(float (&em)[5][Q], const float *_
 #pragma unroll
     for (int l = L0; l < L1; ++l)
     {
-        const float4 *src = reinterpret_cast<const float4 *>(emis_lane + (size_t)code[l] * ROW);
-#if DCP_HINTS
-        float4 a = l < 3 ? ldg_keep(src) : (l == 4 ? ldg_stream(src) : __ldg(src));
-#else
-        float4 a = __ldg(src);
-#endif
-        float tmp[8];
-        tmp[0] = a.x, tmp[1] = a.y, tmp[2] = a.z, tmp[3] = a.w;
-        if (Q > 4)
+        const float *src = emis_lane + (size_t)code[l] * ROW;
+        if (Q >= 4)
         {
-            /* second half: +128 floats */
-#if DCP_HINTS
-            float4 b = l < 3 ? ldg_keep(src + 32) : (l == 4 ? ldg_stream(src + 32) : __ldg(src + 32));
-#else
-            float4 b = __ldg(src + 32);
-#endif
-            tmp[4] = b.x, tmp[5] = b.y, tmp[6] = b.z, tmp[7] = b.w;
+            float4 a = __ldg(reinterpret_cast<const float4 *>(src));
+            em[l][0] = a.x, em[l][1] = a.y, em[l][2] = a.z, em[l][3] = a.w;
         }
+        else
+        {
+            /* Q < 4: only the first Q floats of the lane's quad are real */
+            float4 a = __ldg(reinterpret_cast<const float4 *>(src));
+            float t[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-        for (int i = 0; i < Q; ++i) em[l][i] = tmp[i];
+            for (int i = 0; i < Q; ++i) em[l][i] = t[i];
+        }
+        /* second half (+128 floats) holds nodes 4..Q-1 of the lane: load exactly Q-4 floats */
+        if (Q == 8)
+        {
+            float4 b = __ldg(reinterpret_cast<const float4 *>(src + 128));
+            em[l][4 % Q] = b.x, em[l][5 % Q] = b.y, em[l][6 % Q] = b.z, em[l][7 % Q] = b.w;
+        }
+        else if (Q == 7)
+        {
+            float2 b = __ldg(reinterpret_cast<const float2 *>(src + 128));
+            float c = __ldg(src + 130);
+            em[l][4 % Q] = b.x, em[l][5 % Q] = b.y, em[l][6 % Q] = c;
+        }
+        else if (Q == 6)
+        {
+            float2 b = __ldg(reinterpret_cast<const float2 *>(src + 128));
+            em[l][4 % Q] = b.x, em[l][5 % Q] = b.y;
+        }
+        else if (Q == 5)
+        {
+            em[l][4 % Q] = __ldg(src + 128);
+        }
     }
 }
 
