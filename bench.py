@@ -99,7 +99,7 @@ class ClockSampler(threading.Thread):
 
     def summary(self):
         self.stop_ev.set()
-        self.join(timeout=6)
+        self.join()
         sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -240,10 +240,13 @@ def main():
     barrier()
     t1 = time.perf_counter()
     h2d = d2h = 0
+    e2e_steps = []
     for _ in range(a.steps):
+        ts = time.perf_counter()
         r = db.scan(reads)
         h2d, d2h = r.timing.h2d_bytes, r.timing.d2h_bytes
         _ = r.nhits
+        e2e_steps.append([round((time.perf_counter() - ts) * 1e3, 2), round(r.timing.total_ms, 2)])
         del r
     barrier()
     e2e_s = time.perf_counter() - t1
@@ -287,7 +290,7 @@ def main():
         "gpu_launches": int(launches),
         "phases_ms_rank0": {"prep": float(np.mean(prep_ms)), "score": k_ms, "trace": float(np.mean(trace_ms)),
                             "total": float(np.mean(total_ms))},
-        "wall_s_timed_region": wall, "setup_s": setup_s,
+        "wall_s_timed_region": wall, "setup_s": setup_s, "e2e_steps_ms_wall_vs_device": e2e_steps,
         "clocks": clocks,
         "roofline": {"bound": "fp32-alu-issue", "kernel": "k_score<7>", "achieved": achieved_ops / 1e12, "peak": peak_ops / 1e12,
                      "unit": "TFLOP/s", "frac": achieved_ops / peak_ops, "traffic": None,

@@ -415,6 +415,15 @@ extern "C" enum rc dcpgpu_db_new(struct dcpgpu_db **out, int device)
     db->device = device;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) db->sm_count = prop.multiProcessorCount;
+    {
+        /* keep freed scratch blocks cached in the pool between scans */
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
+        {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     if (cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking) != cudaSuccess)
     {
         delete db;
@@ -559,7 +568,12 @@ extern "C" void dcpgpu_db_del(struct dcpgpu_db *db)
     cudaFree(db->d_emis), cudaFree(db->d_trans), cudaFree(db->d_metas);
     cudaFree(db->d_null_tabs), cudaFree(db->d_ins_tab);
     for (int q = 0; q <= kMaxQ; ++q) cudaFree(db->d_class[q]);
-    if (db->stream) cudaStreamDestroy(db->stream);
+    if (db->h_stage) cudaFreeHost(db->h_stage);
+    if (db->stream)
+    {
+        cudaStreamSynchronize(db->stream);
+        cudaStreamDestroy(db->stream);
+    }
     delete db;
 }
 
@@ -589,12 +603,20 @@ extern "C" enum rc dcpgpu_seqs_new(struct dcpgpu_seqs **out, struct dcpgpu_db *d
         total += lens[i];
     }
     sq->total = total;
-    uint8_t *h = nullptr;
-    if (cudaMallocHost(&h, total) != cudaSuccess)
+    /* pinned staging buffer, cached in the db and grown on demand */
+    if (db->h_stage_cap < total)
     {
-        delete sq;
-        return dcp_error(RC_ENOMEM, "pinned staging for sequences");
+        if (db->h_stage) cudaFreeHost(db->h_stage);
+        db->h_stage = nullptr, db->h_stage_cap = 0;
+        size_t cap = total + total / 4 + 4096;
+        if (cudaMallocHost(&db->h_stage, cap) != cudaSuccess)
+        {
+            delete sq;
+            return dcp_error(RC_ENOMEM, "pinned staging for sequences");
+        }
+        db->h_stage_cap = cap;
     }
+    uint8_t *h = (uint8_t *)db->h_stage;
     static const int8_t lut_init = 0;
     (void)lut_init;
     int8_t lut[256];
@@ -618,17 +640,15 @@ extern "C" enum rc dcpgpu_seqs_new(struct dcpgpu_seqs **out, struct dcpgpu_db *d
     }
     if (bad)
     {
-        cudaFreeHost(h);
         delete sq;
         return dcp_error(RC_EINVAL, "sequence symbol outside ACGT");
     }
-    cudaError_t e = cudaMalloc(&sq->d_bases, total);
-    if (e == cudaSuccess) e = cudaMalloc(&sq->d_metas, nseqs * sizeof(SeqMeta));
+    cudaError_t e = cudaMallocAsync(&sq->d_bases, total, db->stream);
+    if (e == cudaSuccess) e = cudaMallocAsync(&sq->d_metas, nseqs * sizeof(SeqMeta), db->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(sq->d_bases, h, total, cudaMemcpyHostToDevice, db->stream);
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(sq->d_metas, sq->metas.data(), nseqs * sizeof(SeqMeta), cudaMemcpyHostToDevice, db->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(db->stream);
-    cudaFreeHost(h);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(db->stream); /* staging buffer is reusable again */
     if (e != cudaSuccess)
     {
         dcp_set_error(cudaGetErrorString(e));
@@ -644,20 +664,10 @@ extern "C" void dcpgpu_seqs_del(struct dcpgpu_seqs *sq)
 {
     if (!sq) return;
     cudaSetDevice(sq->db->device);
-    cudaFree(sq->d_bases), cudaFree(sq->d_metas);
+    cudaFreeAsync(sq->d_bases, sq->db->stream), cudaFreeAsync(sq->d_metas, sq->db->stream);
     delete sq;
 }
 
-namespace
-{
-struct DevBuf
-{
-    void *p = nullptr;
-    ~DevBuf() { cudaFree(p); }
-    template <class T>
-    T *as() { return (T *)p; }
-};
-} // namespace
 
 extern "C" enum rc dcpgpu_scan_resident(struct dcpgpu_db *db, struct dcpgpu_seqs *sq,
                                         struct dcpgpu_params const *prm, struct dcpgpu_result **out)
@@ -692,15 +702,15 @@ extern "C" enum rc dcpgpu_scan_resident(struct dcpgpu_db *db, struct dcpgpu_seqs
         }
     }
     DevBuf b_spec, b_rows, b_wcodes, b_counter, b_nhits;
-    CU_TRY(cudaMalloc(&b_spec.p, spec.size() * sizeof(float)));
+    CU_TRY(b_spec.alloc(spec.size() * sizeof(float), st));
     const uint64_t total_recs = sq->total + nseq;
-    CU_TRY(cudaMalloc(&b_rows.p, (size_t)n_null * total_recs * sizeof(RowRec)));
-    CU_TRY(cudaMalloc(&b_wcodes.p, total_recs * sizeof(uint16_t)));
-    CU_TRY(cudaMalloc(&b_counter.p, (kMaxQ + 1) * sizeof(unsigned long long)));
-    CU_TRY(cudaMalloc(&b_nhits.p, 2 * sizeof(unsigned long long)));
-    CU_TRY(cudaMalloc(&res->d_alt, npairs * sizeof(float)));
-    CU_TRY(cudaMalloc(&res->d_null, (size_t)nseq * n_null * sizeof(float)));
-    CU_TRY(cudaMalloc(&res->d_hit, npairs));
+    CU_TRY(b_rows.alloc((size_t)n_null * total_recs * sizeof(RowRec), st));
+    CU_TRY(b_wcodes.alloc(total_recs * sizeof(uint16_t), st));
+    CU_TRY(b_counter.alloc((kMaxQ + 1) * sizeof(unsigned long long), st));
+    CU_TRY(b_nhits.alloc(2 * sizeof(unsigned long long), st));
+    CU_TRY(cudaMallocAsync(&res->d_alt, npairs * sizeof(float), st));
+    CU_TRY(cudaMallocAsync(&res->d_null, (size_t)nseq * n_null * sizeof(float), st));
+    CU_TRY(cudaMallocAsync(&res->d_hit, npairs, st));
 
     cudaEvent_t ev[5];
     for (auto &e : ev) CU_TRY(cudaEventCreate(&e));
@@ -754,7 +764,7 @@ extern "C" enum rc dcpgpu_scan_resident(struct dcpgpu_db *db, struct dcpgpu_seqs
     if (nhits)
     {
         DevBuf b_list;
-        CU_TRY(cudaMalloc(&b_list.p, nhits * sizeof(unsigned long long)));
+        CU_TRY(b_list.alloc(nhits * sizeof(unsigned long long), st));
         k_collect<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(res->d_hit, npairs,
                                                                     b_nhits.as<unsigned long long>() + 1,
                                                                     b_list.as<unsigned long long>());
@@ -765,8 +775,8 @@ extern "C" enum rc dcpgpu_scan_resident(struct dcpgpu_db *db, struct dcpgpu_seqs
         d2h += nhits * sizeof(unsigned long long);
         std::sort(list.begin(), list.end()); /* (sequence, profile) order, independent of scheduling */
         DevBuf b_ga, b_gn;
-        CU_TRY(cudaMalloc(&b_ga.p, nhits * sizeof(float)));
-        CU_TRY(cudaMalloc(&b_gn.p, nhits * sizeof(float)));
+        CU_TRY(b_ga.alloc(nhits * sizeof(float), st));
+        CU_TRY(b_gn.alloc(nhits * sizeof(float), st));
         CU_TRY(cudaMemcpyAsync(b_list.p, list.data(), nhits * sizeof(unsigned long long), cudaMemcpyHostToDevice, st));
         k_gather<<<(unsigned)((nhits + 255) / 256), 256, 0, st>>>(b_list.as<unsigned long long>(), nhits, res->d_alt,
                                                                   res->d_null, db->d_metas, nprof, n_null,
@@ -875,6 +885,7 @@ extern "C" void dcpgpu_result_del(struct dcpgpu_result *r)
 {
     if (!r) return;
     cudaSetDevice(r->db->device);
-    cudaFree(r->d_alt), cudaFree(r->d_null), cudaFree(r->d_hit);
+    cudaStream_t st = r->db->stream;
+    cudaFreeAsync(r->d_alt, st), cudaFreeAsync(r->d_null, st), cudaFreeAsync(r->d_hit, st);
     delete r;
 }

@@ -77,6 +77,8 @@ struct dcpgpu_db
     ProfMeta *d_metas = nullptr;
     uint32_t *d_class[kMaxQ + 1] = {nullptr};
     uint64_t device_bytes = 0;
+    void *h_stage = nullptr; /* pinned staging for sequence uploads (grow-only) */
+    size_t h_stage_cap = 0;
 };
 
 struct dcpgpu_seqs
@@ -113,6 +115,26 @@ struct dcpgpu_result
     dcpgpu_timing timing = {};
 };
 
+
+/* Scratch device buffer of one scan: stream-ordered allocation from the device's default memory
+ * pool (release threshold raised at dcpgpu_db_new, so repeated scans reuse the same blocks and
+ * never pay cudaMalloc/cudaFree). */
+struct DevBuf
+{
+    void *p = nullptr;
+    cudaStream_t st = nullptr;
+    cudaError_t alloc(size_t bytes, cudaStream_t stream)
+    {
+        st = stream;
+        return cudaMallocAsync(&p, bytes ? bytes : 1, stream);
+    }
+    ~DevBuf()
+    {
+        if (p) cudaFreeAsync(p, st);
+    }
+    template <class T>
+    T *as() { return (T *)p; }
+};
 
 /* dcp_trace.cu */
 enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const RowRec *d_rows,

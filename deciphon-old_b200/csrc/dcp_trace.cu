@@ -403,14 +403,6 @@ __global__ void k_walk(const ProfMeta *__restrict__ metas, const SeqMeta *__rest
         }
 }
 
-struct DevBuf
-{
-    void *p = nullptr;
-    ~DevBuf() { cudaFree(p); }
-    template <class T>
-    T *as() { return (T *)p; }
-};
-
 template <int Q>
 void launch_trace(cudaStream_t st, uint32_t njobs, const dcpgpu_db *db, const dcpgpu_seqs *sq, const RowRec *rows,
                   const uint16_t *wcodes, const float *spec, const TraceJob *jobs, uint16_t *cell_bp, uint32_t *row_bp, float *alt)
@@ -429,7 +421,7 @@ enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const
     /* backpointer budget per batch */
     size_t free_b = 0, total_b = 0;
     CU_TRY(cudaMemGetInfo(&free_b, &total_b));
-    const size_t budget = std::max<size_t>(free_b / 2, (size_t)64 << 20);
+    const size_t budget = std::min<size_t>(std::max<size_t>(free_b / 2, (size_t)64 << 20), (size_t)16 << 30);
 
     const std::vector<float> &score_alt = res->hit_alt; /* score pass result of each hit */
 
@@ -462,13 +454,13 @@ enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const
         for (uint32_t i = 0; i < nj; ++i) sorted[i] = jobs[order[i]];
 
         DevBuf b_jobs, b_cells, b_rows, b_alt, b_n, b_off, b_err, b_steps;
-        CU_TRY(cudaMalloc(&b_jobs.p, nj * sizeof(TraceJob)));
-        CU_TRY(cudaMalloc(&b_cells.p, cells * sizeof(uint16_t)));
-        CU_TRY(cudaMalloc(&b_rows.p, rowsz * sizeof(uint32_t)));
-        CU_TRY(cudaMalloc(&b_alt.p, nj * sizeof(float)));
-        CU_TRY(cudaMalloc(&b_n.p, nj * sizeof(uint32_t)));
-        CU_TRY(cudaMalloc(&b_off.p, nj * sizeof(uint64_t)));
-        CU_TRY(cudaMalloc(&b_err.p, sizeof(uint32_t)));
+        CU_TRY(b_jobs.alloc(nj * sizeof(TraceJob), st));
+        CU_TRY(b_cells.alloc(cells * sizeof(uint16_t), st));
+        CU_TRY(b_rows.alloc(rowsz * sizeof(uint32_t), st));
+        CU_TRY(b_alt.alloc(nj * sizeof(float), st));
+        CU_TRY(b_n.alloc(nj * sizeof(uint32_t), st));
+        CU_TRY(b_off.alloc(nj * sizeof(uint64_t), st));
+        CU_TRY(b_err.alloc(sizeof(uint32_t), st));
         CU_TRY(cudaMemcpyAsync(b_jobs.p, sorted.data(), nj * sizeof(TraceJob), cudaMemcpyHostToDevice, st));
         CU_TRY(cudaMemsetAsync(b_err.p, 0, sizeof(uint32_t), st));
         for (uint32_t a = 0; a < nj;)
@@ -510,7 +502,7 @@ enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const
             if (memcmp(&talt[i], &score_alt[hit], sizeof(float)) != 0)
                 return dcp_error(RC_EFAIL, "trace pass and score pass disagree on the alt log-likelihood");
         }
-        CU_TRY(cudaMalloc(&b_steps.p, std::max<uint64_t>(tot, 1) * sizeof(dcp_step)));
+        CU_TRY(b_steps.alloc(std::max<uint64_t>(tot, 1) * sizeof(dcp_step), st));
         CU_TRY(cudaMemcpyAsync(b_off.p, off.data(), nj * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
         k_walk<<<(nj + 63) / 64, 64, 0, st>>>(db->d_metas, sq->d_metas, b_jobs.as<TraceJob>(), nj,
                                               b_cells.as<uint16_t>(), b_rows.as<uint32_t>(), 1, b_n.as<uint32_t>(),
