@@ -312,7 +312,7 @@ k_score(const float *__restrict__ emis, const float *__restrict__ trans, const P
         uint32_t prof = class_profs[pi];
         ProfMeta pm = metas[prof];
         NodeParams<Q> p;
-        load_params<Q>(p, trans + pm.trans_off, lane);
+        load_params<Q>(p, trans + pm.trans_off, 32 * Q, lane * Q);
         const float *emis_lane = emis + pm.emis_off + lane * 4;
         const RowRec *rows_t = rows + (size_t)pm.null_id * total_recs;
         uint32_t s_end = min(nseq, (ci + 1) * kSeqChunk);
@@ -323,6 +323,226 @@ k_score(const float *__restrict__ emis, const float *__restrict__ trans, const P
                                     spec + (size_t)s * 16, lane);
             if (lane == 0) alt_out[(size_t)s * nprof + prof] = T;
         }
+    }
+}
+
+/* ----------------------------------------------------------------------------------------- */
+/* alt Viterbi, score pass, profiles of 257..2048 nodes: W warps (one block) per pair         */
+/* ----------------------------------------------------------------------------------------- */
+/*
+ * Same recurrence, same fp32 operation order and the same lane layout as k_score<8>; node
+ * k-1 = warp * 256 + lane * 8 + sub.  What a single warp exchanges with shuffles is exchanged
+ * between warps through shared memory, three block barriers per row:
+ *   A   V_M / V_I of each warp's last node, per-warp max of V_M (-> E), V_N / V_J of warp 0
+ *   B   each warp's last D after its local chain
+ *   C   __syncthreads_or: did any warp's last D rise when the left neighbour's D came in?
+ *       (repeat B, C while it did -- exact lazy propagation, as inside a warp)
+ */
+struct MwShared
+{
+    float vm_last[2][kMaxW], vi_last[2][kMaxW], e_warp[2][kMaxW];
+    float d_last[2][kMaxW];
+    float v_spec[2][4]; /* V_N, V_J, V_C of the row */
+    unsigned long long item;
+};
+
+template <int W, int R>
+__device__ __forceinline__ void mw_row(float (&tm)[5][8], float (&ti)[5][8], float (&tx)[5],
+                                       const NodeParams<8> &p, RowState<8> &rs,
+                                       const float *__restrict__ emis_lane, const RowRec *__restrict__ rec_next,
+                                       const uint16_t *__restrict__ w_next2, int warp, int lane, int par,
+                                       MwShared &sh, float NB, float JB, float EB, float cE, float cX,
+                                       float &E_out, float &vC_out)
+{
+    constexpr int Q = 8;
+    constexpr int ROW = 256 * W;
+    constexpr int S1 = (R + 4) % 5, S2 = (R + 3) % 5, S3 = (R + 2) % 5, S4 = (R + 1) % 5, S5 = R;
+
+    float vm[Q], vi[Q];
+#pragma unroll
+    for (int i = 0; i < Q; ++i)
+        vm[i] = fmaxf(max3(tm[S1][i] + rs.em[0][i], tm[S2][i] + rs.em[1][i], tm[S3][i] + rs.em[2][i]),
+                      fmaxf(tm[S4][i] + rs.em[3][i], tm[S5][i] + rs.em[4][i]));
+#pragma unroll
+    for (int i = 0; i < Q; ++i)
+        vi[i] = fmaxf(max3(ti[S1][i] + rs.eI[0], ti[S2][i] + rs.eI[1], ti[S3][i] + rs.eI[2]),
+                      fmaxf(ti[S4][i] + rs.eI[3], ti[S5][i] + rs.eI[4]));
+    /* N, J, C live in lanes 0..2 of warp 0 */
+    float vx = fmaxf(max3(tx[S1] + rs.eN[0], tx[S2] + rs.eN[1], tx[S3] + rs.eN[2]),
+                     fmaxf(tx[S4] + rs.eN[3], tx[S5] + rs.eN[4]));
+
+    /* next row's loads (same software pipeline as the single-warp kernel) */
+    uint32_t code[5];
+    codes_of(rs.w1, code);
+    load_emis_part<Q, 3, 5, ROW>(rs.em, emis_lane, code);
+    load_row_insert(rec_next, rs.eI);
+    if (warp == 0 && lane < 3) load_row_special(rec_next, rs.eN);
+    rs.w1 = rs.w2;
+    rs.w2 = __ldg(w_next2);
+
+    float eloc = vm[0];
+#pragma unroll
+    for (int i = 1; i < Q; ++i) eloc = fmaxf(eloc, vm[i]);
+    float ew = warp_max(eloc);
+    if (lane == 31) sh.vm_last[par][warp] = vm[Q - 1], sh.vi_last[par][warp] = vi[Q - 1], sh.e_warp[par][warp] = ew;
+    if (warp == 0 && lane < 3) sh.v_spec[par][lane] = vx;
+    float vm_prev = __shfl_up_sync(FULL, vm[Q - 1], 1);
+    float vi_prev = __shfl_up_sync(FULL, vi[Q - 1], 1);
+    load_emis_part<Q, 0, 3, ROW>(rs.em, emis_lane, code);
+    __syncthreads(); /* A */
+
+    if (lane == 0)
+    {
+        vm_prev = warp ? sh.vm_last[par][warp - 1] : NEG_INF;
+        vi_prev = warp ? sh.vi_last[par][warp - 1] : NEG_INF;
+    }
+    float E = sh.e_warp[par][0];
+#pragma unroll
+    for (int w = 1; w < W; ++w) E = fmaxf(E, sh.e_warp[par][w]);
+    const float vN = sh.v_spec[par][0], vJ = sh.v_spec[par][1], vC = sh.v_spec[par][2];
+
+    /* D chain inside the warp with no carry from the left warp */
+    float d[Q];
+    d[0] = vm_prev + p.MD[0];
+#pragma unroll
+    for (int i = 1; i < Q; ++i) d[i] = fmaxf(vm[i - 1] + p.MD[i], d[i - 1] + p.DD[i]);
+    float din;
+    for (;;)
+    {
+        float old = d[Q - 1];
+        din = __shfl_up_sync(FULL, old, 1);
+        if (lane == 0) din = NEG_INF;
+        float x = din;
+#pragma unroll
+        for (int i = 0; i < Q; ++i)
+        {
+            x = x + p.DD[i];
+            d[i] = fmaxf(d[i], x);
+            x = d[i];
+        }
+        if (!__any_sync(FULL, d[Q - 1] > old)) break;
+    }
+    /* carries between warps */
+    float din0 = NEG_INF; /* D of the last node of the warp to the left */
+    for (int round = 0;; ++round)
+    {
+        const int b = round & 1;
+        if (lane == 31) sh.d_last[b][warp] = d[Q - 1];
+        __syncthreads(); /* B */
+        din0 = warp ? sh.d_last[b][warp - 1] : NEG_INF;
+        const float before = __shfl_sync(FULL, d[Q - 1], 31);
+        for (;;)
+        {
+            float old = d[Q - 1];
+            din = __shfl_up_sync(FULL, old, 1);
+            if (lane == 0) din = din0;
+            float x = din;
+#pragma unroll
+            for (int i = 0; i < Q; ++i)
+            {
+                x = x + p.DD[i];
+                d[i] = fmaxf(d[i], x);
+                x = d[i];
+            }
+            if (!__any_sync(FULL, d[Q - 1] > old)) break;
+        }
+        const float after = __shfl_sync(FULL, d[Q - 1], 31);
+        if (!__syncthreads_or(after > before)) break; /* C */
+    }
+
+    float B = max3(vN + NB, vJ + JB, E + EB);
+    tx[R] = fmaxf(E + cE, vx + cX);
+#pragma unroll
+    for (int i = 0; i < Q; ++i)
+    {
+        float pm = i == 0 ? vm_prev : vm[i - 1];
+        float pi = i == 0 ? vi_prev : vi[i - 1];
+        float pd = i == 0 ? din : d[i - 1];
+        tm[R][i] = fmaxf(fmaxf(B + p.ent[i], pm + p.MM[i]), fmaxf(pi + p.IM[i], pd + p.DM[i]));
+        ti[R][i] = fmaxf(vm[i] + p.MI[i], vi[i] + p.II[i]);
+    }
+    E_out = E;
+    vC_out = vC;
+}
+
+template <int W>
+__global__ void __launch_bounds__(W * 32, 8 / W)
+k_score_mw(const float *__restrict__ emis, const float *__restrict__ trans, const ProfMeta *__restrict__ metas,
+           const uint32_t *__restrict__ class_profs, uint32_t n_class_profs, const SeqMeta *__restrict__ seqs,
+           uint32_t nseq, uint64_t total_recs, const RowRec *__restrict__ rows,
+           const uint16_t *__restrict__ wcodes, const float *__restrict__ spec, float *__restrict__ alt_out,
+           uint32_t nprof, unsigned long long *__restrict__ counter)
+{
+    constexpr int Q = 8;
+    constexpr int ROW = 256 * W;
+    __shared__ MwShared sh;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned long long n_items = (unsigned long long)n_class_profs * nseq;
+    for (;;)
+    {
+        if (threadIdx.x == 0) sh.item = atomicAdd(counter, 1ULL);
+        __syncthreads();
+        const unsigned long long item = sh.item;
+        __syncthreads();
+        if (item >= n_items) break;
+        const uint32_t prof = class_profs[item / nseq], s = (uint32_t)(item % nseq);
+        const ProfMeta pm = metas[prof];
+        NodeParams<Q> p;
+        load_params<Q>(p, trans + pm.trans_off, 256 * W, warp * 256 + lane * Q);
+        const float *emis_lane = emis + pm.emis_off + warp * 256 + lane * 4;
+        const SeqMeta sm = seqs[s];
+        const RowRec *recs = rows + (size_t)pm.null_id * total_recs + sm.rec_off;
+        const uint16_t *wc = wcodes + sm.rec_off;
+        const float *sp = spec + (size_t)s * 16;
+        const uint32_t L = sm.len;
+
+        const float NN = sp[0], CC = sp[1], JJ = sp[2], NB = sp[3], CT = sp[4], JB = sp[5];
+        const float ET = sp[9], ECC = sp[10], EB = sp[11], EJJ = sp[12];
+        const float cE = lane == 0 ? NEG_INF : (lane == 1 ? EJJ : ECC);
+        const float cX = lane == 0 ? NN : (lane == 1 ? JJ : CC);
+
+        float tm[5][Q], ti[5][Q], tx[5];
+#pragma unroll
+        for (int r = 0; r < 5; ++r)
+        {
+            tx[r] = NEG_INF;
+#pragma unroll
+            for (int i = 0; i < Q; ++i) tm[r][i] = NEG_INF, ti[r][i] = NEG_INF;
+        }
+#pragma unroll
+        for (int i = 0; i < Q; ++i) tm[4][i] = NB + p.ent[i];
+        tx[4] = (warp == 0 && lane == 0) ? NN : NEG_INF;
+
+        RowState<Q> rs;
+#pragma unroll
+        for (int l = 0; l < 5; ++l) rs.eN[l] = NEG_INF;
+        {
+            uint32_t code[5];
+            codes_of(__ldg(wc + 1), code);
+            load_emis<Q, ROW>(rs.em, emis_lane, code);
+        }
+        load_row_insert(recs + 1, rs.eI);
+        if (warp == 0 && lane < 3) load_row_special(recs + 1, rs.eN);
+        rs.w1 = __ldg(wc + min(2u, L));
+        rs.w2 = __ldg(wc + min(3u, L));
+
+        float E = NEG_INF, vC = NEG_INF;
+        uint32_t j = 1;
+#define MW_ARGS(jj) recs + min((uint32_t)(jj) + 1u, L), wc + min((uint32_t)(jj) + 3u, L), warp, lane, (int)((jj)&1u), sh
+        for (; j + 4 <= L; j += 5)
+        {
+            mw_row<W, 0>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j), NB, JB, EB, cE, cX, E, vC);
+            mw_row<W, 1>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 1), NB, JB, EB, cE, cX, E, vC);
+            mw_row<W, 2>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 2), NB, JB, EB, cE, cX, E, vC);
+            mw_row<W, 3>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 3), NB, JB, EB, cE, cX, E, vC);
+            mw_row<W, 4>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 4), NB, JB, EB, cE, cX, E, vC);
+        }
+        if (j <= L) mw_row<W, 0>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j), NB, JB, EB, cE, cX, E, vC);
+        if (j + 1 <= L) mw_row<W, 1>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 1), NB, JB, EB, cE, cX, E, vC);
+        if (j + 2 <= L) mw_row<W, 2>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 2), NB, JB, EB, cE, cX, E, vC);
+        if (j + 3 <= L) mw_row<W, 3>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 3), NB, JB, EB, cE, cX, E, vC);
+#undef MW_ARGS
+        if (threadIdx.x == 0) alt_out[(size_t)s * nprof + prof] = fmaxf(E + ET, vC + CT);
     }
 }
 
@@ -437,8 +657,8 @@ extern "C" enum rc dcpgpu_db_add(struct dcpgpu_db *db, struct protein_profile co
 {
     if (db->committed) return dcp_error(RC_EFAIL, "database already committed");
     if (prof->core_size == 0) return dcp_error(RC_EINVAL, "profile has not been absorbed");
-    if (prof->core_size > 32 * kMaxQ)
-        return dcp_error(RC_EINVAL, "core_size > 256 is not supported by this build yet");
+    if (prof->core_size > 32 * kMaxQ * kMaxW)
+        return dcp_error(RC_EINVAL, "core_size > 2048 is not supported by this build yet");
     if (db->epsilon >= 0.0f && db->epsilon != prof->cfg.epsilon)
         return dcp_error(RC_EINVAL, "all profiles of a database share one epsilon");
     /* the score pass takes E[j] = max_k V_Mk[j]; that needs delete scores to be log-probabilities */
@@ -478,17 +698,19 @@ extern "C" enum rc dcpgpu_db_commit(struct dcpgpu_db *db)
         uint32_t M = db->profs[i]->core_size;
         /* nodes per lane.  193..224 nodes would fit 7 per lane, but k_score<7> does not fit the
          * register file without spilling in its straight-line form; 8 per lane (7 idle lanes) measured
-         * faster: 515 vs 489 GCUPS at M = 200. */
-        uint32_t Q = (M + 31) / 32;
+         * faster: 515 vs 489 GCUPS at M = 200.  Above 256 nodes W warps share one pair, 8 nodes per lane. */
+        uint32_t Q = (M + 31) / 32, W = 1;
         if (Q == 7) Q = 8;
+        if (Q > 8) Q = 8, W = (M + 255) / 256;
         uint32_t QP = Q <= 4 ? 4 : 8;
         ProfMeta &m = db->metas[i];
         m.M = M, m.Q = Q, m.QP = QP, m.null_id = db->null_id[i];
+        m.W = W, m.cls = W == 1 ? Q : kMaxQ + W;
         m.emis_off = emis_floats;
         m.trans_off = trans_floats;
-        emis_floats += (uint64_t)kTab * 32 * QP;
-        trans_floats += (uint64_t)8 * 32 * Q;
-        db->class_list[Q].push_back((uint32_t)i);
+        emis_floats += (uint64_t)kTab * 32 * QP * W;
+        trans_floats += (uint64_t)8 * 32 * Q * W;
+        db->class_list[m.cls].push_back((uint32_t)i);
     }
     CU_TRY(cudaMalloc(&db->d_emis, emis_floats * sizeof(float)));
     CU_TRY(cudaMalloc(&db->d_trans, trans_floats * sizeof(float)));
@@ -499,7 +721,7 @@ extern "C" enum rc dcpgpu_db_commit(struct dcpgpu_db *db)
                        nprof * sizeof(ProfMeta);
 
     /* transpose per profile into pinned staging, upload in large pieces */
-    const size_t stage_floats = (size_t)kTab * 32 * 8;
+    const size_t stage_floats = (size_t)kTab * 32 * 8 * kMaxW;
     float *stage = nullptr;
     CU_TRY(cudaMallocHost(&stage, stage_floats * sizeof(float)));
     std::vector<float> tr;
@@ -507,19 +729,19 @@ extern "C" enum rc dcpgpu_db_commit(struct dcpgpu_db *db)
     {
         const ProfMeta &m = db->metas[i];
         const protein_profile *p = db->profs[i];
-        const uint32_t ROW = 32 * m.QP;
+        const uint32_t ROW = 32 * m.QP * m.W, PER_WARP = 32 * m.Q;
         for (size_t x = 0; x < (size_t)kTab * ROW; ++x) stage[x] = NEG_INF;
         for (uint32_t k = 0; k < m.M; ++k)
         {
-            uint32_t lane = k / m.Q, sub = k % m.Q;
+            uint32_t warp = k / PER_WARP, lane = (k % PER_WARP) / m.Q, sub = k % m.Q;
             const float *src = p->match_emission + (size_t)k * kTab;
-            /* [code][half][lane][4]: node k = lane*Q + sub sits in half sub/4 at float sub%4 */
-            const size_t at = (size_t)(sub / 4) * 128 + (size_t)lane * 4 + (sub % 4);
+            /* [code][warp][half][lane][4]: node k sits in half sub/4 at float sub%4 of its lane */
+            const size_t at = (size_t)warp * 32 * m.QP + (size_t)(sub / 4) * 128 + (size_t)lane * 4 + (sub % 4);
             for (int c = 0; c < kTab; ++c) stage[(size_t)c * ROW + at] = src[c];
         }
         CU_TRY(cudaMemcpyAsync(db->d_emis + m.emis_off, stage, (size_t)kTab * ROW * sizeof(float),
                                cudaMemcpyHostToDevice, db->stream));
-        const uint32_t NP = 32 * m.Q;
+        const uint32_t NP = 32 * m.Q * m.W;
         tr.assign((size_t)8 * NP, NEG_INF);
         for (uint32_t k = 1; k <= m.M; ++k) /* node k, slot k-1 */
         {
@@ -546,7 +768,7 @@ extern "C" enum rc dcpgpu_db_commit(struct dcpgpu_db *db)
         CU_TRY(cudaMemcpy(db->d_null_tabs + t * kTab, db->null_tabs[t].data(), kTab * sizeof(float),
                           cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(db->d_ins_tab, db->profs[0]->insert_emission, kTab * sizeof(float), cudaMemcpyHostToDevice));
-    for (int q = 1; q <= kMaxQ; ++q)
+    for (int q = 1; q <= kNumClasses; ++q)
         if (!db->class_list[q].empty())
         {
             CU_TRY(cudaMalloc(&db->d_class[q], db->class_list[q].size() * sizeof(uint32_t)));
@@ -567,7 +789,7 @@ extern "C" void dcpgpu_db_del(struct dcpgpu_db *db)
     for (auto *p : db->profs) protein_profile_del(p);
     cudaFree(db->d_emis), cudaFree(db->d_trans), cudaFree(db->d_metas);
     cudaFree(db->d_null_tabs), cudaFree(db->d_ins_tab);
-    for (int q = 0; q <= kMaxQ; ++q) cudaFree(db->d_class[q]);
+    for (int q = 0; q <= kNumClasses; ++q) cudaFree(db->d_class[q]);
     if (db->h_stage) cudaFreeHost(db->h_stage);
     if (db->stream)
     {
@@ -706,7 +928,7 @@ extern "C" enum rc dcpgpu_scan_resident(struct dcpgpu_db *db, struct dcpgpu_seqs
     const uint64_t total_recs = sq->total + nseq;
     CU_TRY(b_rows.alloc((size_t)n_null * total_recs * sizeof(RowRec), st));
     CU_TRY(b_wcodes.alloc(total_recs * sizeof(uint16_t), st));
-    CU_TRY(b_counter.alloc((kMaxQ + 1) * sizeof(unsigned long long), st));
+    CU_TRY(b_counter.alloc((kNumClasses + 1) * sizeof(unsigned long long), st));
     CU_TRY(b_nhits.alloc(2 * sizeof(unsigned long long), st));
     CU_TRY(cudaMallocAsync(&res->d_alt, npairs * sizeof(float), st));
     CU_TRY(cudaMallocAsync(&res->d_null, (size_t)nseq * n_null * sizeof(float), st));
@@ -718,7 +940,7 @@ extern "C" enum rc dcpgpu_scan_resident(struct dcpgpu_db *db, struct dcpgpu_seqs
 
     CU_TRY(cudaEventRecord(ev[0], st));
     CU_TRY(cudaMemcpyAsync(b_spec.p, spec.data(), spec.size() * sizeof(float), cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaMemsetAsync(b_counter.p, 0, (kMaxQ + 1) * sizeof(unsigned long long), st));
+    CU_TRY(cudaMemsetAsync(b_counter.p, 0, (kNumClasses + 1) * sizeof(unsigned long long), st));
     CU_TRY(cudaMemsetAsync(b_nhits.p, 0, 2 * sizeof(unsigned long long), st));
     k_rows<<<nseq, 128, 0, st>>>(sq->d_bases, sq->d_metas, nseq, db->d_null_tabs, db->d_ins_tab, n_null, total_recs,
                                  b_rows.as<RowRec>(), b_wcodes.as<uint16_t>());
@@ -746,6 +968,28 @@ extern "C" enum rc dcpgpu_scan_resident(struct dcpgpu_db *db, struct dcpgpu_seqs
             LAUNCH(1) LAUNCH(2) LAUNCH(3) LAUNCH(4) LAUNCH(5) LAUNCH(6) LAUNCH(7) LAUNCH(8)
         }
 #undef LAUNCH
+        launches++;
+        for (uint32_t id : db->class_list[q]) cells += (uint64_t)db->metas[id].M * sq->total;
+    }
+    for (int w = 2; w <= kMaxW; ++w)
+    {
+        const int q = kMaxQ + w;
+        if (db->class_list[q].empty()) continue;
+        uint32_t n_class = (uint32_t)db->class_list[q].size();
+        unsigned long long *ctr = b_counter.as<unsigned long long>() + q;
+        const int mw_blocks = db->sm_count * (8 / w);
+#define LAUNCH_MW(WW)                                                                                          \
+    case WW:                                                                                                   \
+        k_score_mw<WW><<<mw_blocks, WW * 32, 0, st>>>(db->d_emis, db->d_trans, db->d_metas, db->d_class[q],    \
+                                                      n_class, sq->d_metas, nseq, total_recs,                 \
+                                                      b_rows.as<RowRec>(), b_wcodes.as<uint16_t>(),           \
+                                                      b_spec.as<float>(), res->d_alt, nprof, ctr);            \
+        break;
+        switch (w)
+        {
+            LAUNCH_MW(2) LAUNCH_MW(3) LAUNCH_MW(4) LAUNCH_MW(5) LAUNCH_MW(6) LAUNCH_MW(7) LAUNCH_MW(8)
+        }
+#undef LAUNCH_MW
         launches++;
         for (uint32_t id : db->class_list[q]) cells += (uint64_t)db->metas[id].M * sq->total;
     }

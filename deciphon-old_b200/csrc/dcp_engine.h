@@ -15,6 +15,8 @@
 
 constexpr int kTab = DCP_FRAME_TABLE_SIZE;
 constexpr int kMaxQ = 8;          /* nodes per lane, single-warp classes cover M <= 256 */
+constexpr int kMaxW = 8;          /* warps per pair in the multi-warp classes: M <= 8 * 256 = 2048 */
+constexpr int kNumClasses = kMaxQ + kMaxW; /* class c: 1..8 = single warp with Q = c; 8 + W (W = 2..8) = W warps, Q = 8 */
 constexpr int kWarpsPerBlock = 8; /* k_score block = 8 independent warps */
 constexpr int kSeqChunk = 4;      /* sequences per work item */
 
@@ -48,6 +50,7 @@ static_assert(sizeof(RowRec) == 64, "row record is one 64-byte line");
 struct ProfMeta
 {
     uint32_t M, Q, QP, null_id;
+    uint32_t W, cls; /* warps per pair; kernel class */
     uint64_t emis_off;  /* floats into d_emis */
     uint64_t trans_off; /* floats into d_trans */
 };
@@ -72,10 +75,10 @@ struct dcpgpu_db
     std::vector<std::vector<float>> null_tabs;
     std::vector<uint32_t> null_id;
     std::vector<ProfMeta> metas;
-    std::vector<uint32_t> class_list[kMaxQ + 1]; /* profile ids by Q */
+    std::vector<uint32_t> class_list[kNumClasses + 1]; /* profile ids by kernel class */
     float *d_emis = nullptr, *d_trans = nullptr, *d_null_tabs = nullptr, *d_ins_tab = nullptr;
     ProfMeta *d_metas = nullptr;
-    uint32_t *d_class[kMaxQ + 1] = {nullptr};
+    uint32_t *d_class[kNumClasses + 1] = {nullptr};
     uint64_t device_bytes = 0;
     void *h_stage = nullptr; /* pinned staging for sequence uploads (grow-only) */
     size_t h_stage_cap = 0;

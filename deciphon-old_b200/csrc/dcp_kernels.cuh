@@ -22,14 +22,14 @@ __device__ __forceinline__ float warp_max(float x)
 
 __device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
+/* tr = [8 params][NP node slots]; this lane owns slots first .. first+Q-1 */
 template <int Q>
-__device__ __forceinline__ void load_params(NodeParams<Q> &p, const float *__restrict__ tr, int lane)
+__device__ __forceinline__ void load_params(NodeParams<Q> &p, const float *__restrict__ tr, int NP, int first)
 {
-    constexpr int NP = 32 * Q;
 #pragma unroll
     for (int i = 0; i < Q; ++i)
     {
-        int n = lane * Q + i;
+        int n = first + i;
         p.MM[i] = __ldg(tr + 0 * NP + n);
         p.IM[i] = __ldg(tr + 1 * NP + n);
         p.DM[i] = __ldg(tr + 2 * NP + n);
@@ -73,12 +73,10 @@ __device__ __forceinline__ void load_row_special(const RowRec *__restrict__ r, f
  * emis_lane = table base + lane * 4.  (L1 eviction hints -- evict_last on the 1-3 nt lines,
  * no_allocate on the 5 nt lines -- were measured and did not help: 381 vs 399 GCUPS.)
  */
-template <int Q, int L0, int L1>
+template <int Q, int L0, int L1, int ROW = 32 * (Q <= 4 ? 4 : 8)>
 __device__ __forceinline__ void load_emis_part(float (&em)[5][Q], const float *__restrict__ emis_lane,
                                                const uint32_t (&code)[5])
 {
-    constexpr int QP = Q <= 4 ? 4 : 8;
-    constexpr int ROW = 32 * QP;
 #pragma unroll
     for (int l = L0; l < L1; ++l)
     {
@@ -120,11 +118,11 @@ __device__ __forceinline__ void load_emis_part(float (&em)[5][Q], const float *_
     }
 }
 
-template <int Q>
+template <int Q, int ROW = 32 * (Q <= 4 ? 4 : 8)>
 __device__ __forceinline__ void load_emis(float (&em)[5][Q], const float *__restrict__ emis_lane,
                                           const uint32_t (&code)[5])
 {
-    load_emis_part<Q, 0, 5>(em, emis_lane, code);
+    load_emis_part<Q, 0, 5, ROW>(em, emis_lane, code);
 }
 
 #endif

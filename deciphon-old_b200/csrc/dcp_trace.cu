@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(128) k_trace(const float *__restrict__ emis, c
     ProfMeta pm = metas[tj_.prof];
     SeqMeta sm = seqs[tj_.seq];
     NodeParams<Q> p;
-    load_params<Q>(p, trans + pm.trans_off, lane);
+    load_params<Q>(p, trans + pm.trans_off, 32 * Q, lane * Q);
     const float *emis_lane = emis + pm.emis_off + lane * 4;
     const RowRec *r = rows + (size_t)pm.null_id * total_rows + sm.rec_off + 1; /* record of row 1 */
     const uint16_t *wc = wcodes + sm.rec_off; /* wc[j] = window of row j */
@@ -267,6 +267,275 @@ __global__ void __launch_bounds__(128) k_trace(const float *__restrict__ emis, c
     if (lane == 0) alt_out[job] = T;
 }
 
+/* ----------------------------------------------------------------------------------------- */
+/* traceback pass for hits on profiles of 257..2048 nodes: W warps (one block) per hit        */
+/* ----------------------------------------------------------------------------------------- */
+struct MwTraceShared
+{
+    float pM[2][kMaxW][5], pI[2][kMaxW][5]; /* the five sums of each warp's last node */
+    float d_last[2][kMaxW];
+    float e_best[2][kMaxW];
+    int e_code[2][kMaxW];
+};
+
+/* cell backpointers of a row: [sub-node][warp][lane] */
+template <int W, int R>
+__device__ __forceinline__ void trace_row_mw(float (&tm)[5][8], float (&ti)[5][8], float (&tn)[5], float (&tj)[5],
+                                             float (&tc)[5], const NodeParams<8> &p,
+                                             const float *__restrict__ emis_lane, const RowRec *__restrict__ rec,
+                                             uint32_t wcode, int warp, int lane, int par, MwTraceShared &sh,
+                                             const float *__restrict__ sp, uint16_t *__restrict__ cell_bp,
+                                             uint32_t *__restrict__ row_bp, float &T_out)
+{
+    constexpr int Q = 8;
+    constexpr int ROW = 256 * W;
+    constexpr int S[5] = {(R + 4) % 5, (R + 3) % 5, (R + 2) % 5, (R + 1) % 5, R};
+    const float NN = sp[0], CC = sp[1], JJ = sp[2], NB = sp[3], CT = sp[4], JB = sp[5];
+    const float ET = sp[9], ECC = sp[10], EB = sp[11], EJJ = sp[12];
+    struct { float eI[5], eN[5]; } in;
+    load_row_insert(rec, in.eI);
+    load_row_special(rec, in.eN);
+    uint32_t code[5];
+    codes_of(wcode, code);
+    float em[5][Q];
+    load_emis<Q, ROW>(em, emis_lane, code);
+
+    float sM[Q][5], sI[Q][5];
+#pragma unroll
+    for (int i = 0; i < Q; ++i)
+#pragma unroll
+        for (int l = 0; l < 5; ++l)
+        {
+            sM[i][l] = tm[S[l]][i] + em[l][i];
+            sI[i][l] = ti[S[l]][i] + in.eI[l];
+        }
+    float sN[5], sJ[5], sC[5];
+#pragma unroll
+    for (int l = 0; l < 5; ++l)
+    {
+        sN[l] = tn[S[l]] + in.eN[l];
+        sJ[l] = tj[S[l]] + in.eN[l];
+        sC[l] = tc[S[l]] + in.eN[l];
+    }
+    if (lane == 31)
+#pragma unroll
+        for (int l = 0; l < 5; ++l) sh.pM[par][warp][l] = sM[Q - 1][l], sh.pI[par][warp][l] = sI[Q - 1][l];
+    float pM0[5], pI0[5];
+#pragma unroll
+    for (int l = 0; l < 5; ++l)
+    {
+        pM0[l] = __shfl_up_sync(FULL, sM[Q - 1][l], 1);
+        pI0[l] = __shfl_up_sync(FULL, sI[Q - 1][l], 1);
+    }
+    __syncthreads(); /* A */
+    if (lane == 0)
+#pragma unroll
+        for (int l = 0; l < 5; ++l)
+        {
+            pM0[l] = warp ? sh.pM[par][warp - 1][l] : NEG_INF;
+            pI0[l] = warp ? sh.pI[par][warp - 1][l] : NEG_INF;
+        }
+
+    /* D chain (order: M_{k-1} by length, then D_{k-1}) */
+    float d[Q];
+    int dcode[Q];
+#pragma unroll
+    for (int i = 0; i < Q; ++i)
+    {
+        float best = NEG_INF;
+        int c = 0;
+        if (i == 0)
+            first_max5(pM0, p.MD[0], 0, best, c);
+        else
+        {
+            first_max5(sM[i - 1], p.MD[i], 0, best, c);
+            float x = d[i - 1] + p.DD[i];
+            if (x > best) best = x, c = 5;
+        }
+        d[i] = best, dcode[i] = c;
+    }
+    float din = NEG_INF;
+    for (int round = 0;; ++round)
+    {
+        const int b = round & 1;
+        float din0 = NEG_INF;
+        if (round > 0)
+        {
+            if (lane == 31) sh.d_last[b][warp] = d[Q - 1];
+            __syncthreads(); /* B */
+            din0 = warp ? sh.d_last[b][warp - 1] : NEG_INF;
+        }
+        const float before = __shfl_sync(FULL, d[Q - 1], 31);
+        for (;;)
+        {
+            float old = d[Q - 1];
+            din = __shfl_up_sync(FULL, old, 1);
+            if (lane == 0) din = din0;
+            float x = din;
+#pragma unroll
+            for (int i = 0; i < Q; ++i)
+            {
+                x = x + p.DD[i];
+                if (x > d[i]) d[i] = x, dcode[i] = 5;
+                x = d[i];
+            }
+            if (!__any_sync(FULL, d[Q - 1] > old)) break;
+        }
+        const float after = __shfl_sync(FULL, d[Q - 1], 31);
+        /* round 0 is the warp-local chain: always go on to exchange carries at least once */
+        if (!__syncthreads_or(round == 0 || after > before)) break; /* C */
+    }
+
+    /* E: first max over M_1, M_2, D_2, ... ; warps and lanes hold increasing k */
+    float ebest = NEG_INF;
+    int ecode = 0;
+#pragma unroll
+    for (int i = 0; i < Q; ++i)
+    {
+        int k0 = warp * 256 + lane * Q + i; /* k - 1 */
+        float zero = 0.0f;
+        first_max5(sM[i], zero, k0 * 6, ebest, ecode);
+        if (k0 >= 1)
+        {
+            float v = d[i] + zero;
+            if (v > ebest) ebest = v, ecode = k0 * 6 + 5;
+        }
+    }
+    float ew = warp_max(ebest);
+    unsigned who = __ballot_sync(FULL, ebest == ew);
+    ecode = __shfl_sync(FULL, ecode, who ? __ffs(who) - 1 : 0);
+    if (lane == 0) sh.e_best[par][warp] = ew, sh.e_code[par][warp] = ecode;
+    __syncthreads(); /* D */
+    float E = sh.e_best[par][0];
+    ecode = sh.e_code[par][0];
+#pragma unroll
+    for (int w = 1; w < W; ++w)
+        if (sh.e_best[par][w] > E) E = sh.e_best[par][w], ecode = sh.e_code[par][w];
+
+    /* specials: every warp keeps its own copy of the N/J/C rings (identical values) */
+    float best;
+    int ncode = 0, bcode = 0, jcode = 0, ccode = 0, tcode = 0;
+    best = NEG_INF;
+    first_max5(sN, NN, 1, best, ncode);
+    float tinN = best;
+    best = NEG_INF;
+    first_max5(sN, NB, 1, best, bcode);
+    first_max5(sJ, JB, 6, best, bcode);
+    {
+        float v = E + EB;
+        if (v > best) best = v, bcode = 11;
+    }
+    float B = best;
+    best = E + EJJ, jcode = 0;
+    first_max5(sJ, JJ, 1, best, jcode);
+    float tinJ = best;
+    best = E + ECC, ccode = 0;
+    first_max5(sC, CC, 1, best, ccode);
+    float tinC = best;
+    best = E + ET, tcode = 0;
+    first_max5(sC, CT, 1, best, tcode);
+    T_out = best;
+    tn[R] = tinN, tj[R] = tinJ, tc[R] = tinC;
+    if (threadIdx.x == 0)
+        *row_bp = (uint32_t)ecode | (uint32_t)ncode << 15 | (uint32_t)bcode << 18 | (uint32_t)jcode << 22 |
+                  (uint32_t)ccode << 25 | (uint32_t)tcode << 28;
+
+#pragma unroll
+    for (int i = 0; i < Q; ++i)
+    {
+        float mb = B + p.ent[i];
+        int mcode = 0;
+        if (i == 0)
+        {
+            first_max5(pM0, p.MM[0], 1, mb, mcode);
+            first_max5(pI0, p.IM[0], 6, mb, mcode);
+            float v = din + p.DM[0];
+            if (v > mb) mb = v, mcode = 11;
+        }
+        else
+        {
+            first_max5(sM[i - 1], p.MM[i], 1, mb, mcode);
+            first_max5(sI[i - 1], p.IM[i], 6, mb, mcode);
+            float v = d[i - 1] + p.DM[i];
+            if (v > mb) mb = v, mcode = 11;
+        }
+        float ib = NEG_INF;
+        int icode = 0;
+        first_max5(sM[i], p.MI[i], 0, ib, icode);
+        first_max5(sI[i], p.II[i], 5, ib, icode);
+        tm[R][i] = mb;
+        ti[R][i] = ib;
+        cell_bp[i * (32 * W) + warp * 32 + lane] = (uint16_t)(mcode | icode << 4 | dcode[i] << 8);
+    }
+}
+
+template <int W>
+__global__ void __launch_bounds__(W * 32) k_trace_mw(const float *__restrict__ emis, const float *__restrict__ trans,
+                                                     const ProfMeta *__restrict__ metas,
+                                                     const SeqMeta *__restrict__ seqs, uint64_t total_rows,
+                                                     const RowRec *__restrict__ rows,
+                                                     const uint16_t *__restrict__ wcodes,
+                                                     const float *__restrict__ spec,
+                                                     const TraceJob *__restrict__ jobs, uint32_t njobs,
+                                                     uint16_t *__restrict__ cell_bp, uint32_t *__restrict__ row_bp,
+                                                     float *__restrict__ alt_out)
+{
+    constexpr int Q = 8;
+    __shared__ MwTraceShared sh;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t job = blockIdx.x;
+    if (job >= njobs) return;
+    TraceJob tj_ = jobs[job];
+    ProfMeta pm = metas[tj_.prof];
+    SeqMeta sm = seqs[tj_.seq];
+    NodeParams<Q> p;
+    load_params<Q>(p, trans + pm.trans_off, 256 * W, warp * 256 + lane * Q);
+    const float *emis_lane = emis + pm.emis_off + warp * 256 + lane * 4;
+    const RowRec *r = rows + (size_t)pm.null_id * total_rows + sm.rec_off; /* r[j] = record of row j */
+    const uint16_t *wc = wcodes + sm.rec_off;
+    const float *sp = spec + (size_t)tj_.seq * 16;
+    uint16_t *cb = cell_bp + tj_.cell_off;
+    uint32_t *rb = row_bp + tj_.row_off;
+    const uint32_t L = sm.len;
+    constexpr uint32_t CS = Q * 32 * W;
+
+    float tm[5][Q], ti[5][Q], tn[5], tjr[5], tc[5];
+#pragma unroll
+    for (int s = 0; s < 5; ++s)
+    {
+        tn[s] = tjr[s] = tc[s] = NEG_INF;
+#pragma unroll
+        for (int i = 0; i < Q; ++i) tm[s][i] = NEG_INF, ti[s][i] = NEG_INF;
+    }
+    const float NN = sp[0], NB = sp[3];
+#pragma unroll
+    for (int i = 0; i < Q; ++i)
+    {
+        tm[4][i] = NB + p.ent[i];
+        cb[i * (32 * W) + warp * 32 + lane] = 0;
+    }
+    tn[4] = NN;
+    if (threadIdx.x == 0) rb[0] = 0;
+
+    float T = NEG_INF;
+    uint32_t j = 1;
+#define TR_ARGS(jj) r + (jj), wc[(jj)], warp, lane, (int)((jj)&1u), sh, sp, cb + (size_t)(jj) * CS, rb + (jj), T
+    for (; j + 4 <= L; j += 5)
+    {
+        trace_row_mw<W, 0>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j));
+        trace_row_mw<W, 1>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j + 1));
+        trace_row_mw<W, 2>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j + 2));
+        trace_row_mw<W, 3>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j + 3));
+        trace_row_mw<W, 4>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j + 4));
+    }
+    if (j <= L) trace_row_mw<W, 0>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j));
+    if (j + 1 <= L) trace_row_mw<W, 1>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j + 1));
+    if (j + 2 <= L) trace_row_mw<W, 2>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j + 2));
+    if (j + 3 <= L) trace_row_mw<W, 3>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j + 3));
+#undef TR_ARGS
+    if (threadIdx.x == 0) alt_out[job] = T;
+}
+
 /*
  * Follow the backpointers from (T, row L) to S.  mode 0: count steps; mode 1: write them
  * (reversed, then flipped in place) at steps + step_off[job].
@@ -282,8 +551,8 @@ __global__ void k_walk(const ProfMeta *__restrict__ metas, const SeqMeta *__rest
     uint32_t job = blockIdx.x * blockDim.x + threadIdx.x;
     if (job >= njobs) return;
     TraceJob tj = jobs[job];
-    const uint32_t Q = metas[tj.prof].Q;
-    const uint32_t CS = Q * 32;
+    const uint32_t Q = metas[tj.prof].Q, W = metas[tj.prof].W;
+    const uint32_t CS = Q * 32 * W;
     const uint16_t *cb = cell_bp + tj.cell_off;
     const uint32_t *rb = row_bp + tj.row_off;
     const uint32_t L = seqs[tj.seq].len;
@@ -324,7 +593,7 @@ __global__ void k_walk(const ProfMeta *__restrict__ metas, const SeqMeta *__rest
         if (st == W_M || st == W_I || st == W_D)
         {
             uint32_t node = k - 1;
-            uint16_t c = cb[(size_t)r * CS + (node % Q) * 32 + node / Q];
+            uint16_t c = cb[(size_t)r * CS + (node % Q) * (32 * W) + node / Q]; /* [sub][warp][lane] */
             if (st == W_M)
             {
                 uint32_t m = c & 15;
@@ -434,12 +703,12 @@ enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const
         while (end < nhits)
         {
             const HitRec &h = res->hits[end];
-            uint32_t Q = db->metas[h.prof].Q;
+            uint32_t QW = db->metas[h.prof].Q * db->metas[h.prof].W;
             size_t L1 = (size_t)sq->metas[h.seq].len + 1;
-            size_t need = L1 * Q * 32 * sizeof(uint16_t) + L1 * sizeof(uint32_t);
+            size_t need = L1 * QW * 32 * sizeof(uint16_t) + L1 * sizeof(uint32_t);
             if (!jobs.empty() && (cells * 2 + rowsz * 4 + need > budget)) break;
             jobs.push_back({h.seq, h.prof, cells, rowsz});
-            cells += L1 * Q * 32;
+            cells += L1 * QW * 32;
             rowsz += L1;
             ++end;
         }
@@ -448,7 +717,7 @@ enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const
         std::vector<uint32_t> order(nj);
         for (uint32_t i = 0; i < nj; ++i) order[i] = i;
         std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-            return db->metas[jobs[a].prof].Q < db->metas[jobs[b].prof].Q;
+            return db->metas[jobs[a].prof].cls < db->metas[jobs[b].prof].cls;
         });
         std::vector<TraceJob> sorted(nj);
         for (uint32_t i = 0; i < nj; ++i) sorted[i] = jobs[order[i]];
@@ -465,18 +734,27 @@ enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const
         CU_TRY(cudaMemsetAsync(b_err.p, 0, sizeof(uint32_t), st));
         for (uint32_t a = 0; a < nj;)
         {
-            uint32_t Q = db->metas[sorted[a].prof].Q, b = a;
-            while (b < nj && db->metas[sorted[b].prof].Q == Q) ++b;
+            uint32_t cls = db->metas[sorted[a].prof].cls, b = a;
+            while (b < nj && db->metas[sorted[b].prof].cls == cls) ++b;
 #define LT(QQ)                                                                                                   \
     case QQ:                                                                                                     \
-        launch_trace<QQ>(st, b - a, db, sq, d_rows, d_wcodes, d_spec, b_jobs.as<TraceJob>() + a, b_cells.as<uint16_t>(),   \
-                         b_rows.as<uint32_t>(), b_alt.as<float>() + a);                                          \
+        launch_trace<QQ>(st, b - a, db, sq, d_rows, d_wcodes, d_spec, b_jobs.as<TraceJob>() + a,                  \
+                         b_cells.as<uint16_t>(), b_rows.as<uint32_t>(), b_alt.as<float>() + a);                  \
         break;
-            switch (Q)
+#define LTW(WW)                                                                                                  \
+    case kMaxQ + WW:                                                                                             \
+        k_trace_mw<WW><<<b - a, WW * 32, 0, st>>>(db->d_emis, db->d_trans, db->d_metas, sq->d_metas,             \
+                                                  sq->total + sq->nseq, d_rows, d_wcodes, d_spec,                \
+                                                  b_jobs.as<TraceJob>() + a, b - a, b_cells.as<uint16_t>(),      \
+                                                  b_rows.as<uint32_t>(), b_alt.as<float>() + a);                 \
+        break;
+            switch (cls)
             {
                 LT(1) LT(2) LT(3) LT(4) LT(5) LT(6) LT(7) LT(8)
+                LTW(2) LTW(3) LTW(4) LTW(5) LTW(6) LTW(7) LTW(8)
             }
 #undef LT
+#undef LTW
             (*launches)++;
             a = b;
         }

@@ -78,13 +78,44 @@ def test_config1_sampled_profiles(pkg, o32, eps):
     check_scan(pkg, o32, db, twins, seqs, thr=10.0)
 
 
-@pytest.mark.parametrize("M", [2, 31, 32, 33, 96, 128, 129, 200, 224, 255, 256])
+@pytest.mark.parametrize("M", [2, 31, 32, 33, 96, 128, 129, 160, 192, 193, 200, 224, 255, 256])
 def test_every_lane_layout(pkg, o32, M):
     """One profile per nodes-per-lane class boundary; short and ragged sequence lengths."""
     db, twins = make_db(pkg, o32, [(M, M, 2)], 0.01)
     rng = np.random.default_rng(M)
     seqs = [random_seq(rng, n) for n in (1, 2, 3, 4, 5, 6, 7, 9, 10, 11, 14, 15, 16, 61, 150)]
     check_scan(pkg, o32, db, twins, seqs, thr=-1e30, rows=False)
+
+
+@pytest.mark.parametrize("M", [257, 300, 512, 513, 777, 1024, 1500, 2048])
+def test_multi_warp_profiles(pkg, o32, M):
+    """Profiles above 256 nodes: several warps per pair, carries exchanged through shared memory."""
+    db, twins = make_db(pkg, o32, [(M, M, 2), (M + 1, 40, 2)], 0.01)
+    rng = np.random.default_rng(M)
+    seqs = [random_seq(rng, n) for n in (1, 2, 5, 6, 11, 64, 157)]
+    check_scan(pkg, o32, db, twins, seqs, thr=-1e30, rows=False)
+    check_scan(pkg, o32, db, twins, seqs[3:], multi_hits=False, hmmer3_compat=True, thr=-1e30, rows=False)
+
+
+def test_long_plan7_profile_with_hit(pkg, o32):
+    """A 600-node Pfam-shaped profile and a read drawn from it: long D runs across warp boundaries."""
+    rng = np.random.default_rng(77)
+    nl, ma, tr = plan7_profile_inputs(rng, 600)
+    p = pkg.ProteinProfile.from_model(nl, ma, tr, pkg.protein_cfg(pkg.ENTRY_DIST_OCCUPANCY, 0.01), "LONG600")
+    db = pkg.Db(0)
+    db.add(p)
+    db.commit()
+    tw = [oracle_twin(o32, p, 0.01)]
+    # the read skips 40 nodes in the middle: with single-hit scoring the best path deletes them,
+    # and the D run crosses the warp boundary at node 256
+    full = sample_read(rng, ma, 1800, 0.0, 0.0)
+    read = full[:720] + full[840:1500]
+    res, ref = check_scan(pkg, o32, db, tw, [read, full[:900], random_seq(rng, 400)], multi_hits=False, thr=10.0,
+                          flavour=1)
+    assert res.nhits >= 2
+    dels = [st & 0x3fff for st, _ in res.hit_at(0)[2] if (st >> 14) == 2]
+    assert len(dels) >= 30 and min(dels) <= 256 <= max(dels) + 40
+    check_scan(pkg, o32, db, tw, [read, full[:900]], multi_hits=True, thr=10.0, flavour=1)
 
 
 def test_plan7_profiles_with_real_hits(pkg, o32):
@@ -148,6 +179,9 @@ def test_error_paths(pkg, o32):
     assert e.value.rc == pkg.RC_EINVAL
     with pytest.raises(pkg.DcpError):
         db.add(pkg.ProteinProfile.sample(1, 5))  # already committed
+    with pytest.raises(pkg.DcpError) as e:
+        pkg.Db(0).add(pkg.ProteinProfile.sample(3, 2049, pkg.protein_cfg(2, 0.01)))  # > 2048 nodes: not yet
+    assert e.value.rc == pkg.RC_EINVAL
     db2 = pkg.Db(0)
     db2.add(pkg.ProteinProfile.sample(1, 5, pkg.protein_cfg(2, 0.01)))
     with pytest.raises(pkg.DcpError):
