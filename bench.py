@@ -280,6 +280,13 @@ def main():
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    traffic = None  # dram__bytes_read.sum + dram__bytes_write.sum of one k_score launch (ncu --set full), if captured
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if tj.get("profiles_per_gpu") == a.profiles and tj.get("reads") == a.reads and tj.get("core_length") == CORE:
+            traffic = tj["dram_bytes_per_launch"]
+    except Exception:
+        pass
     line = {
         "metric": "viterbi_gcups", "value": gcups, "unit": "GCUPS", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": dev_s / a.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -292,8 +299,8 @@ def main():
                             "total": float(np.mean(total_ms))},
         "wall_s_timed_region": wall, "setup_s": setup_s, "e2e_steps_ms_wall_vs_device": e2e_steps,
         "clocks": clocks,
-        "roofline": {"bound": "fp32-alu-issue", "kernel": "k_score<7>", "achieved": achieved_ops / 1e12, "peak": peak_ops / 1e12,
-                     "unit": "TFLOP/s", "frac": achieved_ops / peak_ops, "traffic": None,
+        "roofline": {"bound": "fp32-alu-issue", "kernel": "k_score<8>", "achieved": achieved_ops / 1e12, "peak": peak_ops / 1e12,
+                     "unit": "TFLOP/s", "frac": achieved_ops / peak_ops, "traffic": traffic,
                      "kernel_gcups": k_gcups, "kernel_ms": k_ms,
                      "peak_source": "measured live: dcpgpu_microbench_alu 2:1 FADD:FMNMX3 mix = %.0f G lane-instr/s "
                                     "(FADD %.0f, FMNMX3 %.0f), x33/27 ops per instruction" % (
