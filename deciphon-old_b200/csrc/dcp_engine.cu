@@ -297,10 +297,17 @@ k_score(const float *__restrict__ emis, const float *__restrict__ trans, const P
         const uint32_t *__restrict__ class_profs, uint32_t n_class_profs, const SeqMeta *__restrict__ seqs,
         uint32_t nseq, uint64_t total_recs, const RowRec *__restrict__ rows, const uint16_t *__restrict__ wcodes,
         const float *__restrict__ spec, float *__restrict__ alt_out, uint32_t nprof,
-        unsigned long long *__restrict__ counter)
+        unsigned long long *__restrict__ counter, uint32_t seq_tile)
 {
     const int lane = threadIdx.x & 31;
+    /*
+     * Work items in tile order: (sequence tile, profile, chunk of kSeqChunk sequences).  All warps
+     * of the GPU walk the items in order, so at any time they share a handful of profiles (their
+     * emission lines are hot in L1/L2) and one tile of sequences (seq_tile sequences' row records,
+     * sized by the host to stay in L2 while every profile passes over them).
+     */
     const uint32_t nchunks = (nseq + kSeqChunk - 1) / kSeqChunk;
+    const uint32_t tile_chunks = seq_tile / kSeqChunk;
     const unsigned long long n_items = (unsigned long long)n_class_profs * nchunks;
     for (;;)
     {
@@ -308,7 +315,13 @@ k_score(const float *__restrict__ emis, const float *__restrict__ trans, const P
         if (lane == 0) item = atomicAdd(counter, 1ULL);
         item = __shfl_sync(FULL, item, 0);
         if (item >= n_items) break;
-        uint32_t pi = (uint32_t)(item / nchunks), ci = (uint32_t)(item % nchunks);
+        /* item -> (tile, profile, chunk in tile); the last tile may be short */
+        const unsigned long long per_full_tile = (unsigned long long)tile_chunks * n_class_profs;
+        const uint32_t tile = (uint32_t)(item / per_full_tile);
+        const unsigned long long in_tile = item - (unsigned long long)tile * per_full_tile;
+        const uint32_t chunks_here = min(tile_chunks, nchunks - tile * tile_chunks);
+        uint32_t pi = (uint32_t)(in_tile / chunks_here);
+        uint32_t ci = tile * tile_chunks + (uint32_t)(in_tile % chunks_here);
         uint32_t prof = class_profs[pi];
         ProfMeta pm = metas[prof];
         NodeParams<Q> p;
@@ -471,7 +484,7 @@ k_score_mw(const float *__restrict__ emis, const float *__restrict__ trans, cons
            const uint32_t *__restrict__ class_profs, uint32_t n_class_profs, const SeqMeta *__restrict__ seqs,
            uint32_t nseq, uint64_t total_recs, const RowRec *__restrict__ rows,
            const uint16_t *__restrict__ wcodes, const float *__restrict__ spec, float *__restrict__ alt_out,
-           uint32_t nprof, unsigned long long *__restrict__ counter)
+           uint32_t nprof, unsigned long long *__restrict__ counter, uint32_t seq_tile)
 {
     constexpr int Q = 8;
     constexpr int ROW = 256 * W;
@@ -485,7 +498,13 @@ k_score_mw(const float *__restrict__ emis, const float *__restrict__ trans, cons
         const unsigned long long item = sh.item;
         __syncthreads();
         if (item >= n_items) break;
-        const uint32_t prof = class_profs[item / nseq], s = (uint32_t)(item % nseq);
+        /* (sequence tile, profile, sequence in tile), as in k_score */
+        const unsigned long long per_full_tile = (unsigned long long)seq_tile * n_class_profs;
+        const uint32_t tile = (uint32_t)(item / per_full_tile);
+        const unsigned long long in_tile = item - (unsigned long long)tile * per_full_tile;
+        const uint32_t seqs_here = min(seq_tile, nseq - tile * seq_tile);
+        const uint32_t prof = class_profs[in_tile / seqs_here];
+        const uint32_t s = tile * seq_tile + (uint32_t)(in_tile % seqs_here);
         const ProfMeta pm = metas[prof];
         NodeParams<Q> p;
         load_params<Q>(p, trans + pm.trans_off, 256 * W, warp * 256 + lane * Q);
@@ -588,10 +607,12 @@ void launch_score(int nblocks, cudaStream_t st, const float *emis, const float *
                   const uint32_t *class_profs, uint32_t n_class, const SeqMeta *seqs, uint32_t nseq,
                   uint64_t total_rows, const RowRec *rows, const uint16_t *wcodes, const float *spec, float *alt,
                   uint32_t nprof,
-                  unsigned long long *counter)
+                  unsigned long long *counter, uint32_t seq_tile)
 {
+    /* no shared memory: give the whole unified array to L1 (emission lines, row records) */
+    cudaFuncSetAttribute(k_score<Q>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     k_score<Q><<<nblocks, kWarpsPerBlock * 32, 0, st>>>(emis, trans, metas, class_profs, n_class, seqs, nseq,
-                                                        total_rows, rows, wcodes, spec, alt, nprof, counter);
+                                                        total_rows, rows, wcodes, spec, alt, nprof, counter, seq_tile);
 }
 
 } // namespace
@@ -950,6 +971,14 @@ extern "C" enum rc dcpgpu_scan_resident(struct dcpgpu_db *db, struct dcpgpu_seqs
     CU_TRY(cudaEventRecord(ev[1], st));
 
     const int nblocks = db->sm_count; /* persistent: one 8-warp block per SM (255 regs/thread) */
+    /* sequences per L2 tile: their row records (64 B per row and null table) should fit ~64 MB */
+    uint32_t seq_tile;
+    {
+        const double rec_bytes_per_seq = (double)total_recs / nseq * sizeof(RowRec) * n_null;
+        double t = (64.0 * 1024 * 1024) / rec_bytes_per_seq;
+        seq_tile = (uint32_t)std::min<double>(std::max<double>(t, kSeqChunk), 1 << 20);
+        seq_tile = std::max<uint32_t>(kSeqChunk, seq_tile / kSeqChunk * kSeqChunk);
+    }
     uint64_t cells = 0;
     for (int q = 1; q <= kMaxQ; ++q)
     {
@@ -961,7 +990,7 @@ extern "C" enum rc dcpgpu_scan_resident(struct dcpgpu_db *db, struct dcpgpu_seqs
         launch_score<QQ>(nblocks, st, db->d_emis, db->d_trans, db->d_metas, db->d_class[q], n_class,       \
                          sq->d_metas, nseq, total_recs, b_rows.as<RowRec>(), b_wcodes.as<uint16_t>(), b_spec.as<float>(), \
                          res->d_alt,                                                                       \
-                         nprof, ctr);                                                                      \
+                         nprof, ctr, seq_tile);                                                                      \
         break;
         switch (q)
         {
@@ -983,7 +1012,7 @@ extern "C" enum rc dcpgpu_scan_resident(struct dcpgpu_db *db, struct dcpgpu_seqs
         k_score_mw<WW><<<mw_blocks, WW * 32, 0, st>>>(db->d_emis, db->d_trans, db->d_metas, db->d_class[q],    \
                                                       n_class, sq->d_metas, nseq, total_recs,                 \
                                                       b_rows.as<RowRec>(), b_wcodes.as<uint16_t>(),           \
-                                                      b_spec.as<float>(), res->d_alt, nprof, ctr);            \
+                                                      b_spec.as<float>(), res->d_alt, nprof, ctr, seq_tile);  \
         break;
         switch (w)
         {
