@@ -73,6 +73,29 @@ __device__ __forceinline__ void load_row_special(const RowRec *__restrict__ r, f
  * emis_lane = table base + lane * 4.  (L1 eviction hints -- evict_last on the 1-3 nt lines,
  * no_allocate on the 5 nt lines -- were measured and did not help: 381 vs 399 GCUPS.)
  */
+#ifndef DCP_POLICY
+#define DCP_POLICY 0
+#endif
+/* L1 policy experiments for the emission lines, by window length l (0..4 = 1..5 nt):
+ * 0 default everywhere; 1: 5-nt lines no_allocate; 2: 4- and 5-nt lines no_allocate;
+ * 3: 1..3-nt lines evict_last, 5-nt no_allocate; 4: 1..3 evict_last, 4..5 no_allocate */
+__device__ __forceinline__ float4 ldg4(const float *p, int L)
+{
+    float4 v;
+    const bool keep = (DCP_POLICY == 3 || DCP_POLICY == 4) && L < 3;
+    const bool stream = (DCP_POLICY == 1 && L == 4) || (DCP_POLICY == 2 && L >= 3) ||
+                        (DCP_POLICY == 3 && L == 4) || (DCP_POLICY == 4 && L >= 3);
+    if (keep)
+        asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    else if (stream)
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    else
+        v = __ldg(reinterpret_cast<const float4 *>(p));
+    return v;
+}
+
 template <int Q, int L0, int L1, int ROW = 32 * (Q <= 4 ? 4 : 8)>
 __device__ __forceinline__ void load_emis_part(float (&em)[5][Q], const float *__restrict__ emis_lane,
                                                const uint32_t (&code)[5])
@@ -83,7 +106,7 @@ __device__ __forceinline__ void load_emis_part(float (&em)[5][Q], const float *_
         const float *src = emis_lane + (size_t)code[l] * ROW;
         if (Q >= 4)
         {
-            float4 a = __ldg(reinterpret_cast<const float4 *>(src));
+            float4 a = ldg4(src, l);
             em[l][0] = a.x, em[l][1] = a.y, em[l][2] = a.z, em[l][3] = a.w;
         }
         else
@@ -97,7 +120,7 @@ __device__ __forceinline__ void load_emis_part(float (&em)[5][Q], const float *_
         /* second half (+128 floats) holds nodes 4..Q-1 of the lane: load exactly Q-4 floats */
         if (Q == 8)
         {
-            float4 b = __ldg(reinterpret_cast<const float4 *>(src + 128));
+            float4 b = ldg4(src + 128, l);
             em[l][4 % Q] = b.x, em[l][5 % Q] = b.y, em[l][6 % Q] = b.z, em[l][7 % Q] = b.w;
         }
         else if (Q == 7)
