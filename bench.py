@@ -114,7 +114,7 @@ def cpu_scan_sample(pkg, models, reads, budget_s, generic):
     from common import oracle_twin
     o = orc.Oracle(double=False)
     cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    o.set_threads(cores)  # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core
     nprof = min(len(models), max(cores, 8))
     used = min(nprof, cores)
     cfg = pkg.protein_cfg(pkg.ENTRY_DIST_OCCUPANCY, 0.01)

@@ -28,6 +28,8 @@ EXPORTS = [
     "protein_profile_accession", "protein_profile_match_emission", "protein_profile_insert_emission",
     "protein_profile_null_emission", "protein_profile_trans", "protein_profile_entry",
     "protein_profile_nuclt_dist", "protein_state_name", "protein_state_is_mute", "xmath_lrt_f32",
+    "protein_h3reader_new", "protein_h3reader_next", "protein_h3reader_model", "protein_h3reader_accession",
+    "protein_h3reader_name", "protein_h3reader_del", "dcpgpu_press_hmm", "dcpgpu_db_accession", "dcpgpu_db_core_size",
     "dcpgpu_db_new", "dcpgpu_db_add", "dcpgpu_db_commit", "dcpgpu_db_nprofiles", "dcpgpu_db_device_bytes",
     "dcpgpu_db_del", "dcpgpu_seqs_new", "dcpgpu_seqs_del", "dcpgpu_scan_resident", "dcpgpu_scan",
     "dcpgpu_result_nseqs", "dcpgpu_result_nprofiles", "dcpgpu_result_null_loglik", "dcpgpu_result_alt_loglik",
@@ -134,6 +136,20 @@ def lib():
     L.dcpgpu_prod_row.restype = C.c_long
     L.dcpgpu_prod_row.argtypes = [vp, vp, C.c_uint64, C.c_int64, C.c_int64, C.c_char_p, C.c_char_p, C.c_long]
     L.dcpgpu_microbench_alu.argtypes = [i, vp]
+    L.protein_h3reader_new.restype = vp
+    L.protein_h3reader_new.argtypes = [_Cfg, vp]
+    L.protein_h3reader_next.argtypes = [vp]
+    L.protein_h3reader_model.restype = vp
+    L.protein_h3reader_model.argtypes = [vp]
+    L.protein_h3reader_accession.restype = C.c_char_p
+    L.protein_h3reader_accession.argtypes = [vp]
+    L.protein_h3reader_name.restype = C.c_char_p
+    L.protein_h3reader_name.argtypes = [vp]
+    L.protein_h3reader_del.argtypes = [vp]
+    L.dcpgpu_press_hmm.argtypes = [vp, vp, _Cfg, C.POINTER(u)]
+    L.dcpgpu_db_accession.restype = C.c_char_p
+    L.dcpgpu_db_accession.argtypes = [vp, u]
+    L.dcpgpu_db_core_size.argtypes = [vp, u]
     L.dcpgpu_last_error.restype = C.c_char_p
     _lib = L
     return L
@@ -270,6 +286,36 @@ class ProteinProfile:
         return rc, cod.raw[:3].decode(errors="replace"), am.raw[:1].decode(errors="replace")
 
 
+_libc = C.CDLL(None)
+_libc.fopen.restype = C.c_void_p
+_libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+_libc.fclose.argtypes = [C.c_void_p]
+
+
+def read_hmm(path, cfg=None):
+    """protein_h3reader_next + protein_profile_absorb over a HMMER3 ASCII file -> [ProteinProfile]."""
+    L = lib()
+    cfg = cfg or protein_cfg()
+    fp = _libc.fopen(os.fsencode(path), b"r")
+    if not fp:
+        raise DcpError(RC_EIO, "cannot open %s" % path)
+    rd = L.protein_h3reader_new(cfg, fp)
+    out = []
+    try:
+        while True:
+            rc = L.protein_h3reader_next(rd)
+            if rc == RC_END:
+                break
+            _check(rc)
+            p = ProteinProfile(L.protein_h3reader_accession(rd).decode(), cfg)
+            _check(L.protein_profile_absorb(p.h, L.protein_h3reader_model(rd)))
+            out.append(p)
+    finally:
+        L.protein_h3reader_del(rd)
+        _libc.fclose(fp)
+    return out
+
+
 def _seq_arrays(seqs):
     bs = [s.encode() if isinstance(s, str) else bytes(s) for s in seqs]
     arr = (C.c_char_p * len(bs))(*bs)
@@ -360,6 +406,21 @@ class Db:
     def add(self, prof):
         _check(lib().dcpgpu_db_add(self.h, prof.h))
         self.profiles.append(prof)
+
+    def press(self, hmm_path, cfg=None):
+        """hmm_press: add every profile of a HMMER3 file (call commit afterwards)."""
+        fp = _libc.fopen(os.fsencode(hmm_path), b"r")
+        if not fp:
+            raise DcpError(RC_EIO, "cannot open %s" % hmm_path)
+        n = C.c_uint(0)
+        try:
+            _check(lib().dcpgpu_press_hmm(self.h, fp, cfg or protein_cfg(), C.byref(n)))
+        finally:
+            _libc.fclose(fp)
+        return n.value
+
+    def accession(self, i):
+        return lib().dcpgpu_db_accession(self.h, i).decode()
 
     def commit(self):
         _check(lib().dcpgpu_db_commit(self.h))

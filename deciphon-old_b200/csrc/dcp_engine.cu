@@ -801,6 +801,14 @@ extern "C" enum rc dcpgpu_db_commit(struct dcpgpu_db *db)
 }
 
 extern "C" unsigned dcpgpu_db_nprofiles(struct dcpgpu_db const *db) { return (unsigned)db->profs.size(); }
+extern "C" char const *dcpgpu_db_accession(struct dcpgpu_db const *db, unsigned i)
+{
+    return i < db->profs.size() ? db->profs[i]->accession : nullptr;
+}
+extern "C" unsigned dcpgpu_db_core_size(struct dcpgpu_db const *db, unsigned i)
+{
+    return i < db->profs.size() ? db->profs[i]->core_size : 0;
+}
 extern "C" uint64_t dcpgpu_db_device_bytes(struct dcpgpu_db const *db) { return db->device_bytes; }
 
 extern "C" void dcpgpu_db_del(struct dcpgpu_db *db)

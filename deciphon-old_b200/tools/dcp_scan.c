@@ -1,0 +1,175 @@
+/*
+ * dcp-scan -- local, file-driven scan: HMMER3 profiles x FASTA nucleotide sequences -> product TSV.
+ *
+ * Stands in for the REST-driven scan_run (src/server/scan.c:215-269), which needs a live
+ * deciphon-sched: press the .hmm in memory (hmm_press, src/server/hmm.c:120-178), scan every
+ * sequence against every profile on the GPU, write prod_fclose's header and one prod_fwrite row
+ * per hit (src/server/prod.c:106-181).  Sequence ids are 1-based file order.
+ *
+ *   dcp-scan [--single-hit] [--hmmer3-compat] [--lrt X] [--epsilon E] [--uniform-entry]
+ *            [--device N] [--scan-id N] [--batch N] profiles.hmm sequences.fasta > products.tsv
+ */
+#include "dcpgpu.h"
+
+#include <ctype.h>
+#include <stdlib.h>
+#include <string.h>
+
+struct seqs
+{
+    char **seq;
+    unsigned *len;
+    int64_t *id;
+    unsigned n, cap;
+};
+
+static int push_seq(struct seqs *s, char *buf, unsigned len, int64_t id)
+{
+    if (s->n == s->cap)
+    {
+        unsigned cap = s->cap ? 2 * s->cap : 1024;
+        char **a = realloc(s->seq, cap * sizeof *a);
+        unsigned *b = a ? realloc(s->len, cap * sizeof *b) : NULL;
+        int64_t *c = b ? realloc(s->id, cap * sizeof *c) : NULL;
+        if (a) s->seq = a;
+        if (b) s->len = b;
+        if (c) s->id = c;
+        if (!a || !b || !c) return -1;
+        s->cap = cap;
+    }
+    s->seq[s->n] = buf, s->len[s->n] = len, s->id[s->n] = id;
+    s->n++;
+    return 0;
+}
+
+/* reads up to `max` records; returns 1 if more may follow, 0 at end of file, -1 on error */
+static int read_fasta(FILE *fp, struct seqs *s, unsigned max, int64_t *next_id, int *pending)
+{
+    char *cur = NULL;
+    size_t len = 0, cap = 0;
+    int c, have = *pending;
+    *pending = 0;
+    for (;;)
+    {
+        c = fgetc(fp);
+        if (c == '>' || c == EOF)
+        {
+            if (have)
+            {
+                if (push_seq(s, cur ? cur : calloc(1, 1), (unsigned)len, (*next_id)++)) return -1;
+                cur = NULL, len = cap = 0, have = 0;
+            }
+            if (c == EOF) return 0;
+            while ((c = fgetc(fp)) != EOF && c != '\n') {}
+            have = 1;
+            if (s->n >= max)
+            {
+                *pending = 1;
+                return 1;
+            }
+            continue;
+        }
+        if (isspace(c)) continue;
+        if (!have) return -1; /* sequence data before any header */
+        if (len + 2 > cap)
+        {
+            cap = cap ? 2 * cap : 4096;
+            char *t = realloc(cur, cap);
+            if (!t) return -1;
+            cur = t;
+        }
+        cur[len++] = (char)toupper(c);
+        cur[len] = '\0';
+    }
+}
+
+static void usage(void)
+{
+    fputs("usage: dcp-scan [--single-hit] [--hmmer3-compat] [--lrt X] [--epsilon E] [--uniform-entry]\n"
+          "                [--device N] [--scan-id N] [--batch N] profiles.hmm sequences.fasta > products.tsv\n",
+          stderr);
+}
+
+int main(int argc, char **argv)
+{
+    struct dcpgpu_params prm = {.multi_hits = true, .hmmer3_compat = false, .lrt_threshold = 10.0, .want_paths = true};
+    struct protein_cfg cfg = {ENTRY_DIST_OCCUPANCY, 0.01f}; /* PROTEIN_CFG_DEFAULT */
+    int device = 0;
+    int64_t scan_id = 1;
+    unsigned batch = 65536;
+    int i = 1;
+    for (; i < argc && argv[i][0] == '-' && argv[i][1] == '-'; ++i)
+    {
+        if (!strcmp(argv[i], "--single-hit")) prm.multi_hits = false;
+        else if (!strcmp(argv[i], "--hmmer3-compat")) prm.hmmer3_compat = true;
+        else if (!strcmp(argv[i], "--uniform-entry")) cfg.entry_dist = ENTRY_DIST_UNIFORM;
+        else if (!strcmp(argv[i], "--lrt") && i + 1 < argc) prm.lrt_threshold = atof(argv[++i]);
+        else if (!strcmp(argv[i], "--epsilon") && i + 1 < argc) cfg.epsilon = (float)atof(argv[++i]);
+        else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--scan-id") && i + 1 < argc) scan_id = atoll(argv[++i]);
+        else if (!strcmp(argv[i], "--batch") && i + 1 < argc) batch = (unsigned)atoi(argv[++i]);
+        else
+        {
+            usage();
+            return 2;
+        }
+    }
+    if (argc - i != 2 || batch == 0)
+    {
+        usage();
+        return 2;
+    }
+    FILE *hmm = fopen(argv[i], "r");
+    FILE *fa = fopen(argv[i + 1], "r");
+    if (!hmm || !fa)
+    {
+        fprintf(stderr, "dcp-scan: cannot open %s\n", hmm ? argv[i + 1] : argv[i]);
+        return 1;
+    }
+    struct dcpgpu_db *db = NULL;
+    enum rc rc = dcpgpu_db_new(&db, device);
+    unsigned nprof = 0;
+    if (!rc) rc = dcpgpu_press_hmm(db, hmm, cfg, &nprof);
+    if (!rc) rc = dcpgpu_db_commit(db);
+    fclose(hmm);
+    if (rc)
+    {
+        fprintf(stderr, "dcp-scan: %s (rc=%d)\n", dcpgpu_last_error(), (int)rc);
+        return 1;
+    }
+    dcpgpu_prod_fwrite_header(stdout);
+    int64_t next_id = 1;
+    int pending = 0, more = 1;
+    uint64_t total_hits = 0, total_seqs = 0;
+    while (more > 0)
+    {
+        struct seqs s = {0};
+        more = read_fasta(fa, &s, batch, &next_id, &pending);
+        if (more < 0)
+        {
+            fputs("dcp-scan: malformed FASTA or out of memory\n", stderr);
+            return 1;
+        }
+        if (s.n)
+        {
+            struct dcpgpu_result *res = NULL;
+            rc = dcpgpu_scan(db, s.n, (char const *const *)s.seq, s.len, &prm, &res);
+            if (!rc) rc = dcpgpu_prod_fwrite(res, db, stdout, scan_id, s.id, s.n, (char const *const *)s.seq);
+            if (rc)
+            {
+                fprintf(stderr, "dcp-scan: %s (rc=%d)\n", dcpgpu_last_error(), (int)rc);
+                return 1;
+            }
+            total_hits += dcpgpu_result_nhits(res);
+            total_seqs += s.n;
+            dcpgpu_result_del(res);
+        }
+        for (unsigned k = 0; k < s.n; ++k) free(s.seq[k]);
+        free(s.seq), free(s.len), free(s.id);
+    }
+    fclose(fa);
+    fprintf(stderr, "dcp-scan: %u profiles x %llu sequences, %llu hits\n", nprof, (unsigned long long)total_seqs,
+            (unsigned long long)total_hits);
+    dcpgpu_db_del(db);
+    return 0;
+}

@@ -160,6 +160,17 @@ float const *protein_profile_entry(struct protein_profile const *);
  * which: -2 null, -1 insert, k >= 0 match node k. */
 enum rc protein_profile_nuclt_dist(struct protein_profile const *, int which, double out[129]);
 
+/* HMMER3 ASCII reader: protein_h3reader_init/next/del (src/model/protein_h3reader.c:18-103).
+ * _next parses the next profile of the file into the reader's protein_model: RC_OK, RC_END at end of
+ * file, RC_EPARSE on malformed input.  The background is HMMER3's Swiss-Prot 50.8 frequencies. */
+struct protein_h3reader;
+struct protein_h3reader *protein_h3reader_new(struct protein_cfg cfg, FILE *fp);
+enum rc protein_h3reader_next(struct protein_h3reader *);
+struct protein_model const *protein_h3reader_model(struct protein_h3reader const *);
+char const *protein_h3reader_accession(struct protein_h3reader const *); /* ACC, else NAME */
+char const *protein_h3reader_name(struct protein_h3reader const *);
+void protein_h3reader_del(struct protein_h3reader *);
+
 /* protein_state_name (src/model/protein_state.c:5-39); returns the name length */
 unsigned protein_state_name(unsigned id, char name[DCP_STATE_NAME_SIZE]);
 bool protein_state_is_mute(unsigned id);
@@ -194,6 +205,14 @@ enum rc dcpgpu_db_commit(struct dcpgpu_db *);
 unsigned dcpgpu_db_nprofiles(struct dcpgpu_db const *);
 uint64_t dcpgpu_db_device_bytes(struct dcpgpu_db const *);
 void dcpgpu_db_del(struct dcpgpu_db *);
+
+/* hmm_press without the REST plumbing (src/server/hmm.c:120-178): every profile of a HMMER3 file is
+ * absorbed and added to `db` (call dcpgpu_db_commit afterwards).  PROTEIN_CFG_DEFAULT is
+ * {ENTRY_DIST_OCCUPANCY, 0.01} (protein_cfg.h:13,22-23). */
+enum rc dcpgpu_press_hmm(struct dcpgpu_db *, FILE *hmm, struct protein_cfg cfg, unsigned *nprofiles);
+/* accession / core size of profile i of the database */
+char const *dcpgpu_db_accession(struct dcpgpu_db const *, unsigned i);
+unsigned dcpgpu_db_core_size(struct dcpgpu_db const *, unsigned i);
 
 /* Stage sequences (ASCII ACGT, not NUL-terminated; lens[i] nucleotides each) on the db's
  * device.  RC_EINVAL for an empty sequence (protein_profile.c:158) or a non-ACGT symbol. */

@@ -1061,6 +1061,21 @@ long orc_product_row(const struct orc_profile *p, long scan_id, long seq_id, con
     return n;
 }
 
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+/* number of OpenMP threads orc_scan uses (NUM_THREADS of the reference's .env, cli_server.c:40-53) */
+int orc_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
 /* ------------------------------------------------------------------ */
 /* scan: restatement of thread_run (src/server/scan_thread.c:86-135)    */
 /* over a batch, OpenMP over profiles like scan.c:239-250.               */

@@ -104,3 +104,38 @@ def ref_paths(ref, nprof):
                 out[(s, p)] = list(zip(ref["step_state"][off[i]:off[i + 1]].tolist(),
                                        ref["step_len"][off[i]:off[i + 1]].tolist()))
     return out
+
+
+SWISSPROT_BG = np.array([0.0787945, 0.0151600, 0.0535222, 0.0668298, 0.0397062, 0.0695071, 0.0229198, 0.0590092,
+                         0.0594422, 0.0963728, 0.0237718, 0.0414386, 0.0482904, 0.0395639, 0.0540978, 0.0683364,
+                         0.0540687, 0.0673417, 0.0114135, 0.0304133])  # HMMER3 background (protein_h3reader.c:79-103)
+
+
+def _score(lp):
+    return "*" if not np.isfinite(lp) else "%.5f" % (-lp)
+
+
+def write_hmm(path, profiles):
+    """Write HMMER3/f ASCII profiles.  profiles: [(name, acc, match_lp[M,20], trans[M+1,7])].
+    Returns, per profile, the (match, trans) arrays as a reader will see them (5-decimal rounding)."""
+    seen = []
+    with open(path, "w") as f:
+        for name, acc, ma, tr in profiles:
+            M = ma.shape[0]
+            f.write("HMMER3/f [3.1b2 | February 2015]\nNAME  %s\nACC   %s\nDESC  synthetic\nLENG  %d\nALPH  amino\n"
+                    "RF    no\nMM    no\nCONS  yes\nCS    no\nMAP   yes\nNSEQ  10\nEFFN  1.5\nCKSUM 1\n"
+                    "STATS LOCAL MSV       -9.0000  0.70000\n" % (name, acc, M))
+            f.write("HMM          " + "        ".join(AMINO) + "   \n")
+            f.write("            m->m     m->i     m->d     i->m     i->i     d->m     d->d\n")
+            f.write("  COMPO   " + "  ".join("%.5f" % 2.9 for _ in range(20)) + "\n")
+            f.write("          " + "  ".join("%.5f" % 2.9 for _ in range(20)) + "\n")
+            f.write("          " + "  ".join(_score(x) for x in tr[0]) + "\n")
+            for k in range(M):
+                cons = AMINO[int(np.argmax(ma[k]))].lower()
+                f.write("%7d   " % (k + 1) + "  ".join(_score(x) for x in ma[k]) + " %6d %s - - -\n" % (k + 1, cons))
+                f.write("          " + "  ".join("%.5f" % 2.9 for _ in range(20)) + "\n")
+                f.write("          " + "  ".join(_score(x) for x in tr[k + 1]) + "\n")
+            f.write("//\n")
+            rnd = lambda a: np.array([[-float(_score(x)) if np.isfinite(x) else -np.inf for x in row] for row in a])
+            seen.append((rnd(ma), rnd(tr)))
+    return seen

@@ -88,6 +88,9 @@ class Oracle:
         ptrs = [a.ctypes.data for a in arrs] + [None if a is None else a.ctypes.data for a in nds]
         return OProfile(self, self.lib.orc_profile_import(M, float(eps), *ptrs))
 
+    def set_threads(self, n):
+        return self.lib.orc_set_threads(int(n))
+
     def sample_inputs(self, seed, M):
         nl = np.empty(20); ma = np.empty((M, 20)); tr = np.empty((M + 1, 7))
         self.lib.orc_sample_inputs(seed, M, nl.ctypes.data, ma.ctypes.data, tr.ctypes.data)

@@ -196,3 +196,48 @@ def test_deterministic_across_runs(pkg, o32):
     b = db.scan(seqs, lrt_threshold=-1e30)
     assert np.array_equal(a.alt_loglik, b.alt_loglik)
     assert [a.hit_at(i) for i in range(0, a.nhits, 37)] == [b.hit_at(i) for i in range(0, b.nhits, 37)]
+
+
+def test_dcp_scan_driver_matches_reference_product_rows(pkg, o32, tmp_path):
+    """dcp-scan (HMMER3 file + FASTA -> TSV) against the oracle's restatement of prod_fwrite."""
+    import os
+    import subprocess
+    from common import write_hmm
+    rng = np.random.default_rng(12)
+    models = []
+    for i, M in enumerate((60, 150, 300)):
+        _, ma, tr = plan7_profile_inputs(rng, M)
+        models.append(("fam%d" % i, "PF9%04d.1" % i, ma, tr))
+    hmm = str(tmp_path / "db.hmm")
+    seen = write_hmm(hmm, models)
+    seqs = [sample_read(rng, seen[i % 3][0], int(rng.integers(200, 700)), 0.02, 0.01) for i in range(7)]
+    seqs.append(random_seq(rng, 333))
+    fasta = tmp_path / "reads.fasta"
+    with open(fasta, "w") as f:
+        for i, s in enumerate(seqs):
+            f.write(">read%d some description\n" % i)
+            for a in range(0, len(s), 60):
+                f.write(s[a:a + 60].lower() if i % 2 else s[a:a + 60])
+                f.write("\n")
+    exe = os.path.join(os.path.dirname(pkg.__file__), "dcp-scan")
+    out = subprocess.run([exe, "--scan-id", "42", "--batch", "3", hmm, str(fasta)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.splitlines(keepends=True)
+    assert lines[0] == "scan_id\tseq_id\tprofile_name\tabc_name\talt_loglik\tnull_loglik\tprofile_typeid\tversion\tmatch\n"
+    cfg = pkg.protein_cfg(pkg.ENTRY_DIST_OCCUPANCY, 0.01)
+    profs = pkg.read_hmm(hmm, cfg)
+    twins = [oracle_twin(o32, p, 0.01) for p in profs]
+    ref = o32.scan(twins, seqs, True, False, 10.0, 1, True)
+    paths = ref_paths(ref, 3)
+    want = []
+    for s in range(len(seqs)):
+        for p in range(3):
+            if ref["hit"][s, p]:
+                want.append(twins[p].product_row(42, s + 1, profs[p].accession, float(ref["alt"][s, p]),
+                                                 float(ref["null"][s, p]), seqs[s], paths[(s, p)]))
+    assert len(want) >= 6
+    assert lines[1:] == want
+    bad = tmp_path / "bad.fasta"
+    bad.write_text(">x\nACGTNNACGT\n")
+    out = subprocess.run([exe, hmm, str(bad)], capture_output=True, text=True)
+    assert out.returncode == 1 and "ACGT" in out.stderr

@@ -152,3 +152,41 @@ def test_plan7_inputs_build(pkg, o32):
     nl, ma, tr = plan7_profile_inputs(rng, 40)
     p = pkg.ProteinProfile.from_model(nl, ma, tr)
     assert np.isfinite(p.entry).all() and abs(np.exp(p.entry.astype(np.float64)) @ np.arange(40, 0, -1) - 1) < 1e-5
+
+
+def test_h3reader_parses_hmmer3_ascii(pkg, tmp_path):
+    """protein_h3reader_next over a HMMER3/f file: same tables as feeding the rounded scores directly."""
+    from common import SWISSPROT_BG, write_hmm
+    rng = np.random.default_rng(4)
+    profs = []
+    for i, M in enumerate((3, 40, 129)):
+        _, ma, tr = plan7_profile_inputs(rng, M)
+        profs.append(("fam%d" % i, "PF%05d.%d" % (i + 1, i + 3), ma, tr))
+    path = str(tmp_path / "mini.hmm")
+    seen = write_hmm(path, profs)
+    cfg = pkg.protein_cfg(pkg.ENTRY_DIST_OCCUPANCY, 0.01)
+    got = pkg.read_hmm(path, cfg)
+    assert [p.accession for p in got] == [p[1] for p in profs]
+    null_lp = np.log(SWISSPROT_BG).astype(np.float32)
+    for p, (ma, tr) in zip(got, seen):
+        want = pkg.ProteinProfile.build(null_lp, ma, tr, cfg)
+        assert p.core_size == ma.shape[0]
+        assert np.array_equal(p.trans, want.trans)
+        assert np.array_equal(p.match_emission, want.match_emission)
+        assert np.array_equal(p.entry, want.entry) and np.array_equal(p.null_emission, want.null_emission)
+
+
+def test_h3reader_rejects_garbage(pkg, tmp_path):
+    bad = tmp_path / "bad.hmm"
+    bad.write_text("HMMER3/f [x]\nNAME a\nLENG 2\nALPH amino\nHMM   A C\n m->m\n  1.0 2.0\n")
+    with pytest.raises(pkg.DcpError) as e:
+        pkg.read_hmm(str(bad))
+    assert e.value.rc == pkg.RC_EPARSE
+    notfmt = tmp_path / "x.hmm"
+    notfmt.write_text("hello\n")
+    with pytest.raises(pkg.DcpError) as e:
+        pkg.read_hmm(str(notfmt))
+    assert e.value.rc == pkg.RC_EPARSE
+    empty = tmp_path / "empty.hmm"
+    empty.write_text("")
+    assert pkg.read_hmm(str(empty)) == []
