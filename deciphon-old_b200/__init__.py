@@ -29,7 +29,9 @@ EXPORTS = [
     "protein_profile_null_emission", "protein_profile_trans", "protein_profile_entry",
     "protein_profile_nuclt_dist", "protein_state_name", "protein_state_is_mute", "xmath_lrt_f32",
     "protein_h3reader_new", "protein_h3reader_next", "protein_h3reader_model", "protein_h3reader_accession",
-    "protein_h3reader_name", "protein_h3reader_del", "dcpgpu_press_hmm", "dcpgpu_db_accession", "dcpgpu_db_core_size",
+    "protein_h3reader_name", "protein_h3reader_del", "protein_db_writer_open", "protein_db_writer_pack_profile",
+    "protein_db_writer_close", "protein_db_reader_open", "protein_db_reader_nprofiles", "protein_db_reader_cfg",
+    "protein_db_reader_profile_size", "protein_db_reader_next", "protein_db_reader_close", "dcpgpu_press_hmm", "dcpgpu_db_accession", "dcpgpu_db_core_size",
     "dcpgpu_db_new", "dcpgpu_db_add", "dcpgpu_db_commit", "dcpgpu_db_nprofiles", "dcpgpu_db_device_bytes",
     "dcpgpu_db_del", "dcpgpu_seqs_new", "dcpgpu_seqs_del", "dcpgpu_scan_resident", "dcpgpu_scan",
     "dcpgpu_result_nseqs", "dcpgpu_result_nprofiles", "dcpgpu_result_null_loglik", "dcpgpu_result_alt_loglik",
@@ -147,6 +149,18 @@ def lib():
     L.protein_h3reader_name.argtypes = [vp]
     L.protein_h3reader_del.argtypes = [vp]
     L.dcpgpu_press_hmm.argtypes = [vp, vp, _Cfg, C.POINTER(u)]
+    L.protein_db_writer_open.restype = vp
+    L.protein_db_writer_open.argtypes = [vp, _Cfg]
+    L.protein_db_writer_pack_profile.argtypes = [vp, vp]
+    L.protein_db_writer_close.argtypes = [vp, C.c_bool]
+    L.protein_db_reader_open.argtypes = [C.POINTER(vp), vp]
+    L.protein_db_reader_nprofiles.argtypes = [vp]
+    L.protein_db_reader_cfg.restype = _Cfg
+    L.protein_db_reader_cfg.argtypes = [vp]
+    L.protein_db_reader_profile_size.restype = C.c_uint32
+    L.protein_db_reader_profile_size.argtypes = [vp, u]
+    L.protein_db_reader_next.argtypes = [vp, C.POINTER(vp)]
+    L.protein_db_reader_close.argtypes = [vp]
     L.dcpgpu_db_accession.restype = C.c_char_p
     L.dcpgpu_db_accession.argtypes = [vp, u]
     L.dcpgpu_db_core_size.argtypes = [vp, u]
@@ -314,6 +328,53 @@ def read_hmm(path, cfg=None):
         L.protein_h3reader_del(rd)
         _libc.fclose(fp)
     return out
+
+
+def write_dcp(path, profiles, cfg=None):
+    """protein_db_writer_open / _pack_profile / db_writer_close."""
+    L = lib()
+    cfg = cfg or protein_cfg()
+    fp = _libc.fopen(os.fsencode(path), b"wb")
+    if not fp:
+        raise DcpError(RC_EIO, "cannot open %s" % path)
+    w = L.protein_db_writer_open(fp, cfg)
+    ok = False
+    try:
+        for p in profiles:
+            _check(L.protein_db_writer_pack_profile(w, p.h))
+        ok = True
+    finally:
+        rc = L.protein_db_writer_close(w, ok)
+        _libc.fclose(fp)
+    _check(rc)
+
+
+def read_dcp(path):
+    """protein_db_reader_open + profile_reader_next -> (cfg, [ProteinProfile])."""
+    L = lib()
+    fp = _libc.fopen(os.fsencode(path), b"rb")
+    if not fp:
+        raise DcpError(RC_EIO, "cannot open %s" % path)
+    rd = C.c_void_p()
+    try:
+        _check(L.protein_db_reader_open(C.byref(rd), fp))
+        cfg = L.protein_db_reader_cfg(rd)
+        out = []
+        while True:
+            h = C.c_void_p()
+            rc = L.protein_db_reader_next(rd, C.byref(h))
+            if rc == RC_END:
+                break
+            _check(rc)
+            p = ProteinProfile.__new__(ProteinProfile)
+            p.h = h
+            out.append(p)
+        assert len(out) == L.protein_db_reader_nprofiles(rd)
+    finally:
+        if rd:
+            L.protein_db_reader_close(rd)
+        _libc.fclose(fp)
+    return cfg, out
 
 
 def _seq_arrays(seqs):

@@ -7,7 +7,8 @@
  * per hit (src/server/prod.c:106-181).  Sequence ids are 1-based file order.
  *
  *   dcp-scan [--single-hit] [--hmmer3-compat] [--lrt X] [--epsilon E] [--uniform-entry]
- *            [--device N] [--scan-id N] [--batch N] profiles.hmm sequences.fasta > products.tsv
+ *            [--device N] [--scan-id N] [--batch N] profiles.{hmm,dcp} sequences.fasta > products.tsv
+ *   dcp-scan --press [--epsilon E] [--uniform-entry] profiles.hmm database.dcp       (hmm_press to a file)
  */
 #include "dcpgpu.h"
 
@@ -83,10 +84,69 @@ static int read_fasta(FILE *fp, struct seqs *s, unsigned max, int64_t *next_id, 
     }
 }
 
+static int ends_with(char const *s, char const *suffix)
+{
+    size_t n = strlen(s), m = strlen(suffix);
+    return n >= m && !strcmp(s + n - m, suffix);
+}
+
+/* hmm_press (src/server/hmm.c:120-178) to a local .dcp file; no GPU involved */
+static int press(char const *hmm_path, char const *dcp_path, struct protein_cfg cfg)
+{
+    FILE *hmm = fopen(hmm_path, "r"), *out = fopen(dcp_path, "wb");
+    if (!hmm || !out)
+    {
+        fprintf(stderr, "dcp-scan: cannot open %s\n", hmm ? dcp_path : hmm_path);
+        return 1;
+    }
+    struct protein_h3reader *rd = protein_h3reader_new(cfg, hmm);
+    struct protein_db_writer *w = protein_db_writer_open(out, cfg);
+    enum rc rc = (rd && w) ? RC_OK : RC_ENOMEM;
+    unsigned n = 0;
+    while (!rc && (rc = protein_h3reader_next(rd)) == RC_OK)
+    {
+        struct protein_profile *p = protein_profile_new(protein_h3reader_accession(rd), cfg);
+        rc = p ? protein_profile_absorb(p, protein_h3reader_model(rd)) : RC_ENOMEM;
+        if (!rc) rc = protein_db_writer_pack_profile(w, p);
+        protein_profile_del(p);
+        if (!rc) ++n;
+    }
+    if (rc == RC_END) rc = RC_OK;
+    enum rc rc2 = w ? protein_db_writer_close(w, rc == RC_OK) : RC_OK;
+    protein_h3reader_del(rd);
+    fclose(hmm), fclose(out);
+    if (rc || rc2)
+    {
+        fprintf(stderr, "dcp-scan: %s (rc=%d)\n", dcpgpu_last_error(), (int)(rc ? rc : rc2));
+        return 1;
+    }
+    fprintf(stderr, "dcp-scan: pressed %u profiles into %s\n", n, dcp_path);
+    return 0;
+}
+
+/* load a pressed database: protein_db_reader_open + profile_reader_next per profile */
+static enum rc load_dcp(struct dcpgpu_db *db, FILE *fp, unsigned *nprof)
+{
+    struct protein_db_reader *rd = NULL;
+    enum rc rc = protein_db_reader_open(&rd, fp);
+    if (rc) return rc;
+    struct protein_profile *p = NULL;
+    while ((rc = protein_db_reader_next(rd, &p)) == RC_OK)
+    {
+        rc = dcpgpu_db_add(db, p);
+        protein_profile_del(p);
+        if (rc) break;
+        ++*nprof;
+    }
+    protein_db_reader_close(rd);
+    return rc == RC_END ? RC_OK : rc;
+}
+
 static void usage(void)
 {
     fputs("usage: dcp-scan [--single-hit] [--hmmer3-compat] [--lrt X] [--epsilon E] [--uniform-entry]\n"
-          "                [--device N] [--scan-id N] [--batch N] profiles.hmm sequences.fasta > products.tsv\n",
+          "                [--device N] [--scan-id N] [--batch N] profiles.{hmm,dcp} sequences.fasta > products.tsv\n"
+          "       dcp-scan --press [--epsilon E] [--uniform-entry] profiles.hmm database.dcp\n",
           stderr);
 }
 
@@ -97,10 +157,12 @@ int main(int argc, char **argv)
     int device = 0;
     int64_t scan_id = 1;
     unsigned batch = 65536;
+    int do_press = 0;
     int i = 1;
     for (; i < argc && argv[i][0] == '-' && argv[i][1] == '-'; ++i)
     {
-        if (!strcmp(argv[i], "--single-hit")) prm.multi_hits = false;
+        if (!strcmp(argv[i], "--press")) do_press = 1;
+        else if (!strcmp(argv[i], "--single-hit")) prm.multi_hits = false;
         else if (!strcmp(argv[i], "--hmmer3-compat")) prm.hmmer3_compat = true;
         else if (!strcmp(argv[i], "--uniform-entry")) cfg.entry_dist = ENTRY_DIST_UNIFORM;
         else if (!strcmp(argv[i], "--lrt") && i + 1 < argc) prm.lrt_threshold = atof(argv[++i]);
@@ -119,7 +181,8 @@ int main(int argc, char **argv)
         usage();
         return 2;
     }
-    FILE *hmm = fopen(argv[i], "r");
+    if (do_press) return press(argv[i], argv[i + 1], cfg);
+    FILE *hmm = fopen(argv[i], ends_with(argv[i], ".dcp") ? "rb" : "r");
     FILE *fa = fopen(argv[i + 1], "r");
     if (!hmm || !fa)
     {
@@ -129,7 +192,7 @@ int main(int argc, char **argv)
     struct dcpgpu_db *db = NULL;
     enum rc rc = dcpgpu_db_new(&db, device);
     unsigned nprof = 0;
-    if (!rc) rc = dcpgpu_press_hmm(db, hmm, cfg, &nprof);
+    if (!rc) rc = ends_with(argv[i], ".dcp") ? load_dcp(db, hmm, &nprof) : dcpgpu_press_hmm(db, hmm, cfg, &nprof);
     if (!rc) rc = dcpgpu_db_commit(db);
     fclose(hmm);
     if (rc)

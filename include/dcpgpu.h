@@ -171,6 +171,23 @@ char const *protein_h3reader_accession(struct protein_h3reader const *); /* ACC,
 char const *protein_h3reader_name(struct protein_h3reader const *);
 void protein_h3reader_del(struct protein_h3reader *);
 
+/* .dcp database container (MessagePack), src/db/writer.c, protein_writer.c, reader.c, protein_reader.c,
+ * profile_reader.c and protein_profile_pack/unpack (protein_profile.c:38-117,338-400).  Same root/header/
+ * profile maps and key order as the reference; the imm-defined blobs ("abc", "amino", "null", "alt") are
+ * stored as explicit arrays instead (dcp_db.c header comment). */
+struct protein_db_writer;
+struct protein_db_reader;
+struct protein_db_writer *protein_db_writer_open(FILE *fp, struct protein_cfg cfg);
+enum rc protein_db_writer_pack_profile(struct protein_db_writer *, struct protein_profile const *);
+enum rc protein_db_writer_close(struct protein_db_writer *, bool successfully); /* frees the writer */
+enum rc protein_db_reader_open(struct protein_db_reader **out, FILE *fp);
+unsigned protein_db_reader_nprofiles(struct protein_db_reader const *);
+struct protein_cfg protein_db_reader_cfg(struct protein_db_reader const *);
+uint32_t protein_db_reader_profile_size(struct protein_db_reader const *, unsigned i);
+/* next profile of the file (caller frees with protein_profile_del); RC_END after the last */
+enum rc protein_db_reader_next(struct protein_db_reader *, struct protein_profile **out);
+void protein_db_reader_close(struct protein_db_reader *);
+
 /* protein_state_name (src/model/protein_state.c:5-39); returns the name length */
 unsigned protein_state_name(unsigned id, char name[DCP_STATE_NAME_SIZE]);
 bool protein_state_is_mute(unsigned id);

@@ -190,3 +190,35 @@ def test_h3reader_rejects_garbage(pkg, tmp_path):
     empty = tmp_path / "empty.hmm"
     empty.write_text("")
     assert pkg.read_hmm(str(empty)) == []
+
+
+def test_dcp_database_round_trip(pkg, tmp_path):
+    """test/protein_db.c in spirit: write sampled profiles (seeds 1, 2), read back, same numbers."""
+    cfg = pkg.protein_cfg(pkg.ENTRY_DIST_OCCUPANCY, 0.01)
+    profs = [pkg.ProteinProfile.sample(1, 2, cfg, "seed1"), pkg.ProteinProfile.sample(2, 2, cfg, "seed2"),
+             pkg.ProteinProfile.sample(3, 300, cfg, "PF00003.1")]
+    path = str(tmp_path / "db.dcp")
+    pkg.write_dcp(path, profs, cfg)
+    raw = open(path, "rb").read()
+    assert raw[0] == 0x82 and raw[1:8] == b"\xa6header" and b"\xcd\xc6\xf0" in raw[:40]  # map(2), magic 0xC6F0
+    rcfg, back = pkg.read_dcp(path)
+    assert rcfg.entry_dist == cfg.entry_dist and rcfg.epsilon == cfg.epsilon
+    assert len(back) == 3  # EQ(db.nprofiles, 2) in the reference's test
+    for a, b in zip(profs, back):
+        assert a.accession == b.accession and a.core_size == b.core_size
+        for f in ("match_emission", "insert_emission", "null_emission", "trans", "entry"):
+            assert np.array_equal(getattr(a, f), getattr(b, f), equal_nan=True)
+        for w in (-2, -1, 0, a.core_size - 1):
+            assert np.array_equal(a.nuclt_dist(w), b.nuclt_dist(w))
+        assert a.decode("ACGT", 1) == b.decode("ACGT", 1)
+    # truncated / corrupt files are parse errors, not crashes
+    bad = str(tmp_path / "bad.dcp")
+    open(bad, "wb").write(raw[:len(raw) // 2])
+    with pytest.raises(pkg.DcpError) as e:
+        pkg.read_dcp(bad)
+    assert e.value.rc == pkg.RC_EPARSE
+    open(bad, "wb").write(raw.replace(b"\xcd\xc6\xf0", b"\xcd\xc6\xf1", 1))
+    with pytest.raises(pkg.DcpError):
+        pkg.read_dcp(bad)
+    with pytest.raises(pkg.DcpError):
+        pkg.write_dcp(str(tmp_path / "x.dcp"), [pkg.ProteinProfile.sample(1, 2, pkg.protein_cfg(2, 0.02))], cfg)
