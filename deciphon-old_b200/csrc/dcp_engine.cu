@@ -340,36 +340,41 @@ k_score(const float *__restrict__ emis, const float *__restrict__ trans, const P
 }
 
 /* ----------------------------------------------------------------------------------------- */
-/* alt Viterbi, score pass, profiles of 257..2048 nodes: W warps (one block) per pair         */
+/* alt Viterbi, score pass, profiles of 257..4096 nodes: a group of warps per pair            */
 /* ----------------------------------------------------------------------------------------- */
 /*
  * Same recurrence, same fp32 operation order and the same lane layout as k_score<8>; node
- * k-1 = warp * 256 + lane * 8 + sub.  What a single warp exchanges with shuffles is exchanged
- * between warps through shared memory, three block barriers per row:
- *   A   V_M / V_I of each warp's last node, per-warp max of V_M (-> E), V_N / V_J of warp 0
+ * k-1 = gwarp * 256 + lane * 8 + sub.  257..2048 nodes: W warps of one block (CL = 1);
+ * 2049..4096 nodes: W warps in each block of a 2-block cluster (CL = 2, 255 registers x 16 warps do
+ * not fit one SM), exchanging through distributed shared memory.  What a single warp exchanges with
+ * shuffles is exchanged between warps through shared memory, three group barriers per row:
+ *   A   V_M / V_I of each warp's last node, per-warp max of V_M (-> E), V_N / V_J / V_C of warp 0
  *   B   each warp's last D after its local chain
- *   C   __syncthreads_or: did any warp's last D rise when the left neighbour's D came in?
+ *   C   group-wide OR: did any warp's last D rise when the left neighbour's D came in?
  *       (repeat B, C while it did -- exact lazy propagation, as inside a warp)
  */
 struct MwShared
 {
-    float vm_last[2][kMaxW], vi_last[2][kMaxW], e_warp[2][kMaxW];
-    float d_last[2][kMaxW];
+    float vm_last[2][kMaxGroupWarps], vi_last[2][kMaxGroupWarps], e_warp[2][kMaxGroupWarps];
+    float d_last[2][kMaxGroupWarps];
     float v_spec[2][4]; /* V_N, V_J, V_C of the row */
+    int flag[2][2];
     unsigned long long item;
 };
 
-template <int W, int R>
+template <int W, int CL, int R>
 __device__ __forceinline__ void mw_row(float (&tm)[5][8], float (&ti)[5][8], float (&tx)[5],
                                        const NodeParams<8> &p, RowState<8> &rs,
                                        const float *__restrict__ emis_lane, const RowRec *__restrict__ rec_next,
-                                       const uint16_t *__restrict__ w_next2, int warp, int lane, int par,
-                                       MwShared &sh, float NB, float JB, float EB, float cE, float cX,
+                                       const uint16_t *__restrict__ w_next2, int gw, int lane, int par,
+                                       Group<CL, MwShared> &grp, float NB, float JB, float EB, float cE, float cX,
                                        float &E_out, float &vC_out)
 {
     constexpr int Q = 8;
-    constexpr int ROW = 256 * W;
+    constexpr int TW = W * CL;
+    constexpr int ROW = 256 * TW;
     constexpr int S1 = (R + 4) % 5, S2 = (R + 3) % 5, S3 = (R + 2) % 5, S4 = (R + 1) % 5, S5 = R;
+    MwShared &sh = *grp.me;
 
     float vm[Q], vi[Q];
 #pragma unroll
@@ -380,7 +385,7 @@ __device__ __forceinline__ void mw_row(float (&tm)[5][8], float (&ti)[5][8], flo
     for (int i = 0; i < Q; ++i)
         vi[i] = fmaxf(max3(ti[S1][i] + rs.eI[0], ti[S2][i] + rs.eI[1], ti[S3][i] + rs.eI[2]),
                       fmaxf(ti[S4][i] + rs.eI[3], ti[S5][i] + rs.eI[4]));
-    /* N, J, C live in lanes 0..2 of warp 0 */
+    /* N, J, C live in lanes 0..2 of the group's first warp */
     float vx = fmaxf(max3(tx[S1] + rs.eN[0], tx[S2] + rs.eN[1], tx[S3] + rs.eN[2]),
                      fmaxf(tx[S4] + rs.eN[3], tx[S5] + rs.eN[4]));
 
@@ -389,7 +394,7 @@ __device__ __forceinline__ void mw_row(float (&tm)[5][8], float (&ti)[5][8], flo
     codes_of(rs.w1, code);
     load_emis_part<Q, 3, 5, ROW>(rs.em, emis_lane, code);
     load_row_insert(rec_next, rs.eI);
-    if (warp == 0 && lane < 3) load_row_special(rec_next, rs.eN);
+    if (gw == 0 && lane < 3) load_row_special(rec_next, rs.eN);
     rs.w1 = rs.w2;
     rs.w2 = __ldg(w_next2);
 
@@ -397,21 +402,26 @@ __device__ __forceinline__ void mw_row(float (&tm)[5][8], float (&ti)[5][8], flo
 #pragma unroll
     for (int i = 1; i < Q; ++i) eloc = fmaxf(eloc, vm[i]);
     float ew = warp_max(eloc);
-    if (lane == 31) sh.vm_last[par][warp] = vm[Q - 1], sh.vi_last[par][warp] = vi[Q - 1], sh.e_warp[par][warp] = ew;
-    if (warp == 0 && lane < 3) sh.v_spec[par][lane] = vx;
+    if (lane == 31)
+    {
+        GRP_PUT(grp, vm_last[par][gw], vm[Q - 1]);
+        GRP_PUT(grp, vi_last[par][gw], vi[Q - 1]);
+        GRP_PUT(grp, e_warp[par][gw], ew);
+    }
+    if (gw == 0 && lane < 3) GRP_PUT(grp, v_spec[par][lane], vx);
     float vm_prev = __shfl_up_sync(FULL, vm[Q - 1], 1);
     float vi_prev = __shfl_up_sync(FULL, vi[Q - 1], 1);
     load_emis_part<Q, 0, 3, ROW>(rs.em, emis_lane, code);
-    __syncthreads(); /* A */
+    grp.sync(); /* A */
 
     if (lane == 0)
     {
-        vm_prev = warp ? sh.vm_last[par][warp - 1] : NEG_INF;
-        vi_prev = warp ? sh.vi_last[par][warp - 1] : NEG_INF;
+        vm_prev = gw ? sh.vm_last[par][gw - 1] : NEG_INF;
+        vi_prev = gw ? sh.vi_last[par][gw - 1] : NEG_INF;
     }
     float E = sh.e_warp[par][0];
 #pragma unroll
-    for (int w = 1; w < W; ++w) E = fmaxf(E, sh.e_warp[par][w]);
+    for (int w = 1; w < TW; ++w) E = fmaxf(E, sh.e_warp[par][w]);
     const float vN = sh.v_spec[par][0], vJ = sh.v_spec[par][1], vC = sh.v_spec[par][2];
 
     /* D chain inside the warp with no carry from the left warp */
@@ -440,9 +450,9 @@ __device__ __forceinline__ void mw_row(float (&tm)[5][8], float (&ti)[5][8], flo
     for (int round = 0;; ++round)
     {
         const int b = round & 1;
-        if (lane == 31) sh.d_last[b][warp] = d[Q - 1];
-        __syncthreads(); /* B */
-        din0 = warp ? sh.d_last[b][warp - 1] : NEG_INF;
+        if (lane == 31) GRP_PUT(grp, d_last[b][gw], d[Q - 1]);
+        grp.sync(); /* B */
+        din0 = gw ? sh.d_last[b][gw - 1] : NEG_INF;
         const float before = __shfl_sync(FULL, d[Q - 1], 31);
         for (;;)
         {
@@ -460,7 +470,7 @@ __device__ __forceinline__ void mw_row(float (&tm)[5][8], float (&ti)[5][8], flo
             if (!__any_sync(FULL, d[Q - 1] > old)) break;
         }
         const float after = __shfl_sync(FULL, d[Q - 1], 31);
-        if (!__syncthreads_or(after > before)) break; /* C */
+        if (!grp.any(after > before, sh.flag, CL == 2 ? grp.peer->flag : sh.flag, b)) break; /* C */
     }
 
     float B = max3(vN + NB, vJ + JB, E + EB);
@@ -478,8 +488,8 @@ __device__ __forceinline__ void mw_row(float (&tm)[5][8], float (&ti)[5][8], flo
     vC_out = vC;
 }
 
-template <int W>
-__global__ void __launch_bounds__(W * 32, 8 / W)
+template <int W, int CL>
+__global__ void __launch_bounds__(W * 32, CL == 2 ? 1 : 8 / W)
 k_score_mw(const float *__restrict__ emis, const float *__restrict__ trans, const ProfMeta *__restrict__ metas,
            const uint32_t *__restrict__ class_profs, uint32_t n_class_profs, const SeqMeta *__restrict__ seqs,
            uint32_t nseq, uint64_t total_recs, const RowRec *__restrict__ rows,
@@ -487,16 +497,24 @@ k_score_mw(const float *__restrict__ emis, const float *__restrict__ trans, cons
            uint32_t nprof, unsigned long long *__restrict__ counter, uint32_t seq_tile)
 {
     constexpr int Q = 8;
-    constexpr int ROW = 256 * W;
+    constexpr int TW = W * CL;
+    constexpr int ROW = 256 * TW;
     __shared__ MwShared sh;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Group<CL, MwShared> grp;
+    grp.init(&sh);
+    const int lane = threadIdx.x & 31, gw = grp.rank * W + (threadIdx.x >> 5);
     const unsigned long long n_items = (unsigned long long)n_class_profs * nseq;
+    if (CL == 2) grp.sync(); /* both blocks' shared memory exists before the first remote store */
     for (;;)
     {
-        if (threadIdx.x == 0) sh.item = atomicAdd(counter, 1ULL);
-        __syncthreads();
+        if (grp.rank == 0 && threadIdx.x == 0)
+        {
+            unsigned long long it = atomicAdd(counter, 1ULL);
+            GRP_PUT(grp, item, it);
+        }
+        grp.sync();
         const unsigned long long item = sh.item;
-        __syncthreads();
+        grp.sync();
         if (item >= n_items) break;
         /* (sequence tile, profile, sequence in tile), as in k_score */
         const unsigned long long per_full_tile = (unsigned long long)seq_tile * n_class_profs;
@@ -507,8 +525,8 @@ k_score_mw(const float *__restrict__ emis, const float *__restrict__ trans, cons
         const uint32_t s = tile * seq_tile + (uint32_t)(in_tile % seqs_here);
         const ProfMeta pm = metas[prof];
         NodeParams<Q> p;
-        load_params<Q>(p, trans + pm.trans_off, 256 * W, warp * 256 + lane * Q);
-        const float *emis_lane = emis + pm.emis_off + warp * 256 + lane * 4;
+        load_params<Q>(p, trans + pm.trans_off, ROW, gw * 256 + lane * Q);
+        const float *emis_lane = emis + pm.emis_off + gw * 256 + lane * 4;
         const SeqMeta sm = seqs[s];
         const RowRec *recs = rows + (size_t)pm.null_id * total_recs + sm.rec_off;
         const uint16_t *wc = wcodes + sm.rec_off;
@@ -530,7 +548,7 @@ k_score_mw(const float *__restrict__ emis, const float *__restrict__ trans, cons
         }
 #pragma unroll
         for (int i = 0; i < Q; ++i) tm[4][i] = NB + p.ent[i];
-        tx[4] = (warp == 0 && lane == 0) ? NN : NEG_INF;
+        tx[4] = (gw == 0 && lane == 0) ? NN : NEG_INF;
 
         RowState<Q> rs;
 #pragma unroll
@@ -541,27 +559,27 @@ k_score_mw(const float *__restrict__ emis, const float *__restrict__ trans, cons
             load_emis<Q, ROW>(rs.em, emis_lane, code);
         }
         load_row_insert(recs + 1, rs.eI);
-        if (warp == 0 && lane < 3) load_row_special(recs + 1, rs.eN);
+        if (gw == 0 && lane < 3) load_row_special(recs + 1, rs.eN);
         rs.w1 = __ldg(wc + min(2u, L));
         rs.w2 = __ldg(wc + min(3u, L));
 
         float E = NEG_INF, vC = NEG_INF;
         uint32_t j = 1;
-#define MW_ARGS(jj) recs + min((uint32_t)(jj) + 1u, L), wc + min((uint32_t)(jj) + 3u, L), warp, lane, (int)((jj)&1u), sh
+#define MW_ARGS(jj) recs + min((uint32_t)(jj) + 1u, L), wc + min((uint32_t)(jj) + 3u, L), gw, lane, (int)((jj)&1u), grp
         for (; j + 4 <= L; j += 5)
         {
-            mw_row<W, 0>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j), NB, JB, EB, cE, cX, E, vC);
-            mw_row<W, 1>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 1), NB, JB, EB, cE, cX, E, vC);
-            mw_row<W, 2>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 2), NB, JB, EB, cE, cX, E, vC);
-            mw_row<W, 3>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 3), NB, JB, EB, cE, cX, E, vC);
-            mw_row<W, 4>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 4), NB, JB, EB, cE, cX, E, vC);
+            mw_row<W, CL, 0>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j), NB, JB, EB, cE, cX, E, vC);
+            mw_row<W, CL, 1>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 1), NB, JB, EB, cE, cX, E, vC);
+            mw_row<W, CL, 2>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 2), NB, JB, EB, cE, cX, E, vC);
+            mw_row<W, CL, 3>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 3), NB, JB, EB, cE, cX, E, vC);
+            mw_row<W, CL, 4>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 4), NB, JB, EB, cE, cX, E, vC);
         }
-        if (j <= L) mw_row<W, 0>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j), NB, JB, EB, cE, cX, E, vC);
-        if (j + 1 <= L) mw_row<W, 1>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 1), NB, JB, EB, cE, cX, E, vC);
-        if (j + 2 <= L) mw_row<W, 2>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 2), NB, JB, EB, cE, cX, E, vC);
-        if (j + 3 <= L) mw_row<W, 3>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 3), NB, JB, EB, cE, cX, E, vC);
+        if (j <= L) mw_row<W, CL, 0>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j), NB, JB, EB, cE, cX, E, vC);
+        if (j + 1 <= L) mw_row<W, CL, 1>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 1), NB, JB, EB, cE, cX, E, vC);
+        if (j + 2 <= L) mw_row<W, CL, 2>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 2), NB, JB, EB, cE, cX, E, vC);
+        if (j + 3 <= L) mw_row<W, CL, 3>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 3), NB, JB, EB, cE, cX, E, vC);
 #undef MW_ARGS
-        if (threadIdx.x == 0) alt_out[(size_t)s * nprof + prof] = fmaxf(E + ET, vC + CT);
+        if (gw == 0 && lane == 0) alt_out[(size_t)s * nprof + prof] = fmaxf(E + ET, vC + CT);
     }
 }
 
@@ -678,8 +696,8 @@ extern "C" enum rc dcpgpu_db_add(struct dcpgpu_db *db, struct protein_profile co
 {
     if (db->committed) return dcp_error(RC_EFAIL, "database already committed");
     if (prof->core_size == 0) return dcp_error(RC_EINVAL, "profile has not been absorbed");
-    if (prof->core_size > 32 * kMaxQ * kMaxW)
-        return dcp_error(RC_EINVAL, "core_size > 2048 is not supported by this build yet");
+    if (prof->core_size > DCP_PROTEIN_MODEL_CORE_SIZE_MAX)
+        return dcp_error(RC_EINVAL, "profile is too long"); /* limits.h:11, protein_profile.c:58 */
     if (db->epsilon >= 0.0f && db->epsilon != prof->cfg.epsilon)
         return dcp_error(RC_EINVAL, "all profiles of a database share one epsilon");
     /* the score pass takes E[j] = max_k V_Mk[j]; that needs delete scores to be log-probabilities */
@@ -722,7 +740,11 @@ extern "C" enum rc dcpgpu_db_commit(struct dcpgpu_db *db)
          * faster: 515 vs 489 GCUPS at M = 200.  Above 256 nodes W warps share one pair, 8 nodes per lane. */
         uint32_t Q = (M + 31) / 32, W = 1;
         if (Q == 7) Q = 8;
-        if (Q > 8) Q = 8, W = (M + 255) / 256;
+        if (Q > 8)
+        {
+            Q = 8, W = (M + 255) / 256;
+            if (W > kMaxW) W = (W + 1) / 2 * 2; /* two blocks of W/2 warps (cluster) */
+        }
         uint32_t QP = Q <= 4 ? 4 : 8;
         ProfMeta &m = db->metas[i];
         m.M = M, m.Q = Q, m.QP = QP, m.null_id = db->null_id[i];
@@ -742,7 +764,7 @@ extern "C" enum rc dcpgpu_db_commit(struct dcpgpu_db *db)
                        nprof * sizeof(ProfMeta);
 
     /* transpose per profile into pinned staging, upload in large pieces */
-    const size_t stage_floats = (size_t)kTab * 32 * 8 * kMaxW;
+    const size_t stage_floats = (size_t)kTab * 32 * 8 * kMaxGroupWarps;
     float *stage = nullptr;
     CU_TRY(cudaMallocHost(&stage, stage_floats * sizeof(float)));
     std::vector<float> tr;
@@ -1008,25 +1030,35 @@ extern "C" enum rc dcpgpu_scan_resident(struct dcpgpu_db *db, struct dcpgpu_seqs
         launches++;
         for (uint32_t id : db->class_list[q]) cells += (uint64_t)db->metas[id].M * sq->total;
     }
-    for (int w = 2; w <= kMaxW; ++w)
+    for (int q = kMaxQ + 2; q <= kNumClasses; ++q)
     {
-        const int q = kMaxQ + w;
         if (db->class_list[q].empty()) continue;
         uint32_t n_class = (uint32_t)db->class_list[q].size();
         unsigned long long *ctr = b_counter.as<unsigned long long>() + q;
-        const int mw_blocks = db->sm_count * (8 / w);
-#define LAUNCH_MW(WW)                                                                                          \
-    case WW:                                                                                                   \
-        k_score_mw<WW><<<mw_blocks, WW * 32, 0, st>>>(db->d_emis, db->d_trans, db->d_metas, db->d_class[q],    \
-                                                      n_class, sq->d_metas, nseq, total_recs,                 \
-                                                      b_rows.as<RowRec>(), b_wcodes.as<uint16_t>(),           \
-                                                      b_spec.as<float>(), res->d_alt, nprof, ctr, seq_tile);  \
-        break;
-        switch (w)
+        const int tw = q - kMaxQ;              /* warps per pair: 2..8 one block, 10/12/14/16 two blocks */
+        const int cl = tw > kMaxW ? 2 : 1, w = tw / cl;
+        const unsigned blocks = cl == 2 ? (unsigned)(db->sm_count / 2 * 2) : (unsigned)(db->sm_count * (8 / w));
+        cudaError_t le = cudaErrorInvalidValue;
+#define MW_LAUNCH(WW, CC)                                                                                     \
+    le = launch_group(k_score_mw<WW, CC>, CC, blocks, WW * 32, st, db->d_emis, db->d_trans, db->d_metas,      \
+                      db->d_class[q], n_class, sq->d_metas, nseq, total_recs, b_rows.as<RowRec>(),            \
+                      b_wcodes.as<uint16_t>(), b_spec.as<float>(), res->d_alt, nprof, ctr, seq_tile)
+        switch (tw)
         {
-            LAUNCH_MW(2) LAUNCH_MW(3) LAUNCH_MW(4) LAUNCH_MW(5) LAUNCH_MW(6) LAUNCH_MW(7) LAUNCH_MW(8)
+        case 2: MW_LAUNCH(2, 1); break;
+        case 3: MW_LAUNCH(3, 1); break;
+        case 4: MW_LAUNCH(4, 1); break;
+        case 5: MW_LAUNCH(5, 1); break;
+        case 6: MW_LAUNCH(6, 1); break;
+        case 7: MW_LAUNCH(7, 1); break;
+        case 8: MW_LAUNCH(8, 1); break;
+        case 10: MW_LAUNCH(5, 2); break;
+        case 12: MW_LAUNCH(6, 2); break;
+        case 14: MW_LAUNCH(7, 2); break;
+        case 16: MW_LAUNCH(8, 2); break;
         }
-#undef LAUNCH_MW
+#undef MW_LAUNCH
+        CU_TRY(le);
         launches++;
         for (uint32_t id : db->class_list[q]) cells += (uint64_t)db->metas[id].M * sq->total;
     }

@@ -15,8 +15,10 @@
 
 constexpr int kTab = DCP_FRAME_TABLE_SIZE;
 constexpr int kMaxQ = 8;          /* nodes per lane, single-warp classes cover M <= 256 */
-constexpr int kMaxW = 8;          /* warps per pair in the multi-warp classes: M <= 8 * 256 = 2048 */
-constexpr int kNumClasses = kMaxQ + kMaxW; /* class c: 1..8 = single warp with Q = c; 8 + W (W = 2..8) = W warps, Q = 8 */
+constexpr int kMaxW = 8;          /* warps per block in the multi-warp classes: M <= 8 * 256 = 2048 per block */
+constexpr int kMaxGroupWarps = 16; /* two blocks (a cluster) per pair above 2048 nodes: M <= 4096 */
+constexpr int kNumClasses = kMaxQ + kMaxGroupWarps; /* class c: 1..8 = one warp, Q = c; 8 + TW = TW warps per pair, Q = 8
+                                                     * (TW = 2..8 one block; 10, 12, 14, 16 two blocks) */
 constexpr int kWarpsPerBlock = 8; /* k_score block = 8 independent warps */
 constexpr int kSeqChunk = 4;      /* sequences per work item */
 

@@ -148,4 +148,75 @@ __device__ __forceinline__ void load_emis(float (&em)[5][Q], const float *__rest
     load_emis_part<Q, 0, 5, ROW>(em, emis_lane, code);
 }
 
+/* ----------------------------------------------------------------------------------------- */
+/* group of warps sharing one pair: W warps of one block (CL = 1) or of a 2-block cluster     */
+/* ----------------------------------------------------------------------------------------- */
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+
+/*
+ * Barrier / broadcast helpers.  With CL = 2 every value a warp publishes is stored into BOTH
+ * blocks' shared memory (distributed shared memory, cluster.map_shared_rank) so that reads stay
+ * local, and the block barrier becomes a cluster barrier.
+ */
+template <int CL, class Shared>
+struct Group
+{
+    Shared *me, *peer;
+    int rank;
+
+    __device__ __forceinline__ void init(Shared *mine)
+    {
+        me = mine, peer = nullptr, rank = 0;
+        if (CL == 2)
+        {
+            cg::cluster_group cl = cg::this_cluster();
+            rank = (int)cl.block_rank();
+            peer = cl.map_shared_rank(mine, rank ^ 1);
+        }
+    }
+    __device__ __forceinline__ void sync()
+    {
+        if (CL == 2) cg::this_cluster().sync();
+        else __syncthreads();
+    }
+    /* OR of a predicate over every thread of the group; `flag` = two ints per block, caller alternates slot */
+    __device__ __forceinline__ bool any(bool pred, int (*flag)[2], int (*peer_flag)[2], int slot)
+    {
+        bool r = __syncthreads_or(pred);
+        if (CL == 2)
+        {
+            if (threadIdx.x == 0) flag[slot][rank] = r, peer_flag[slot][rank] = r;
+            cg::this_cluster().sync();
+            r = flag[slot][0] | flag[slot][1];
+        }
+        return r;
+    }
+};
+#define GRP_PUT(grp, field, value)                                                                  \
+    do                                                                                              \
+    {                                                                                               \
+        (grp).me->field = (value);                                                                  \
+        if (CL == 2) (grp).peer->field = (value);                                                   \
+    } while (0)
+
+/* launch helper: plain launch for one block per pair, cluster launch (2 blocks) above 2048 nodes */
+template <class... Params, class... Args>
+static cudaError_t launch_group(void (*kernel)(Params...), int cl, unsigned blocks, unsigned threads, cudaStream_t st,
+                                Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(blocks), cfg.blockDim = dim3(threads), cfg.dynamicSmemBytes = 0, cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    if (cl == 2)
+    {
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr, cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
+}
+
+
 #endif

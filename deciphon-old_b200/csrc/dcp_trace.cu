@@ -272,24 +272,28 @@ __global__ void __launch_bounds__(128) k_trace(const float *__restrict__ emis, c
 /* ----------------------------------------------------------------------------------------- */
 struct MwTraceShared
 {
-    float pM[2][kMaxW][5], pI[2][kMaxW][5]; /* the five sums of each warp's last node */
-    float d_last[2][kMaxW];
-    float e_best[2][kMaxW];
-    int e_code[2][kMaxW];
+    float pM[2][kMaxGroupWarps][5], pI[2][kMaxGroupWarps][5]; /* the five sums of each warp's last node */
+    float d_last[2][kMaxGroupWarps];
+    float e_best[2][kMaxGroupWarps];
+    int e_code[2][kMaxGroupWarps];
+    int flag[2][2];
 };
 
 /* cell backpointers of a row: [sub-node][warp][lane] */
-template <int W, int R>
+template <int W, int CL, int R>
 __device__ __forceinline__ void trace_row_mw(float (&tm)[5][8], float (&ti)[5][8], float (&tn)[5], float (&tj)[5],
                                              float (&tc)[5], const NodeParams<8> &p,
                                              const float *__restrict__ emis_lane, const RowRec *__restrict__ rec,
-                                             uint32_t wcode, int warp, int lane, int par, MwTraceShared &sh,
+                                             uint32_t wcode, int warp, int lane, int par,
+                                             Group<CL, MwTraceShared> &grp,
                                              const float *__restrict__ sp, uint16_t *__restrict__ cell_bp,
                                              uint32_t *__restrict__ row_bp, float &T_out)
 {
     constexpr int Q = 8;
-    constexpr int ROW = 256 * W;
+    constexpr int TW = W * CL; /* `warp` is the warp's index in the whole group, 0..TW-1 */
+    constexpr int ROW = 256 * TW;
     constexpr int S[5] = {(R + 4) % 5, (R + 3) % 5, (R + 2) % 5, (R + 1) % 5, R};
+    MwTraceShared &sh = *grp.me;
     const float NN = sp[0], CC = sp[1], JJ = sp[2], NB = sp[3], CT = sp[4], JB = sp[5];
     const float ET = sp[9], ECC = sp[10], EB = sp[11], EJJ = sp[12];
     struct { float eI[5], eN[5]; } in;
@@ -319,7 +323,11 @@ __device__ __forceinline__ void trace_row_mw(float (&tm)[5][8], float (&ti)[5][8
     }
     if (lane == 31)
 #pragma unroll
-        for (int l = 0; l < 5; ++l) sh.pM[par][warp][l] = sM[Q - 1][l], sh.pI[par][warp][l] = sI[Q - 1][l];
+        for (int l = 0; l < 5; ++l)
+        {
+            GRP_PUT(grp, pM[par][warp][l], sM[Q - 1][l]);
+            GRP_PUT(grp, pI[par][warp][l], sI[Q - 1][l]);
+        }
     float pM0[5], pI0[5];
 #pragma unroll
     for (int l = 0; l < 5; ++l)
@@ -327,7 +335,7 @@ __device__ __forceinline__ void trace_row_mw(float (&tm)[5][8], float (&ti)[5][8
         pM0[l] = __shfl_up_sync(FULL, sM[Q - 1][l], 1);
         pI0[l] = __shfl_up_sync(FULL, sI[Q - 1][l], 1);
     }
-    __syncthreads(); /* A */
+    grp.sync(); /* A */
     if (lane == 0)
 #pragma unroll
         for (int l = 0; l < 5; ++l)
@@ -361,8 +369,8 @@ __device__ __forceinline__ void trace_row_mw(float (&tm)[5][8], float (&ti)[5][8
         float din0 = NEG_INF;
         if (round > 0)
         {
-            if (lane == 31) sh.d_last[b][warp] = d[Q - 1];
-            __syncthreads(); /* B */
+            if (lane == 31) GRP_PUT(grp, d_last[b][warp], d[Q - 1]);
+            grp.sync(); /* B */
             din0 = warp ? sh.d_last[b][warp - 1] : NEG_INF;
         }
         const float before = __shfl_sync(FULL, d[Q - 1], 31);
@@ -383,7 +391,7 @@ __device__ __forceinline__ void trace_row_mw(float (&tm)[5][8], float (&ti)[5][8
         }
         const float after = __shfl_sync(FULL, d[Q - 1], 31);
         /* round 0 is the warp-local chain: always go on to exchange carries at least once */
-        if (!__syncthreads_or(round == 0 || after > before)) break; /* C */
+        if (!grp.any(round == 0 || after > before, sh.flag, CL == 2 ? grp.peer->flag : sh.flag, b)) break; /* C */
     }
 
     /* E: first max over M_1, M_2, D_2, ... ; warps and lanes hold increasing k */
@@ -404,12 +412,16 @@ __device__ __forceinline__ void trace_row_mw(float (&tm)[5][8], float (&ti)[5][8
     float ew = warp_max(ebest);
     unsigned who = __ballot_sync(FULL, ebest == ew);
     ecode = __shfl_sync(FULL, ecode, who ? __ffs(who) - 1 : 0);
-    if (lane == 0) sh.e_best[par][warp] = ew, sh.e_code[par][warp] = ecode;
-    __syncthreads(); /* D */
+    if (lane == 0)
+    {
+        GRP_PUT(grp, e_best[par][warp], ew);
+        GRP_PUT(grp, e_code[par][warp], ecode);
+    }
+    grp.sync(); /* D */
     float E = sh.e_best[par][0];
     ecode = sh.e_code[par][0];
 #pragma unroll
-    for (int w = 1; w < W; ++w)
+    for (int w = 1; w < TW; ++w)
         if (sh.e_best[par][w] > E) E = sh.e_best[par][w], ecode = sh.e_code[par][w];
 
     /* specials: every warp keeps its own copy of the N/J/C rings (identical values) */
@@ -436,7 +448,7 @@ __device__ __forceinline__ void trace_row_mw(float (&tm)[5][8], float (&ti)[5][8
     first_max5(sC, CT, 1, best, tcode);
     T_out = best;
     tn[R] = tinN, tj[R] = tinJ, tc[R] = tinC;
-    if (threadIdx.x == 0)
+    if (warp == 0 && lane == 0)
         *row_bp = (uint32_t)ecode | (uint32_t)ncode << 15 | (uint32_t)bcode << 18 | (uint32_t)jcode << 22 |
                   (uint32_t)ccode << 25 | (uint32_t)tcode << 28;
 
@@ -465,11 +477,11 @@ __device__ __forceinline__ void trace_row_mw(float (&tm)[5][8], float (&ti)[5][8
         first_max5(sI[i], p.II[i], 5, ib, icode);
         tm[R][i] = mb;
         ti[R][i] = ib;
-        cell_bp[i * (32 * W) + warp * 32 + lane] = (uint16_t)(mcode | icode << 4 | dcode[i] << 8);
+        cell_bp[i * (32 * TW) + warp * 32 + lane] = (uint16_t)(mcode | icode << 4 | dcode[i] << 8);
     }
 }
 
-template <int W>
+template <int W, int CL>
 __global__ void __launch_bounds__(W * 32) k_trace_mw(const float *__restrict__ emis, const float *__restrict__ trans,
                                                      const ProfMeta *__restrict__ metas,
                                                      const SeqMeta *__restrict__ seqs, uint64_t total_rows,
@@ -481,15 +493,18 @@ __global__ void __launch_bounds__(W * 32) k_trace_mw(const float *__restrict__ e
                                                      float *__restrict__ alt_out)
 {
     constexpr int Q = 8;
+    constexpr int TW = W * CL;
     __shared__ MwTraceShared sh;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t job = blockIdx.x;
+    Group<CL, MwTraceShared> grp;
+    grp.init(&sh);
+    const int lane = threadIdx.x & 31, warp = grp.rank * W + (threadIdx.x >> 5);
+    const uint32_t job = blockIdx.x / CL;
     if (job >= njobs) return;
     TraceJob tj_ = jobs[job];
     ProfMeta pm = metas[tj_.prof];
     SeqMeta sm = seqs[tj_.seq];
     NodeParams<Q> p;
-    load_params<Q>(p, trans + pm.trans_off, 256 * W, warp * 256 + lane * Q);
+    load_params<Q>(p, trans + pm.trans_off, 256 * TW, warp * 256 + lane * Q);
     const float *emis_lane = emis + pm.emis_off + warp * 256 + lane * 4;
     const RowRec *r = rows + (size_t)pm.null_id * total_rows + sm.rec_off; /* r[j] = record of row j */
     const uint16_t *wc = wcodes + sm.rec_off;
@@ -497,7 +512,7 @@ __global__ void __launch_bounds__(W * 32) k_trace_mw(const float *__restrict__ e
     uint16_t *cb = cell_bp + tj_.cell_off;
     uint32_t *rb = row_bp + tj_.row_off;
     const uint32_t L = sm.len;
-    constexpr uint32_t CS = Q * 32 * W;
+    constexpr uint32_t CS = Q * 32 * TW;
 
     float tm[5][Q], ti[5][Q], tn[5], tjr[5], tc[5];
 #pragma unroll
@@ -512,28 +527,30 @@ __global__ void __launch_bounds__(W * 32) k_trace_mw(const float *__restrict__ e
     for (int i = 0; i < Q; ++i)
     {
         tm[4][i] = NB + p.ent[i];
-        cb[i * (32 * W) + warp * 32 + lane] = 0;
+        cb[i * (32 * TW) + warp * 32 + lane] = 0;
     }
     tn[4] = NN;
-    if (threadIdx.x == 0) rb[0] = 0;
+    if (warp == 0 && lane == 0) rb[0] = 0;
+    if (CL == 2) grp.sync(); /* both blocks' shared memory exists before the first remote store */
 
     float T = NEG_INF;
     uint32_t j = 1;
-#define TR_ARGS(jj) r + (jj), wc[(jj)], warp, lane, (int)((jj)&1u), sh, sp, cb + (size_t)(jj) * CS, rb + (jj), T
+#define TR_ARGS(jj) r + (jj), wc[(jj)], warp, lane, (int)((jj)&1u), grp, sp, cb + (size_t)(jj) * CS, rb + (jj), T
     for (; j + 4 <= L; j += 5)
     {
-        trace_row_mw<W, 0>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j));
-        trace_row_mw<W, 1>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j + 1));
-        trace_row_mw<W, 2>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j + 2));
-        trace_row_mw<W, 3>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j + 3));
-        trace_row_mw<W, 4>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j + 4));
+        trace_row_mw<W, CL, 0>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j));
+        trace_row_mw<W, CL, 1>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j + 1));
+        trace_row_mw<W, CL, 2>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j + 2));
+        trace_row_mw<W, CL, 3>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j + 3));
+        trace_row_mw<W, CL, 4>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j + 4));
     }
-    if (j <= L) trace_row_mw<W, 0>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j));
-    if (j + 1 <= L) trace_row_mw<W, 1>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j + 1));
-    if (j + 2 <= L) trace_row_mw<W, 2>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j + 2));
-    if (j + 3 <= L) trace_row_mw<W, 3>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j + 3));
+    if (j <= L) trace_row_mw<W, CL, 0>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j));
+    if (j + 1 <= L) trace_row_mw<W, CL, 1>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j + 1));
+    if (j + 2 <= L) trace_row_mw<W, CL, 2>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j + 2));
+    if (j + 3 <= L) trace_row_mw<W, CL, 3>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j + 3));
 #undef TR_ARGS
-    if (threadIdx.x == 0) alt_out[job] = T;
+    if (warp == 0 && lane == 0) alt_out[job] = T;
+    if (CL == 2) grp.sync(); /* no block may exit while its peer can still store into its shared memory */
 }
 
 /*
@@ -741,17 +758,17 @@ enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const
         launch_trace<QQ>(st, b - a, db, sq, d_rows, d_wcodes, d_spec, b_jobs.as<TraceJob>() + a,                  \
                          b_cells.as<uint16_t>(), b_rows.as<uint32_t>(), b_alt.as<float>() + a);                  \
         break;
-#define LTW(WW)                                                                                                  \
-    case kMaxQ + WW:                                                                                             \
-        k_trace_mw<WW><<<b - a, WW * 32, 0, st>>>(db->d_emis, db->d_trans, db->d_metas, sq->d_metas,             \
-                                                  sq->total + sq->nseq, d_rows, d_wcodes, d_spec,                \
-                                                  b_jobs.as<TraceJob>() + a, b - a, b_cells.as<uint16_t>(),      \
-                                                  b_rows.as<uint32_t>(), b_alt.as<float>() + a);                 \
+#define LTW(TWW, WW, CC)                                                                                         \
+    case kMaxQ + TWW:                                                                                            \
+        launch_group(k_trace_mw<WW, CC>, CC, (b - a) * CC, WW * 32, st, db->d_emis, db->d_trans, db->d_metas,     \
+                     sq->d_metas, sq->total + sq->nseq, d_rows, d_wcodes, d_spec, b_jobs.as<TraceJob>() + a,     \
+                     b - a, b_cells.as<uint16_t>(), b_rows.as<uint32_t>(), b_alt.as<float>() + a);               \
         break;
             switch (cls)
             {
                 LT(1) LT(2) LT(3) LT(4) LT(5) LT(6) LT(7) LT(8)
-                LTW(2) LTW(3) LTW(4) LTW(5) LTW(6) LTW(7) LTW(8)
+                LTW(2, 2, 1) LTW(3, 3, 1) LTW(4, 4, 1) LTW(5, 5, 1) LTW(6, 6, 1) LTW(7, 7, 1) LTW(8, 8, 1)
+                LTW(10, 5, 2) LTW(12, 6, 2) LTW(14, 7, 2) LTW(16, 8, 2)
             }
 #undef LT
 #undef LTW

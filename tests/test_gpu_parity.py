@@ -87,7 +87,7 @@ def test_every_lane_layout(pkg, o32, M):
     check_scan(pkg, o32, db, twins, seqs, thr=-1e30, rows=False)
 
 
-@pytest.mark.parametrize("M", [257, 300, 512, 513, 777, 1024, 1500, 2048])
+@pytest.mark.parametrize("M", [257, 300, 512, 513, 777, 1024, 1500, 2048, 2049, 2561, 3000, 3585, 4096])
 def test_multi_warp_profiles(pkg, o32, M):
     """Profiles above 256 nodes: several warps per pair, carries exchanged through shared memory."""
     db, twins = make_db(pkg, o32, [(M, M, 2), (M + 1, 40, 2)], 0.01)
@@ -180,7 +180,7 @@ def test_error_paths(pkg, o32):
     with pytest.raises(pkg.DcpError):
         db.add(pkg.ProteinProfile.sample(1, 5))  # already committed
     with pytest.raises(pkg.DcpError) as e:
-        pkg.Db(0).add(pkg.ProteinProfile.sample(3, 2049, pkg.protein_cfg(2, 0.01)))  # > 2048 nodes: not yet
+        pkg.ProteinProfile.sample(3, 4097, pkg.protein_cfg(2, 0.01))  # PROTEIN_MODEL_CORE_SIZE_MAX = 4096
     assert e.value.rc == pkg.RC_EINVAL
     db2 = pkg.Db(0)
     db2.add(pkg.ProteinProfile.sample(1, 5, pkg.protein_cfg(2, 0.01)))

@@ -133,12 +133,12 @@ def test_config3_shape_pfam_lengths(pkg, o32):
 
 
 def test_config4_shape_long_profiles_long_contigs(pkg):
-    """configs[3] shape: long profiles (M ~ 2000) x 10 kbp contigs: multi-warp kernels, large traceback."""
+    """configs[3] shape: long profiles (M ~ 3000) x 10 kbp contigs: two-block cluster kernels, large traceback."""
     rng = np.random.default_rng(4)
-    db, profs, models = build_db(pkg, rng, [2000, 1800, 1500])
+    db, profs, models = build_db(pkg, rng, [3000, 2900, 2100])
     contigs = []
     for i in range(6):
-        core = sample_read(rng, models[i % 3][1], 3 * len(models[i % 3][1]) + 300, 0.01, 0.01)
+        core = sample_read(rng, models[i % 3][1], 3 * len(models[i % 3][1]) + 300, 0.01, 0.01)[:9000]
         pad = 10000 - len(core)
         contigs.append(random_seq(rng, pad // 2) + core + random_seq(rng, pad - pad // 2))
     res = db.scan(contigs)
