@@ -292,7 +292,7 @@ __device__ __forceinline__ float score_pair(const NodeParams<Q> &p, const float 
 }
 
 template <int Q>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 1)
+__global__ void __launch_bounds__(score_warps(Q) * 32, 1)
 k_score(const float *__restrict__ emis, const float *__restrict__ trans, const ProfMeta *__restrict__ metas,
         const uint32_t *__restrict__ class_profs, uint32_t n_class_profs, const SeqMeta *__restrict__ seqs,
         uint32_t nseq, uint64_t total_recs, const RowRec *__restrict__ rows, const uint16_t *__restrict__ wcodes,
@@ -347,11 +347,13 @@ k_score(const float *__restrict__ emis, const float *__restrict__ trans, const P
  * k-1 = gwarp * 256 + lane * 8 + sub.  257..2048 nodes: W warps of one block (CL = 1);
  * 2049..4096 nodes: W warps in each block of a 2-block cluster (CL = 2, 255 registers x 16 warps do
  * not fit one SM), exchanging through distributed shared memory.  What a single warp exchanges with
- * shuffles is exchanged between warps through shared memory, three group barriers per row:
- *   A   V_M / V_I of each warp's last node, per-warp max of V_M (-> E), V_N / V_J / V_C of warp 0
- *   B   each warp's last D after its local chain
- *   C   group-wide OR: did any warp's last D rise when the left neighbour's D came in?
- *       (repeat B, C while it did -- exact lazy propagation, as inside a warp)
+ * shuffles is exchanged between warps through shared memory, two group barriers per row:
+ *   A   V_M / V_I / D of each warp's last node (D from the warp-local chain), per-warp max of V_M (-> E),
+ *       V_N / V_J / V_C of warp 0
+ *   C   group-wide OR: did any warp's last D rise when the left neighbour's values came in?
+ *       (if so publish the new D, barrier B, and repeat -- exact lazy propagation, as inside a warp)
+ * Measured alternatives that were not faster: keeping 8 warps per SM with 5 or 6 nodes per lane
+ * (M = 600: 252 vs 267 GCUPS) -- the barriers, not the occupancy, bound these kernels.
  */
 struct MwShared
 {
@@ -402,17 +404,42 @@ __device__ __forceinline__ void mw_row(float (&tm)[5][8], float (&ti)[5][8], flo
 #pragma unroll
     for (int i = 1; i < Q; ++i) eloc = fmaxf(eloc, vm[i]);
     float ew = warp_max(eloc);
+    float vm_prev = __shfl_up_sync(FULL, vm[Q - 1], 1);
+    float vi_prev = __shfl_up_sync(FULL, vi[Q - 1], 1);
+    load_emis_part<Q, 0, 3, ROW>(rs.em, emis_lane, code);
+
+    /* D chain inside the warp, nothing from the warp to the left yet: the warp's first node starts at -inf
+     * (its M->D and D->D sources both live in the left warp and arrive together after barrier A) */
+    float d[Q];
+    d[0] = lane == 0 ? NEG_INF : vm_prev + p.MD[0];
+#pragma unroll
+    for (int i = 1; i < Q; ++i) d[i] = fmaxf(vm[i - 1] + p.MD[i], d[i - 1] + p.DD[i]);
+    float din;
+    for (;;)
+    {
+        float old = d[Q - 1];
+        din = __shfl_up_sync(FULL, old, 1);
+        float x = lane == 0 ? NEG_INF : din + p.DD[0];
+        d[0] = fmaxf(d[0], x);
+        x = d[0];
+#pragma unroll
+        for (int i = 1; i < Q; ++i)
+        {
+            x = x + p.DD[i];
+            d[i] = fmaxf(d[i], x);
+            x = d[i];
+        }
+        if (!__any_sync(FULL, d[Q - 1] > old)) break;
+    }
     if (lane == 31)
     {
         GRP_PUT(grp, vm_last[par][gw], vm[Q - 1]);
         GRP_PUT(grp, vi_last[par][gw], vi[Q - 1]);
         GRP_PUT(grp, e_warp[par][gw], ew);
+        GRP_PUT(grp, d_last[0][gw], d[Q - 1]);
     }
     if (gw == 0 && lane < 3) GRP_PUT(grp, v_spec[par][lane], vx);
-    float vm_prev = __shfl_up_sync(FULL, vm[Q - 1], 1);
-    float vi_prev = __shfl_up_sync(FULL, vi[Q - 1], 1);
-    load_emis_part<Q, 0, 3, ROW>(rs.em, emis_lane, code);
-    grp.sync(); /* A */
+    grp.sync(); /* A: boundary values, per-warp maxima, specials and the local D chains' ends */
 
     if (lane == 0)
     {
@@ -424,34 +451,16 @@ __device__ __forceinline__ void mw_row(float (&tm)[5][8], float (&ti)[5][8], flo
     for (int w = 1; w < TW; ++w) E = fmaxf(E, sh.e_warp[par][w]);
     const float vN = sh.v_spec[par][0], vJ = sh.v_spec[par][1], vC = sh.v_spec[par][2];
 
-    /* D chain inside the warp with no carry from the left warp */
-    float d[Q];
-    d[0] = vm_prev + p.MD[0];
-#pragma unroll
-    for (int i = 1; i < Q; ++i) d[i] = fmaxf(vm[i - 1] + p.MD[i], d[i - 1] + p.DD[i]);
-    float din;
-    for (;;)
-    {
-        float old = d[Q - 1];
-        din = __shfl_up_sync(FULL, old, 1);
-        if (lane == 0) din = NEG_INF;
-        float x = din;
-#pragma unroll
-        for (int i = 0; i < Q; ++i)
-        {
-            x = x + p.DD[i];
-            d[i] = fmaxf(d[i], x);
-            x = d[i];
-        }
-        if (!__any_sync(FULL, d[Q - 1] > old)) break;
-    }
-    /* carries between warps */
+    /* carries between warps: D of the warp's first node = max(V_M(left) + MD, D(left) + DD), then lazily on */
     float din0 = NEG_INF; /* D of the last node of the warp to the left */
     for (int round = 0;; ++round)
     {
         const int b = round & 1;
-        if (lane == 31) GRP_PUT(grp, d_last[b][gw], d[Q - 1]);
-        grp.sync(); /* B */
+        if (round > 0)
+        {
+            if (lane == 31) GRP_PUT(grp, d_last[b][gw], d[Q - 1]);
+            grp.sync(); /* B */
+        }
         din0 = gw ? sh.d_last[b][gw - 1] : NEG_INF;
         const float before = __shfl_sync(FULL, d[Q - 1], 31);
         for (;;)
@@ -459,9 +468,11 @@ __device__ __forceinline__ void mw_row(float (&tm)[5][8], float (&ti)[5][8], flo
             float old = d[Q - 1];
             din = __shfl_up_sync(FULL, old, 1);
             if (lane == 0) din = din0;
-            float x = din;
+            float x = lane == 0 ? fmaxf(vm_prev + p.MD[0], din0 + p.DD[0]) : din + p.DD[0];
+            d[0] = fmaxf(d[0], x);
+            x = d[0];
 #pragma unroll
-            for (int i = 0; i < Q; ++i)
+            for (int i = 1; i < Q; ++i)
             {
                 x = x + p.DD[i];
                 d[i] = fmaxf(d[i], x);
@@ -629,7 +640,7 @@ void launch_score(int nblocks, cudaStream_t st, const float *emis, const float *
 {
     /* no shared memory: give the whole unified array to L1 (emission lines, row records) */
     cudaFuncSetAttribute(k_score<Q>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
-    k_score<Q><<<nblocks, kWarpsPerBlock * 32, 0, st>>>(emis, trans, metas, class_profs, n_class, seqs, nseq,
+    k_score<Q><<<nblocks, score_warps(Q) * 32, 0, st>>>(emis, trans, metas, class_profs, n_class, seqs, nseq,
                                                         total_rows, rows, wcodes, spec, alt, nprof, counter, seq_tile);
 }
 
