@@ -37,10 +37,19 @@ OPS_PER_CELL = 33  # 18 FADD + 15 two-input max
 INSTR_PER_CELL = 27  # 18 FADD + 9 FMNMX3
 
 
+WORKLOAD = "config2"
+
+
 def gen_models(n, M, seed):
     from common import plan7_profile_inputs
     rng = np.random.default_rng(seed)
-    return [plan7_profile_inputs(rng, M) for _ in range(n)]
+    if WORKLOAD in ("pfam", "short"):  # clipped log-normal, median ~130
+        sizes = np.clip(np.exp(rng.normal(np.log(130), 0.75, n)), 50, 2000).astype(int)
+    elif WORKLOAD == "long":
+        sizes = rng.integers(2800, 3200, n)
+    else:
+        sizes = [M] * n
+    return [plan7_profile_inputs(rng, int(m)) for m in sizes]
 
 
 def gen_reads(models, nreads, L, seed):
@@ -146,17 +155,24 @@ def main():
     ap.add_argument("--profiles", type=int, default=1000, help="profiles per GPU")
     ap.add_argument("--reads", type=int, default=10000)
     ap.add_argument("--core", type=int, default=CORE, help="profile core length (experiments; the metric is quoted at 200)")
+    ap.add_argument("--workload", default="config2", choices=["config2", "pfam", "long", "short"],
+                    help="config2 (default, the headline metric) or a scaled-down shape of BASELINE configs 3/4/5: "
+                         "pfam = Pfam length distribution 50..2000 x 1.5 kbp reads, long = core ~3000 x 10 kbp contigs, "
+                         "short = Pfam lengths x 150 bp reads (secondary numbers for DESIGN.md, not the bench line)")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     ap.add_argument("--no-cpu", action="store_true")
     a = ap.parse_args()
     globals()["CORE"] = a.core
+    globals()["WORKLOAD"] = a.workload
+    if a.workload != "config2":
+        globals()["READ_LEN"] = {"pfam": 1500, "long": 10000, "short": 150}[a.workload]
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     import __graft_entry__ as ge
     pkg = ge.load_pkg()
-    config = {"workload": "configs[1]: %d synthetic profiles (core length %d) per GPU x %d synthetic %d nt frameshifted "
+    config = {"workload": ("configs[1]" if a.workload == "config2" else "shape of " + a.workload) + ": %d synthetic profiles (core length %d) per GPU x %d synthetic %d nt frameshifted "
                           "coding reads, multi_hits, LRT>=10, traceback of hits" % (a.profiles, CORE, a.reads, READ_LEN),
               "profiles_per_gpu": a.profiles, "reads": a.reads, "core_length": CORE, "read_length": READ_LEN,
               "sharding": "profiles by cumulative core length, no collective", "l2": "emission tables %.2f GB per GPU >> 126 MB L2"
@@ -273,7 +289,9 @@ def main():
     peak_ops = alu["mix_ginst"] * 1e9 * OPS_PER_CELL / INSTR_PER_CELL  # lane-ops/s at the measured mix issue rate
     achieved_ops = cells * OPS_PER_CELL / (k_ms * 1e-3)
     # algorithmic HBM bytes of one score launch: tables once + row records once per profile + outputs
-    alg_bytes = len(mine) * (202 * 1364 * 4 + 8 * 201 * 4) + sum(len(x) for x in reads) * 64 + len(reads) * len(mine) * 4
+    # tables (M+2 emission tables, 8 transition scores per node) + row records + one score per pair
+    alg_bytes = (sum((models[i][1].shape[0] + 2) * 1364 * 4 + 8 * (models[i][1].shape[0] + 1) * 4 for i in mine)
+                 + sum(len(x) for x in reads) * 66 + len(reads) * len(mine) * 4)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
