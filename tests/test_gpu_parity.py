@@ -156,6 +156,28 @@ def test_multiple_hits_per_read(pkg, o32):
     assert not any(st == pkg.PROTEIN_J_STATE for st, _ in res2.hit_at(0)[2])
 
 
+def test_exact_ties_follow_the_documented_order(pkg, o32):
+    """Degenerate profiles (every node identical, homopolymer reads) create exact score ties everywhere; the
+    GPU takes the same winner as the oracle: first maximum in (transition order, source length) -- DESIGN.md 3."""
+    M = 70
+    null_lp = np.log(np.full(20, 0.05))
+    match_lp = np.tile(np.log(np.full(20, 0.05)), (M, 1))
+    t = np.log(np.array([0.90, 0.05, 0.05, 0.5, 0.5, 0.5, 0.5]))
+    tr = np.tile(t, (M + 1, 1))
+    tr[0][6] = -np.inf
+    tr[M][2] = tr[M][6] = -np.inf
+    for entry in (pkg.ENTRY_DIST_UNIFORM, pkg.ENTRY_DIST_OCCUPANCY):
+        p = pkg.ProteinProfile.from_model(null_lp, match_lp, tr, pkg.protein_cfg(entry, 0.01), "TIES")
+        db = pkg.Db(0)
+        db.add(p)
+        db.commit()
+        tw = [oracle_twin(o32, p, 0.01)]
+        seqs = ["A" * 90, "ACG" * 40, "AAAC" * 25, "G" * 7]
+        for mh in (True, False):
+            res, ref = check_scan(pkg, o32, db, tw, seqs, multi_hits=mh, thr=-1e30)
+            assert res.nhits == len(seqs)
+
+
 def test_scores_only_and_resident_path(pkg, o32):
     db, twins = make_db(pkg, o32, [(1, 40, 2), (2, 70, 2)], 0.01)
     rng = np.random.default_rng(9)
