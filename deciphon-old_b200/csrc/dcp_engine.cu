@@ -97,6 +97,37 @@ __global__ void k_null(const SeqMeta *__restrict__ seqs, uint32_t nseq, uint32_t
 /* ----------------------------------------------------------------------------------------- */
 /* alt Viterbi, score pass                                                                   */
 /* ----------------------------------------------------------------------------------------- */
+/* ---- TMA (cp.async.bulk) + mbarrier helpers for the streamed 4/5-nt emission lines ---- */
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+/* one bulk copy global -> shared (SASS UBLKCP), completion counted in bytes on `bar` */
+__device__ __forceinline__ void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok = 0;
+    for (uint32_t spin = 0; !ok; ++spin)
+    {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+        if (spin > (1u << 26)) __trap(); /* a lost bulk copy must not hang the GPU */
+    }
+}
+
 /* loads in flight for the next row(s) */
 template <int Q>
 struct RowState
@@ -105,6 +136,7 @@ struct RowState
     float eI[5], eN[5];
     uint32_t w1;       /* window of the row after it (addresses of the next emission loads) */
     uint32_t w2;       /* window two rows ahead, in flight */
+    uint32_t w3;       /* TMA variant: window three rows ahead */
 };
 
 /*
@@ -119,15 +151,45 @@ struct RowState
  *   rs.w1            window of row j+1, loaded during row j-1: addresses of row j+1's emission loads
  *   rs.w2            window of row j+2, loaded here
  */
-template <int Q, int R>
+/* per-warp staging of the streamed lines: [2 stages][4-nt line, 5-nt line][32 * QP floats] + 2 mbarriers */
+struct TmaCtx
+{
+    float *ring;
+    uint64_t *bar;
+    uint32_t g; /* rows issued so far by this warp: stage = g & 1, phase parity = (g >> 1) & 1 */
+};
+
+template <int Q, int R, bool TMA>
 __device__ __forceinline__ void score_row(float (&tm)[5][Q], float (&ti)[5][Q], float (&tx)[5],
                                           const NodeParams<Q> &p, RowState<Q> &rs,
                                           const float *__restrict__ emis_lane,
                                           const RowRec *__restrict__ rec_next,
                                           const uint16_t *__restrict__ w_next2, int lane, float NB, float JB,
-                                          float EB, float cE, float cX, float &E_out, float &vx_out)
+                                          float EB, float cE, float cX, float &E_out, float &vx_out, TmaCtx &tc)
 {
     constexpr int S1 = (R + 4) % 5, S2 = (R + 3) % 5, S3 = (R + 2) % 5, S4 = (R + 1) % 5, S5 = R;
+    constexpr int QP = Q <= 4 ? 4 : 8, LINE = 32 * QP;
+
+    if constexpr (TMA)
+    {
+        /* this row's 4- and 5-nt lines were bulk-copied into the stage two rows ago */
+        const uint32_t st = tc.g & 1u;
+        mbar_wait(tc.bar + st, (tc.g >> 1) & 1u);
+#pragma unroll
+        for (int l = 3; l < 5; ++l)
+        {
+            const float4 *line = reinterpret_cast<const float4 *>(tc.ring + (st * 2 + (l - 3)) * LINE);
+            float4 a = line[lane];
+            float t[8] = {a.x, a.y, a.z, a.w, 0.f, 0.f, 0.f, 0.f};
+            if (Q > 4)
+            {
+                float4 b = line[32 + lane];
+                t[4] = b.x, t[5] = b.y, t[6] = b.z, t[7] = b.w;
+            }
+#pragma unroll
+            for (int i = 0; i < Q; ++i) rs.em[l][i] = t[i];
+        }
+    }
 
     float vm[Q], vi[Q];
 #pragma unroll
@@ -147,11 +209,31 @@ __device__ __forceinline__ void score_row(float (&tm)[5][Q], float (&ti)[5][Q], 
      * the shared emissions (their registers were just consumed) and the window two rows ahead */
     uint32_t code[5];
     codes_of(rs.w1, code);
-    load_emis_part<Q, 3, 5>(rs.em, emis_lane, code);
+    if constexpr (TMA)
+    {
+        /* the stage is consumed (vm above used its values): refill it with the lines of row j+2 */
+        __syncwarp();
+        if (lane == 0)
+        {
+            const uint32_t st = tc.g & 1u;
+            const float *base = emis_lane; /* lane 0: start of the profile's table */
+            mbar_expect_tx(tc.bar + st, 2 * LINE * 4);
+            tma_load_1d(tc.ring + (st * 2 + 0) * LINE, base + (size_t)(84u + (rs.w2 & 255u)) * LINE, LINE * 4, tc.bar + st);
+            tma_load_1d(tc.ring + (st * 2 + 1) * LINE, base + (size_t)(340u + (rs.w2 & 1023u)) * LINE, LINE * 4, tc.bar + st);
+        }
+        tc.g++;
+        rs.w1 = rs.w2;
+        rs.w2 = rs.w3;
+        rs.w3 = __ldg(w_next2);
+    }
+    else
+    {
+        load_emis_part<Q, 3, 5>(rs.em, emis_lane, code);
+        rs.w1 = rs.w2;
+        rs.w2 = __ldg(w_next2);
+    }
     load_row_insert(rec_next, rs.eI);
     if (lane < 3) load_row_special(rec_next, rs.eN);
-    rs.w1 = rs.w2;
-    rs.w2 = __ldg(w_next2);
 
     /* E[j]: every M_k -> E is 0 and D_k <= max V_M because MD, DD <= 0 (checked at commit) */
     float eloc = vm[0];
@@ -233,10 +315,10 @@ __device__ __forceinline__ void score_row(float (&tm)[5][Q], float (&ti)[5][Q], 
 }
 
 /* recs / wc = record and window of row 0 of this sequence (L+1 of each) */
-template <int Q>
+template <int Q, bool TMA>
 __device__ __forceinline__ float score_pair(const NodeParams<Q> &p, const float *__restrict__ emis_lane,
                                             const RowRec *__restrict__ recs, const uint16_t *__restrict__ wc,
-                                            uint32_t L, const float *__restrict__ sp, int lane)
+                                            uint32_t L, const float *__restrict__ sp, int lane, TmaCtx &tc)
 {
     const float NN = sp[0], CC = sp[1], JJ = sp[2], NB = sp[3], CT = sp[4], JB = sp[5];
     const float ET = sp[9], ECC = sp[10], EB = sp[11], EJJ = sp[12];
@@ -269,29 +351,62 @@ __device__ __forceinline__ float score_pair(const NodeParams<Q> &p, const float 
     if (lane < 3) load_row_special(recs + 1, rs.eN);
     rs.w1 = __ldg(wc + min(2u, L));
     rs.w2 = __ldg(wc + min(3u, L));
+    rs.w3 = 0;
+    if constexpr (TMA)
+    {
+        /* the streamed lines of rows 1 and 2 go into the two stages; from here on every row refills the
+         * stage it has just consumed with the lines of the row two ahead */
+        constexpr int LINE = 32 * (Q <= 4 ? 4 : 8);
+        const uint32_t wa = __ldg(wc + 1), wb = rs.w1;
+        __syncwarp();
+        if (lane == 0)
+        {
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+            {
+                const uint32_t st = (tc.g + k) & 1u, w = k ? wb : wa;
+                mbar_expect_tx(tc.bar + st, 2 * LINE * 4);
+                tma_load_1d(tc.ring + (st * 2 + 0) * LINE, emis_lane + (size_t)(84u + (w & 255u)) * LINE, LINE * 4, tc.bar + st);
+                tma_load_1d(tc.ring + (st * 2 + 1) * LINE, emis_lane + (size_t)(340u + (w & 1023u)) * LINE, LINE * 4, tc.bar + st);
+            }
+        }
+        /* row j refills with row j+2: its window must be in w2 when row j runs */
+        rs.w1 = __ldg(wc + min(2u, L)); /* window of row 2 (addresses of row 2's short lines) */
+        rs.w2 = __ldg(wc + min(3u, L)); /* window of row 3: refilled by row 1 */
+        rs.w3 = __ldg(wc + min(4u, L));
+    }
 
     float E = NEG_INF, vx = NEG_INF;
     uint32_t j = 1;
-#define ROW_ARGS(jj) recs + min((uint32_t)(jj) + 1u, L), wc + min((uint32_t)(jj) + 3u, L)
+#define ROW_ARGS(jj) recs + min((uint32_t)(jj) + 1u, L), wc + min((uint32_t)(jj) + (TMA ? 4u : 3u), L)
     for (; j + 4 <= L; j += 5)
     {
-        score_row<Q, 0>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j), lane, NB, JB, EB, cE, cX, E, vx);
-        score_row<Q, 1>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 1), lane, NB, JB, EB, cE, cX, E, vx);
-        score_row<Q, 2>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 2), lane, NB, JB, EB, cE, cX, E, vx);
-        score_row<Q, 3>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 3), lane, NB, JB, EB, cE, cX, E, vx);
-        score_row<Q, 4>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 4), lane, NB, JB, EB, cE, cX, E, vx);
+        score_row<Q, 0, TMA>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j), lane, NB, JB, EB, cE, cX, E, vx, tc);
+        score_row<Q, 1, TMA>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 1), lane, NB, JB, EB, cE, cX, E, vx, tc);
+        score_row<Q, 2, TMA>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 2), lane, NB, JB, EB, cE, cX, E, vx, tc);
+        score_row<Q, 3, TMA>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 3), lane, NB, JB, EB, cE, cX, E, vx, tc);
+        score_row<Q, 4, TMA>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 4), lane, NB, JB, EB, cE, cX, E, vx, tc);
     }
-    if (j <= L) score_row<Q, 0>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j), lane, NB, JB, EB, cE, cX, E, vx);
-    if (j + 1 <= L) score_row<Q, 1>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 1), lane, NB, JB, EB, cE, cX, E, vx);
-    if (j + 2 <= L) score_row<Q, 2>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 2), lane, NB, JB, EB, cE, cX, E, vx);
-    if (j + 3 <= L) score_row<Q, 3>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 3), lane, NB, JB, EB, cE, cX, E, vx);
+    if (j <= L) score_row<Q, 0, TMA>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j), lane, NB, JB, EB, cE, cX, E, vx, tc);
+    if (j + 1 <= L) score_row<Q, 1, TMA>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 1), lane, NB, JB, EB, cE, cX, E, vx, tc);
+    if (j + 2 <= L) score_row<Q, 2, TMA>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 2), lane, NB, JB, EB, cE, cX, E, vx, tc);
+    if (j + 3 <= L) score_row<Q, 3, TMA>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 3), lane, NB, JB, EB, cE, cX, E, vx, tc);
 #undef ROW_ARGS
+    if constexpr (TMA)
+    {
+        /* rows L+1 and L+2 were requested too (clamped windows): drain them so the stages are free again */
+        mbar_wait(tc.bar + (tc.g & 1u), (tc.g >> 1) & 1u);
+        tc.g++;
+        mbar_wait(tc.bar + (tc.g & 1u), (tc.g >> 1) & 1u);
+        tc.g++;
+        __syncwarp();
+    }
     /* T[L] = max(E[L] + (EC+CT), V_C[L] + CT); V_C lives in lane 2 */
     float vC = __shfl_sync(FULL, vx, 2);
     return fmaxf(E + ET, vC + CT);
 }
 
-template <int Q>
+template <int Q, bool TMA>
 __global__ void __launch_bounds__(score_warps(Q) * 32, 1)
 k_score(const float *__restrict__ emis, const float *__restrict__ trans, const ProfMeta *__restrict__ metas,
         const uint32_t *__restrict__ class_profs, uint32_t n_class_profs, const SeqMeta *__restrict__ seqs,
@@ -300,6 +415,23 @@ k_score(const float *__restrict__ emis, const float *__restrict__ trans, const P
         unsigned long long *__restrict__ counter, uint32_t seq_tile)
 {
     const int lane = threadIdx.x & 31;
+    TmaCtx tc = {nullptr, nullptr, 0};
+    if constexpr (TMA)
+    {
+        extern __shared__ __align__(128) unsigned char smem_raw[];
+        constexpr int LINE = 32 * (Q <= 4 ? 4 : 8);
+        const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        tc.ring = reinterpret_cast<float *>(smem_raw) + (size_t)warp * 4 * LINE;
+        tc.bar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)nwarps * 4 * LINE * sizeof(float)) + warp * 2;
+        if (lane == 0)
+        {
+            mbar_init(tc.bar, 1);
+            mbar_init(tc.bar + 1, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncwarp();
+    }
     /*
      * Work items in tile order: (sequence tile, profile, chunk of kSeqChunk sequences).  All warps
      * of the GPU walk the items in order, so at any time they share a handful of profiles (their
@@ -332,8 +464,8 @@ k_score(const float *__restrict__ emis, const float *__restrict__ trans, const P
         for (uint32_t s = ci * kSeqChunk; s < s_end; ++s)
         {
             SeqMeta sm = seqs[s];
-            float T = score_pair<Q>(p, emis_lane, rows_t + sm.rec_off, wcodes + sm.rec_off, sm.len,
-                                    spec + (size_t)s * 16, lane);
+            float T = score_pair<Q, TMA>(p, emis_lane, rows_t + sm.rec_off, wcodes + sm.rec_off, sm.len,
+                                         spec + (size_t)s * 16, lane, tc);
             if (lane == 0) alt_out[(size_t)s * nprof + prof] = T;
         }
     }
@@ -638,9 +770,21 @@ void launch_score(int nblocks, cudaStream_t st, const float *emis, const float *
                   uint32_t nprof,
                   unsigned long long *counter, uint32_t seq_tile)
 {
+    static const bool use_tma = getenv("DCPGPU_TMA") && atoi(getenv("DCPGPU_TMA")) != 0;
+    if (use_tma)
+    {
+        /* experiment: 4/5-nt emission lines through cp.async.bulk + mbarrier into a per-warp shared ring */
+        const int warps = score_warps(Q), LINE = 32 * (Q <= 4 ? 4 : 8);
+        const size_t smem = (size_t)warps * 4 * LINE * sizeof(float) + (size_t)warps * 2 * sizeof(uint64_t);
+        cudaFuncSetAttribute(k_score<Q, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_score<Q, true><<<nblocks, warps * 32, smem, st>>>(emis, trans, metas, class_profs, n_class, seqs, nseq,
+                                                            total_rows, rows, wcodes, spec, alt, nprof, counter,
+                                                            seq_tile);
+        return;
+    }
     /* no shared memory: give the whole unified array to L1 (emission lines, row records) */
-    cudaFuncSetAttribute(k_score<Q>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
-    k_score<Q><<<nblocks, score_warps(Q) * 32, 0, st>>>(emis, trans, metas, class_profs, n_class, seqs, nseq,
+    cudaFuncSetAttribute(k_score<Q, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    k_score<Q, false><<<nblocks, score_warps(Q) * 32, 0, st>>>(emis, trans, metas, class_profs, n_class, seqs, nseq,
                                                         total_rows, rows, wcodes, spec, alt, nprof, counter, seq_tile);
 }
 
