@@ -263,3 +263,32 @@ def test_dcp_scan_driver_matches_reference_product_rows(pkg, o32, tmp_path):
     bad.write_text(">x\nACGTNNACGT\n")
     out = subprocess.run([exe, hmm, str(bad)], capture_output=True, text=True)
     assert out.returncode == 1 and "ACGT" in out.stderr
+
+
+def test_fp32_path_within_reference_tolerance_of_double_oracle(pkg, o32, o64):
+    """The reference's CI runs float and double builds against the same goldens with rel. tolerance 5e-5 for float
+    (test/hope_support.h:26).  The fp32 GPU scores must sit within that tolerance of the DOUBLE oracle fed the
+    same fp32-rounded tables (accumulation error only), at config-2 pair shapes (M = 200, L ~ 1000)."""
+    rng = np.random.default_rng(21)
+    db = pkg.Db(0)
+    profs, models = [], []
+    for i, M in enumerate((200, 200, 120)):
+        nl, ma, tr = plan7_profile_inputs(rng, M)
+        p = pkg.ProteinProfile.from_model(nl, ma, tr, pkg.protein_cfg(pkg.ENTRY_DIST_OCCUPANCY, 0.01), "T%d" % i)
+        db.add(p)
+        profs.append(p)
+        models.append(ma)
+    db.commit()
+    seqs = [sample_read(rng, models[i % 3], 1000, 0.02, 0.01) for i in range(6)] + [random_seq(rng, 1000)]
+    res = db.scan(seqs, lrt_threshold=10.0)
+    twins64 = [oracle_twin(o64, p, 0.01) for p in profs]
+    worst = 0.0
+    for s in range(len(seqs)):
+        for k in range(3):
+            rc, nl, al = twins64[k].scores_fast(seqs[s])
+            assert rc == 0
+            worst = max(worst, abs(res.alt_loglik[s, k] - al) / abs(al), abs(res.null_loglik[s, k] - nl) / abs(nl))
+            lrt64 = -2 * (nl - al)
+            if abs(lrt64 - 10.0) > 1e-2:  # away from the threshold the hit decision agrees with double arithmetic
+                assert bool(res.hit[s, k]) == (lrt64 >= 10.0)
+    assert worst < 5e-5, worst
