@@ -847,7 +847,17 @@ extern "C" enum rc dcpgpu_db_new(struct dcpgpu_db **out, int device)
     return RC_OK;
 }
 
+static enum rc db_take(struct dcpgpu_db *db, struct protein_profile *prof, bool owned);
+
 extern "C" enum rc dcpgpu_db_add(struct dcpgpu_db *db, struct protein_profile const *prof)
+{
+    return db_take(db, const_cast<protein_profile *>(prof), false);
+}
+
+/* same as dcpgpu_db_add, but the database takes ownership of `prof` (no copy); used by the press */
+enum rc dcp_db_adopt(struct dcpgpu_db *db, struct protein_profile *prof) { return db_take(db, prof, true); }
+
+static enum rc db_take(struct dcpgpu_db *db, struct protein_profile *prof, bool owned)
 {
     if (db->committed) return dcp_error(RC_EFAIL, "database already committed");
     if (prof->core_size == 0) return dcp_error(RC_EINVAL, "profile has not been absorbed");
@@ -859,7 +869,7 @@ extern "C" enum rc dcpgpu_db_add(struct dcpgpu_db *db, struct protein_profile co
     for (unsigned i = 0; i <= prof->core_size; ++i)
         if (prof->trans[i].MD > 0.0f || prof->trans[i].DD > 0.0f)
             return dcp_error(RC_EINVAL, "MD/DD transition scores must be <= 0");
-    protein_profile *copy = profile_clone(prof);
+    protein_profile *copy = owned ? prof : profile_clone(prof);
     if (!copy) return dcp_error(RC_ENOMEM, "clone profile");
     db->epsilon = prof->cfg.epsilon;
     uint32_t id = UINT32_MAX;
@@ -973,6 +983,13 @@ extern "C" enum rc dcpgpu_db_commit(struct dcpgpu_db *db)
             CU_TRY(cudaMemcpy(db->d_class[q], db->class_list[q].data(), db->class_list[q].size() * sizeof(uint32_t),
                               cudaMemcpyHostToDevice));
         }
+    /* the host copies stay for decode and product rows; those need the nucleotide distributions, transitions
+     * and names, not the 5.4 KB per node of match emissions that now live in HBM */
+    for (auto *p : db->profs)
+    {
+        free(p->match_emission);
+        p->match_emission = nullptr;
+    }
     db->committed = true;
     return RC_OK;
 }

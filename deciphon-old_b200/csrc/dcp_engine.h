@@ -149,5 +149,6 @@ struct DevBuf
 enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const RowRec *d_rows,
                        const uint16_t *d_wcodes, const float *d_spec, uint64_t *launches);
 const protein_profile *dcp_db_profile(struct dcpgpu_db const *db, unsigned i);
+enum rc dcp_db_adopt(struct dcpgpu_db *db, struct protein_profile *prof); /* takes ownership, no copy */
 
 #endif
