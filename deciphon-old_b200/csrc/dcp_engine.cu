@@ -726,6 +726,28 @@ k_score_mw(const float *__restrict__ emis, const float *__restrict__ trans, cons
     }
 }
 
+/*
+ * Match emission tables, host layout [node][code] -> device layout [code][warp][half][lane][4]
+ * (node k-1 = warp * 32 Q + lane * Q + sub sits in half sub/4, float sub%4 of its lane; pads are -inf).
+ */
+__global__ void k_layout(const float *__restrict__ raw, float *__restrict__ out, uint32_t M, uint32_t Q, uint32_t QP,
+                         uint32_t W)
+{
+    const uint32_t ROW = 32 * QP * W;
+    const size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= (size_t)kTab * ROW) return;
+    const uint32_t code = (uint32_t)(x / ROW), pos = (uint32_t)(x % ROW);
+    const uint32_t warp = pos / (32 * QP), r = pos % (32 * QP);
+    const uint32_t half = r / 128, lane = (r % 128) / 4, sub = half * 4 + (r % 4);
+    float v = NEG_INF;
+    if (sub < Q)
+    {
+        const uint32_t k = warp * 32 * Q + lane * Q + sub;
+        if (k < M) v = raw[(size_t)k * kTab + code];
+    }
+    out[x] = v;
+}
+
 /* xmath_lrt + threshold (scan_thread.c:121-123): hit iff finite and not (lrt < threshold) */
 __global__ void k_lrt(const float *__restrict__ alt, const float *__restrict__ null_by_tab,
                       const ProfMeta *__restrict__ metas, uint32_t nseq, uint32_t nprof, uint32_t n_null,
@@ -928,29 +950,35 @@ extern "C" enum rc dcpgpu_db_commit(struct dcpgpu_db *db)
     db->device_bytes = (emis_floats + trans_floats + (db->null_tabs.size() + 1) * kTab) * sizeof(float) +
                        nprof * sizeof(ProfMeta);
 
-    /* transpose per profile into pinned staging, upload in large pieces */
-    const size_t stage_floats = (size_t)kTab * 32 * 8 * kMaxGroupWarps;
-    float *stage = nullptr;
-    CU_TRY(cudaMallocHost(&stage, stage_floats * sizeof(float)));
-    std::vector<float> tr;
+    /* Upload the tables as the host holds them ([node][code], contiguous) through two pinned buffers and let
+     * k_layout transpose them into the kernels' [code][warp][half][lane][4] layout on the device. */
+    const size_t raw_max = (size_t)DCP_PROTEIN_MODEL_CORE_SIZE_MAX * kTab;
+    float *stage[2] = {nullptr, nullptr};
+    float *d_raw[2] = {nullptr, nullptr};
+    cudaEvent_t freed[2];
+    for (int b = 0; b < 2; ++b)
+    {
+        CU_TRY(cudaMallocHost(&stage[b], raw_max * sizeof(float)));
+        CU_TRY(cudaMalloc(&d_raw[b], raw_max * sizeof(float)));
+        CU_TRY(cudaEventCreateWithFlags(&freed[b], cudaEventDisableTiming));
+    }
+    std::vector<float> tr_all(trans_floats, NEG_INF);
     for (size_t i = 0; i < nprof; ++i)
     {
         const ProfMeta &m = db->metas[i];
         const protein_profile *p = db->profs[i];
-        const uint32_t ROW = 32 * m.QP * m.W, PER_WARP = 32 * m.Q;
-        for (size_t x = 0; x < (size_t)kTab * ROW; ++x) stage[x] = NEG_INF;
-        for (uint32_t k = 0; k < m.M; ++k)
-        {
-            uint32_t warp = k / PER_WARP, lane = (k % PER_WARP) / m.Q, sub = k % m.Q;
-            const float *src = p->match_emission + (size_t)k * kTab;
-            /* [code][warp][half][lane][4]: node k sits in half sub/4 at float sub%4 of its lane */
-            const size_t at = (size_t)warp * 32 * m.QP + (size_t)(sub / 4) * 128 + (size_t)lane * 4 + (sub % 4);
-            for (int c = 0; c < kTab; ++c) stage[(size_t)c * ROW + at] = src[c];
-        }
-        CU_TRY(cudaMemcpyAsync(db->d_emis + m.emis_off, stage, (size_t)kTab * ROW * sizeof(float),
-                               cudaMemcpyHostToDevice, db->stream));
+        const int b = (int)(i & 1);
+        if (i >= 2) CU_TRY(cudaEventSynchronize(freed[b])); /* the copy out of stage[b] has completed */
+        const size_t raw = (size_t)m.M * kTab;
+        memcpy(stage[b], p->match_emission, raw * sizeof(float));
+        CU_TRY(cudaMemcpyAsync(d_raw[b], stage[b], raw * sizeof(float), cudaMemcpyHostToDevice, db->stream));
+        CU_TRY(cudaEventRecord(freed[b], db->stream));
+        const uint32_t ROW = 32 * m.QP * m.W;
+        const size_t out = (size_t)kTab * ROW;
+        k_layout<<<(unsigned)((out + 255) / 256), 256, 0, db->stream>>>(d_raw[b], db->d_emis + m.emis_off, m.M, m.Q,
+                                                                         m.QP, m.W);
         const uint32_t NP = 32 * m.Q * m.W;
-        tr.assign((size_t)8 * NP, NEG_INF);
+        float *tr = tr_all.data() + m.trans_off;
         for (uint32_t k = 1; k <= m.M; ++k) /* node k, slot k-1 */
         {
             uint32_t n = k - 1;
@@ -967,10 +995,16 @@ extern "C" enum rc dcpgpu_db_commit(struct dcpgpu_db *db)
             }
             tr[7 * NP + n] = p->entry[k - 1];
         }
-        CU_TRY(cudaStreamSynchronize(db->stream)); /* stage is reused */
-        CU_TRY(cudaMemcpy(db->d_trans + m.trans_off, tr.data(), tr.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
-    cudaFreeHost(stage);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(db->stream));
+    CU_TRY(cudaMemcpy(db->d_trans, tr_all.data(), trans_floats * sizeof(float), cudaMemcpyHostToDevice));
+    for (int b = 0; b < 2; ++b)
+    {
+        cudaFreeHost(stage[b]);
+        cudaFree(d_raw[b]);
+        cudaEventDestroy(freed[b]);
+    }
     CU_TRY(cudaMemcpy(db->d_metas, db->metas.data(), nprof * sizeof(ProfMeta), cudaMemcpyHostToDevice));
     for (size_t t = 0; t < db->null_tabs.size(); ++t)
         CU_TRY(cudaMemcpy(db->d_null_tabs + t * kTab, db->null_tabs[t].data(), kTab * sizeof(float),
