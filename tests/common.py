@@ -47,22 +47,17 @@ def plan7_profile_inputs(rng, M, sharp=4.0):
     null_lp = np.log(bg / bg.sum())
     g = rng.gamma(1.0 / sharp, 1.0, size=(M, 20)) * bg + 1e-6
     match_lp = np.log(g / g.sum(1, keepdims=True))
-    tr = np.zeros((M + 1, 7))
-    for i in range(M + 1):
-        mm = rng.uniform(0.85, 0.97)
-        mi = (1 - mm) * rng.uniform(0.3, 0.7)
-        md = 1 - mm - mi
-        im = rng.uniform(0.4, 0.8)
-        dm = rng.uniform(0.3, 0.8)
-        t = np.log(np.array([mm, mi, md, im, 1 - im, dm, 1 - dm]))
-        if i == 0:
-            t[6] = -np.inf
-            t[5] = 0.0
-        if i == M:
-            t = np.log(np.array([mm + md, mi, 1e-300, im, 1 - im, 1.0, 1e-300]))
-            t[2] = -np.inf
-            t[6] = -np.inf
-        tr[i] = t
+    n = M + 1
+    mm = rng.uniform(0.85, 0.97, n)
+    mi = (1 - mm) * rng.uniform(0.3, 0.7, n)
+    md = 1 - mm - mi
+    im = rng.uniform(0.4, 0.8, n)
+    dm = rng.uniform(0.3, 0.8, n)
+    with np.errstate(divide="ignore"):
+        tr = np.log(np.stack([mm, mi, md, im, 1 - im, dm, 1 - dm], axis=1))
+        tr[0, 6] = -np.inf  # node 0 has no delete state
+        tr[0, 5] = 0.0
+        tr[M] = np.log(np.array([mm[M] + md[M], mi[M], 0.0, im[M], 1 - im[M], 1.0, 0.0]))  # last node: no M->D, D->D
     return null_lp, match_lp, tr
 
 
