@@ -28,3 +28,18 @@ def merge_hits(per_rank):
     merged = [h for hits in per_rank for h in hits]
     merged.sort(key=lambda h: (h[0], h[1]))
     return merged
+
+
+def plan(pkg, core_sizes, nseqs, world):
+    """Choose the axis to shard over: profiles by cumulative core length when that balances
+    (imbalance <= 10 %), otherwise sequences (every rank holds all profiles and scans a contiguous slice).
+    Returns ("profiles", shard_of_profile) or ("sequences", [(lo, hi)] per rank)."""
+    sizes = np.asarray(core_sizes, np.int64)
+    if world <= 1:
+        return "profiles", np.zeros(len(sizes), np.uint32)
+    shard = pkg.shard_profiles(sizes, world)
+    loads = np.bincount(shard, weights=sizes, minlength=world)
+    if len(sizes) >= world and loads.max() <= 1.10 * loads.mean():
+        return "profiles", shard
+    per = -(-nseqs // world)
+    return "sequences", [(min(r * per, nseqs), min((r + 1) * per, nseqs)) for r in range(world)]

@@ -48,6 +48,21 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def test_axis_choice(pkg):
+    import importlib
+    sharding = importlib.import_module("deciphon_old_b200.sharding")
+    rng = np.random.default_rng(0)
+    many = np.clip(np.exp(rng.normal(np.log(130), 0.7, 2000)), 50, 2000).astype(int)
+    axis, shard = sharding.plan(pkg, many, 100000, 8)
+    assert axis == "profiles" and len(shard) == 2000 and shard.max() == 7
+    # config 4: 50 long profiles of unequal length over 8 GPUs do not balance -> shard the contigs instead
+    few = [3000] * 3 + [2000] * 2
+    axis, parts = sharding.plan(pkg, few, 10001, 8)
+    assert axis == "sequences" and parts[0] == (0, 1251) and parts[-1][1] == 10001
+    assert sum(hi - lo for lo, hi in parts) == 10001
+    assert sharding.plan(pkg, few, 10, 1)[0] == "profiles"
+
+
 def test_two_rank_shard_and_merge():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
