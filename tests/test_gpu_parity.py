@@ -292,3 +292,27 @@ def test_fp32_path_within_reference_tolerance_of_double_oracle(pkg, o32, o64):
             if abs(lrt64 - 10.0) > 1e-2:  # away from the threshold the hit decision agrees with double arithmetic
                 assert bool(res.hit[s, k]) == (lrt64 >= 10.0)
     assert worst < 5e-5, worst
+
+
+def test_zero_probability_transitions_and_emissions(pkg, o32):
+    """'*' scores (probability 0) anywhere in the model: -inf arithmetic must stay NaN-free and bit-exact."""
+    rng = np.random.default_rng(8)
+    db = pkg.Db(0)
+    twins = []
+    for i, M in enumerate((40, 200, 300)):
+        nl, ma, tr = plan7_profile_inputs(rng, M)
+        tr = tr.copy()
+        ma = ma.copy()
+        for col in (1, 2, 3, 4, 5, 6):  # MI MD IM II DM DD
+            idx = rng.choice(np.arange(1, M), size=max(1, M // 10), replace=False)
+            tr[idx, col] = -np.inf
+        ma[rng.integers(0, M, M // 5), rng.integers(0, 20, M // 5)] = -np.inf  # impossible residues
+        p = pkg.ProteinProfile.from_model(nl, ma, tr, pkg.protein_cfg(pkg.ENTRY_DIST_OCCUPANCY, 0.01), "Z%d" % i)
+        assert np.isfinite(p.entry).any()
+        db.add(p)
+        twins.append(oracle_twin(o32, p, 0.01))
+    db.commit()
+    seqs = [random_seq(rng, n) for n in (7, 150, 401)] + ["ACG" * 60]
+    for mh in (True, False):
+        res, ref = check_scan(pkg, o32, db, twins, seqs, multi_hits=mh, thr=-1e30, rows=False)
+        assert not np.isnan(res.alt_loglik).any()
