@@ -1191,7 +1191,16 @@ extern "C" enum rc dcpgpu_scan_resident(struct dcpgpu_db *db, struct dcpgpu_seqs
     CU_TRY(cudaMallocAsync(&res->d_null, (size_t)nseq * n_null * sizeof(float), st));
     CU_TRY(cudaMallocAsync(&res->d_hit, npairs, st));
 
-    cudaEvent_t ev[5];
+    struct Events
+    {
+        cudaEvent_t e[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+        ~Events()
+        {
+            for (auto x : e)
+                if (x) cudaEventDestroy(x);
+        }
+    } events;
+    cudaEvent_t(&ev)[5] = events.e;
     for (auto &e : ev) CU_TRY(cudaEventCreate(&e));
     uint64_t launches = 0;
 
@@ -1335,7 +1344,6 @@ extern "C" enum rc dcpgpu_scan_resident(struct dcpgpu_db *db, struct dcpgpu_seqs
     t.alt_cells = cells;
     t.h2d_bytes = spec.size() * sizeof(float);
     t.d2h_bytes = d2h + res->steps.size() * sizeof(dcp_step) + res->hits.size() * 8;
-    for (auto &e : ev) cudaEventDestroy(e);
     guard.r = nullptr;
     *out = res;
     return RC_OK;
