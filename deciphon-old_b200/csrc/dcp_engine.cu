@@ -19,6 +19,9 @@
  * Emission tables live in HBM transposed: [profile][code 0..1363][lane][QP] so that the 32 lanes
  * of a warp read one contiguous 32*QP*4-byte line per (row, length) with LDG.128.
  */
+#ifndef DCP_NOTAIL_MAXQ
+#define DCP_NOTAIL_MAXQ 6
+#endif
 #include "dcp_kernels.cuh"
 
 #include <algorithm>
@@ -379,6 +382,31 @@ __device__ __forceinline__ float score_pair(const NodeParams<Q> &p, const float 
     float E = NEG_INF, vx = NEG_INF;
     uint32_t j = 1;
 #define ROW_ARGS(jj) recs + min((uint32_t)(jj) + 1u, L), wc + min((uint32_t)(jj) + (TMA ? 4u : 3u), L)
+    if constexpr (Q <= DCP_NOTAIL_MAXQ)
+    {
+    /* always whole groups of five rows (one copy of the row code in the instruction cache): rows past L
+     * recompute on clamped inputs and are ignored; E and V_X of row L are latched when they pass */
+    float E_L = NEG_INF, vx_L = NEG_INF;
+#define LATCH(jj)                                                                                              \
+    if ((jj) == L) E_L = E, vx_L = vx;
+    for (; j <= L; j += 5)
+    {
+        score_row<Q, 0, TMA>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j), lane, NB, JB, EB, cE, cX, E, vx, tc);
+        LATCH(j)
+        score_row<Q, 1, TMA>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 1), lane, NB, JB, EB, cE, cX, E, vx, tc);
+        LATCH(j + 1)
+        score_row<Q, 2, TMA>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 2), lane, NB, JB, EB, cE, cX, E, vx, tc);
+        LATCH(j + 2)
+        score_row<Q, 3, TMA>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 3), lane, NB, JB, EB, cE, cX, E, vx, tc);
+        LATCH(j + 3)
+        score_row<Q, 4, TMA>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 4), lane, NB, JB, EB, cE, cX, E, vx, tc);
+        LATCH(j + 4)
+    }
+#undef LATCH
+    E = E_L, vx = vx_L;
+    }
+    else
+    {
     for (; j + 4 <= L; j += 5)
     {
         score_row<Q, 0, TMA>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j), lane, NB, JB, EB, cE, cX, E, vx, tc);
@@ -391,6 +419,7 @@ __device__ __forceinline__ float score_pair(const NodeParams<Q> &p, const float 
     if (j + 1 <= L) score_row<Q, 1, TMA>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 1), lane, NB, JB, EB, cE, cX, E, vx, tc);
     if (j + 2 <= L) score_row<Q, 2, TMA>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 2), lane, NB, JB, EB, cE, cX, E, vx, tc);
     if (j + 3 <= L) score_row<Q, 3, TMA>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 3), lane, NB, JB, EB, cE, cX, E, vx, tc);
+    }
 #undef ROW_ARGS
     if constexpr (TMA)
     {
