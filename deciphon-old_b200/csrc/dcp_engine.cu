@@ -1245,11 +1245,16 @@ extern "C" enum rc dcpgpu_scan_resident(struct dcpgpu_db *db, struct dcpgpu_seqs
     CU_TRY(cudaEventRecord(ev[1], st));
 
     const int nblocks = db->sm_count; /* persistent: one 8-warp block per SM (255 regs/thread) */
-    /* sequences per L2 tile: their row records (64 B per row and null table) should fit ~64 MB */
+    /* sequences per L2 tile: their row records (64 B per row and null table) stay L2-resident while every
+     * profile passes.  32 MB measured best (DRAM bytes per config-2 launch: 64 MB 145 GB, 48 MB 78 GB,
+     * 32 MB 34 GB, 16 MB 74 GB; profiles/r01_tile_sweep_dram.csv): data read by all SMs is held in both L2
+     * partitions, so about half of the 126 MB is usable for it. */
     uint32_t seq_tile;
     {
         const double rec_bytes_per_seq = (double)total_recs / nseq * sizeof(RowRec) * n_null;
-        double t = (64.0 * 1024 * 1024) / rec_bytes_per_seq;
+        double tile_mb = 32.0;
+        if (const char *e = getenv("DCPGPU_TILE_MB")) tile_mb = std::max(0.25, atof(e)); /* experiment knob */
+        double t = (tile_mb * 1024 * 1024) / rec_bytes_per_seq;
         seq_tile = (uint32_t)std::min<double>(std::max<double>(t, kSeqChunk), 1 << 20);
         seq_tile = std::max<uint32_t>(kSeqChunk, seq_tile / kSeqChunk * kSeqChunk);
     }
