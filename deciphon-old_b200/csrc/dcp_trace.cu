@@ -43,6 +43,31 @@ __device__ __forceinline__ void first_max5(const float (&s)[5], float t, int bas
     }
 }
 
+
+/*
+ * The trace kernels run one copy of the row code and rotate the five-row rings with register moves (95 moves against
+ * ~1700 instructions of a row).  The score kernels' five-fold unrolling (static ring slots, no moves) made the trace
+ * kernels 9 x 1700 instructions long, and the instruction cache misses were their top stall (ncu: no_instruction
+ * 3.0 of 7.3 cycles per issue, profiles/r01_k_trace_mw_long_ncu.txt).
+ */
+template <int Q>
+__device__ __forceinline__ void ring_rotate(float (&tm)[5][Q], float (&ti)[5][Q], float (&tn)[5], float (&tj)[5],
+                                            float (&tc)[5])
+{
+#pragma unroll
+    for (int i = 0; i < Q; ++i)
+    {
+        float a = tm[0][i], b = ti[0][i];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) tm[s][i] = tm[s + 1][i], ti[s][i] = ti[s + 1][i];
+        tm[4][i] = a, ti[4][i] = b;
+    }
+    float a = tn[0], b = tj[0], c = tc[0];
+#pragma unroll
+    for (int s = 0; s < 4; ++s) tn[s] = tn[s + 1], tj[s] = tj[s + 1], tc[s] = tc[s + 1];
+    tn[4] = a, tj[4] = b, tc[4] = c;
+}
+
 template <int Q, int R>
 __device__ __forceinline__ void trace_row(float (&tm)[5][Q], float (&ti)[5][Q], float (&tn)[5], float (&tj)[5],
                                           float (&tc)[5], const NodeParams<Q> &p,
@@ -252,18 +277,12 @@ __global__ void __launch_bounds__(128) k_trace(const float *__restrict__ emis, c
     float T = NEG_INF;
     uint32_t j = 1;
     constexpr uint32_t CS = Q * 32; /* cell backpointers per row */
-    for (; j + 4 <= L; j += 5)
+#pragma unroll 1
+    for (; j <= L; ++j)
     {
-        trace_row<Q, 0>(tm, ti, tn, tjr, tc, p, emis_lane, r + (j - 1), wc[(j - 1) + 1], lane, sp, cb + (size_t)j * CS, rb + j, T);
-        trace_row<Q, 1>(tm, ti, tn, tjr, tc, p, emis_lane, r + j, wc[j + 1], lane, sp, cb + (size_t)(j + 1) * CS, rb + j + 1, T);
-        trace_row<Q, 2>(tm, ti, tn, tjr, tc, p, emis_lane, r + (j + 1), wc[(j + 1) + 1], lane, sp, cb + (size_t)(j + 2) * CS, rb + j + 2, T);
-        trace_row<Q, 3>(tm, ti, tn, tjr, tc, p, emis_lane, r + (j + 2), wc[(j + 2) + 1], lane, sp, cb + (size_t)(j + 3) * CS, rb + j + 3, T);
-        trace_row<Q, 4>(tm, ti, tn, tjr, tc, p, emis_lane, r + (j + 3), wc[(j + 3) + 1], lane, sp, cb + (size_t)(j + 4) * CS, rb + j + 4, T);
+        trace_row<Q, 0>(tm, ti, tn, tjr, tc, p, emis_lane, r + (j - 1), wc[j], lane, sp, cb + (size_t)j * CS, rb + j, T);
+        ring_rotate<Q>(tm, ti, tn, tjr, tc);
     }
-    if (j <= L) trace_row<Q, 0>(tm, ti, tn, tjr, tc, p, emis_lane, r + (j - 1), wc[(j - 1) + 1], lane, sp, cb + (size_t)j * CS, rb + j, T);
-    if (j + 1 <= L) trace_row<Q, 1>(tm, ti, tn, tjr, tc, p, emis_lane, r + j, wc[j + 1], lane, sp, cb + (size_t)(j + 1) * CS, rb + j + 1, T);
-    if (j + 2 <= L) trace_row<Q, 2>(tm, ti, tn, tjr, tc, p, emis_lane, r + (j + 1), wc[(j + 1) + 1], lane, sp, cb + (size_t)(j + 2) * CS, rb + j + 2, T);
-    if (j + 3 <= L) trace_row<Q, 3>(tm, ti, tn, tjr, tc, p, emis_lane, r + (j + 2), wc[(j + 2) + 1], lane, sp, cb + (size_t)(j + 3) * CS, rb + j + 3, T);
     if (lane == 0) alt_out[job] = T;
 }
 
@@ -321,30 +340,16 @@ __device__ __forceinline__ void trace_row_mw(float (&tm)[5][8], float (&ti)[5][8
         sJ[l] = tj[S[l]] + in.eN[l];
         sC[l] = tc[S[l]] + in.eN[l];
     }
-    if (lane == 31)
-#pragma unroll
-        for (int l = 0; l < 5; ++l)
-        {
-            GRP_PUT(grp, pM[par][warp][l], sM[Q - 1][l]);
-            GRP_PUT(grp, pI[par][warp][l], sI[Q - 1][l]);
-        }
     float pM0[5], pI0[5];
 #pragma unroll
     for (int l = 0; l < 5; ++l)
     {
         pM0[l] = __shfl_up_sync(FULL, sM[Q - 1][l], 1);
         pI0[l] = __shfl_up_sync(FULL, sI[Q - 1][l], 1);
+        if (lane == 0) pM0[l] = NEG_INF, pI0[l] = NEG_INF; /* the left warp's values arrive with barrier A */
     }
-    grp.sync(); /* A */
-    if (lane == 0)
-#pragma unroll
-        for (int l = 0; l < 5; ++l)
-        {
-            pM0[l] = warp ? sh.pM[par][warp - 1][l] : NEG_INF;
-            pI0[l] = warp ? sh.pI[par][warp - 1][l] : NEG_INF;
-        }
 
-    /* D chain (order: M_{k-1} by length, then D_{k-1}) */
+    /* D chain (order: M_{k-1} by length, then D_{k-1}), first inside the warp: its first node has no source yet */
     float d[Q];
     int dcode[Q];
 #pragma unroll
@@ -363,16 +368,53 @@ __device__ __forceinline__ void trace_row_mw(float (&tm)[5][8], float (&ti)[5][8
         d[i] = best, dcode[i] = c;
     }
     float din = NEG_INF;
+    for (;;)
+    {
+        float old = d[Q - 1];
+        din = __shfl_up_sync(FULL, old, 1);
+        if (lane == 0) din = NEG_INF;
+        float x = din;
+#pragma unroll
+        for (int i = 0; i < Q; ++i)
+        {
+            x = x + p.DD[i];
+            if (x > d[i]) d[i] = x, dcode[i] = 5;
+            x = d[i];
+        }
+        if (!__any_sync(FULL, d[Q - 1] > old)) break;
+    }
+    if (lane == 31)
+    {
+#pragma unroll
+        for (int l = 0; l < 5; ++l)
+        {
+            GRP_PUT(grp, pM[par][warp][l], sM[Q - 1][l]);
+            GRP_PUT(grp, pI[par][warp][l], sI[Q - 1][l]);
+        }
+        GRP_PUT(grp, d_last[0][warp], d[Q - 1]);
+    }
+    grp.sync(); /* A: the five sums of each warp's last node and the end of its local D chain */
+    if (lane == 0 && warp)
+    {
+#pragma unroll
+        for (int l = 0; l < 5; ++l) pM0[l] = sh.pM[par][warp - 1][l], pI0[l] = sh.pI[par][warp - 1][l];
+        /* M_{k-1} -> D_k candidates of the warp's first node come first in the order; its D_{k-1} follows below */
+        first_max5(pM0, p.MD[0], 0, d[0], dcode[0]);
+    }
+
+    /* carries between warps, lazily; the per-warp E candidates ride on the same barrier (C): when no warp's last D
+     * rose, every D was final and so are the candidates published in that round */
+    float ew;
+    int ecode;
     for (int round = 0;; ++round)
     {
         const int b = round & 1;
-        float din0 = NEG_INF;
         if (round > 0)
         {
             if (lane == 31) GRP_PUT(grp, d_last[b][warp], d[Q - 1]);
             grp.sync(); /* B */
-            din0 = warp ? sh.d_last[b][warp - 1] : NEG_INF;
         }
+        const float din0 = warp ? sh.d_last[b][warp - 1] : NEG_INF;
         const float before = __shfl_sync(FULL, d[Q - 1], 31);
         for (;;)
         {
@@ -390,34 +432,33 @@ __device__ __forceinline__ void trace_row_mw(float (&tm)[5][8], float (&ti)[5][8
             if (!__any_sync(FULL, d[Q - 1] > old)) break;
         }
         const float after = __shfl_sync(FULL, d[Q - 1], 31);
-        /* round 0 is the warp-local chain: always go on to exchange carries at least once */
-        if (!grp.any(round == 0 || after > before, sh.flag, CL == 2 ? grp.peer->flag : sh.flag, b)) break; /* C */
-    }
 
-    /* E: first max over M_1, M_2, D_2, ... ; warps and lanes hold increasing k */
-    float ebest = NEG_INF;
-    int ecode = 0;
+        /* E: first max over M_1, M_2, D_2, ... ; warps and lanes hold increasing k */
+        float ebest = NEG_INF;
+        ecode = 0;
 #pragma unroll
-    for (int i = 0; i < Q; ++i)
-    {
-        int k0 = warp * 256 + lane * Q + i; /* k - 1 */
-        float zero = 0.0f;
-        first_max5(sM[i], zero, k0 * 6, ebest, ecode);
-        if (k0 >= 1)
+        for (int i = 0; i < Q; ++i)
         {
-            float v = d[i] + zero;
-            if (v > ebest) ebest = v, ecode = k0 * 6 + 5;
+            int k0 = warp * 256 + lane * Q + i; /* k - 1 */
+            float zero = 0.0f;
+            first_max5(sM[i], zero, k0 * 6, ebest, ecode);
+            if (k0 >= 1)
+            {
+                float v = d[i] + zero;
+                if (v > ebest) ebest = v, ecode = k0 * 6 + 5;
+            }
         }
+        ew = warp_max(ebest);
+        unsigned who = __ballot_sync(FULL, ebest == ew);
+        ecode = __shfl_sync(FULL, ecode, who ? __ffs(who) - 1 : 0);
+        if (lane == 0)
+        {
+            GRP_PUT(grp, e_best[par][warp], ew);
+            GRP_PUT(grp, e_code[par][warp], ecode);
+        }
+        /* round 0 already used the left warp's local chain end; a warp whose last D rose has to be re-read */
+        if (!grp.any(after > before, sh.flag, CL == 2 ? grp.peer->flag : sh.flag, b)) break; /* C */
     }
-    float ew = warp_max(ebest);
-    unsigned who = __ballot_sync(FULL, ebest == ew);
-    ecode = __shfl_sync(FULL, ecode, who ? __ffs(who) - 1 : 0);
-    if (lane == 0)
-    {
-        GRP_PUT(grp, e_best[par][warp], ew);
-        GRP_PUT(grp, e_code[par][warp], ecode);
-    }
-    grp.sync(); /* D */
     float E = sh.e_best[par][0];
     ecode = sh.e_code[par][0];
 #pragma unroll
@@ -536,18 +577,12 @@ __global__ void __launch_bounds__(W * 32) k_trace_mw(const float *__restrict__ e
     float T = NEG_INF;
     uint32_t j = 1;
 #define TR_ARGS(jj) r + (jj), wc[(jj)], warp, lane, (int)((jj)&1u), grp, sp, cb + (size_t)(jj) * CS, rb + (jj), T
-    for (; j + 4 <= L; j += 5)
+#pragma unroll 1
+    for (; j <= L; ++j)
     {
         trace_row_mw<W, CL, 0>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j));
-        trace_row_mw<W, CL, 1>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j + 1));
-        trace_row_mw<W, CL, 2>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j + 2));
-        trace_row_mw<W, CL, 3>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j + 3));
-        trace_row_mw<W, CL, 4>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j + 4));
+        ring_rotate<Q>(tm, ti, tn, tjr, tc);
     }
-    if (j <= L) trace_row_mw<W, CL, 0>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j));
-    if (j + 1 <= L) trace_row_mw<W, CL, 1>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j + 1));
-    if (j + 2 <= L) trace_row_mw<W, CL, 2>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j + 2));
-    if (j + 3 <= L) trace_row_mw<W, CL, 3>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j + 3));
 #undef TR_ARGS
     if (warp == 0 && lane == 0) alt_out[job] = T;
     if (CL == 2) grp.sync(); /* no block may exit while its peer can still store into its shared memory */
