@@ -523,6 +523,8 @@ struct MwShared
     float v_spec[2][4]; /* V_N, V_J, V_C of the row */
     int flag[2][2];
     unsigned long long item;
+    alignas(16) float xch[2][kMaxGroupWarps][8]; /* 2-block groups: Group::exchange buffers ... */
+    unsigned long long xbar[2];                  /* ... and their mbarriers */
 };
 
 template <int W, int CL, int R>
@@ -592,60 +594,116 @@ __device__ __forceinline__ void mw_row(float (&tm)[5][8], float (&ti)[5][8], flo
         }
         if (!__any_sync(FULL, d[Q - 1] > old)) break;
     }
-    if (lane == 31)
+#ifndef DCP_CLUSTER_XCH
+#define DCP_CLUSTER_XCH 1
+#endif
+    float E, vN, vJ, vC;
+    if constexpr (CL == 2 && DCP_CLUSTER_XCH)
     {
-        GRP_PUT(grp, vm_last[par][gw], vm[Q - 1]);
-        GRP_PUT(grp, vi_last[par][gw], vi[Q - 1]);
-        GRP_PUT(grp, e_warp[par][gw], ew);
-        GRP_PUT(grp, d_last[0][gw], d[Q - 1]);
-    }
-    if (gw == 0 && lane < 3) GRP_PUT(grp, v_spec[par][lane], vx);
-    grp.sync(); /* A: boundary values, per-warp maxima, specials and the local D chains' ends */
-
-    if (lane == 0)
-    {
-        vm_prev = gw ? sh.vm_last[par][gw - 1] : NEG_INF;
-        vi_prev = gw ? sh.vi_last[par][gw - 1] : NEG_INF;
-    }
-    float E = sh.e_warp[par][0];
-#pragma unroll
-    for (int w = 1; w < TW; ++w) E = fmaxf(E, sh.e_warp[par][w]);
-    const float vN = sh.v_spec[par][0], vJ = sh.v_spec[par][1], vC = sh.v_spec[par][2];
-
-    /* carries between warps: D of the warp's first node = max(V_M(left) + MD, D(left) + DD), then lazily on */
-    float din0 = NEG_INF; /* D of the last node of the warp to the left */
-    for (int round = 0;; ++round)
-    {
-        const int b = round & 1;
-        if (round > 0)
+        /* A: boundary values, per-warp maxima, the local D chains' ends and the specials, one exchange */
+        const float xN = __shfl_sync(FULL, vx, 0), xJ = __shfl_sync(FULL, vx, 1), xC = __shfl_sync(FULL, vx, 2);
+        const float pay_a[8] = {vm[Q - 1], vi[Q - 1], ew, d[Q - 1], xN, xJ, xC, 0.0f};
+        int s = grp.exchange(gw, lane, pay_a);
         {
-            if (lane == 31) GRP_PUT(grp, d_last[b][gw], d[Q - 1]);
-            grp.sync(); /* B */
+            const float(*x)[8] = sh.xch[s];
+            if (lane == 0)
+            {
+                vm_prev = gw ? x[gw - 1][0] : NEG_INF;
+                vi_prev = gw ? x[gw - 1][1] : NEG_INF;
+            }
+            E = x[0][2];
+#pragma unroll
+            for (int w = 1; w < TW; ++w) E = fmaxf(E, x[w][2]);
+            vN = x[0][4], vJ = x[0][5], vC = x[0][6];
         }
-        din0 = gw ? sh.d_last[b][gw - 1] : NEG_INF;
-        const float before = __shfl_sync(FULL, d[Q - 1], 31);
+        float din0 = gw ? sh.xch[s][gw - 1][3] : NEG_INF;
+        /* carries between warps, lazily: every round ends with an exchange of (did my last D rise, my last D) */
         for (;;)
         {
-            float old = d[Q - 1];
-            din = __shfl_up_sync(FULL, old, 1);
-            if (lane == 0) din = din0;
-            float x = lane == 0 ? fmaxf(vm_prev + p.MD[0], din0 + p.DD[0]) : din + p.DD[0];
-            d[0] = fmaxf(d[0], x);
-            x = d[0];
-#pragma unroll
-            for (int i = 1; i < Q; ++i)
+            const float before = __shfl_sync(FULL, d[Q - 1], 31);
+            for (;;)
             {
-                x = x + p.DD[i];
-                d[i] = fmaxf(d[i], x);
-                x = d[i];
+                float old = d[Q - 1];
+                din = __shfl_up_sync(FULL, old, 1);
+                if (lane == 0) din = din0;
+                float x = lane == 0 ? fmaxf(vm_prev + p.MD[0], din0 + p.DD[0]) : din + p.DD[0];
+                d[0] = fmaxf(d[0], x);
+                x = d[0];
+#pragma unroll
+                for (int i = 1; i < Q; ++i)
+                {
+                    x = x + p.DD[i];
+                    d[i] = fmaxf(d[i], x);
+                    x = d[i];
+                }
+                if (!__any_sync(FULL, d[Q - 1] > old)) break;
             }
-            if (!__any_sync(FULL, d[Q - 1] > old)) break;
+            const float pay_c[8] = {d[Q - 1] > before ? 1.0f : 0.0f, d[Q - 1], 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+            s = grp.exchange(gw, lane, pay_c);
+            float rose = sh.xch[s][0][0];
+#pragma unroll
+            for (int w = 1; w < TW; ++w) rose = fmaxf(rose, sh.xch[s][w][0]);
+            if (rose == 0.0f) break; /* C */
+            din0 = gw ? sh.xch[s][gw - 1][1] : NEG_INF;
         }
-        /* two warps: the left warp has no carry-in, so the D it published at A was final, and nobody reads
-         * the right warp's -- no second round can happen and barrier C is not needed (M = 512: 457 -> 520 GCUPS) */
-        if (TW == 2) break;
-        const float after = __shfl_sync(FULL, d[Q - 1], 31);
-        if (!grp.any(after > before, sh.flag, CL == 2 ? grp.peer->flag : sh.flag, b)) break; /* C */
+    }
+    else
+    {
+        if (lane == 31)
+        {
+            GRP_PUT(grp, vm_last[par][gw], vm[Q - 1]);
+            GRP_PUT(grp, vi_last[par][gw], vi[Q - 1]);
+            GRP_PUT(grp, e_warp[par][gw], ew);
+            GRP_PUT(grp, d_last[0][gw], d[Q - 1]);
+        }
+        if (gw == 0 && lane < 3) GRP_PUT(grp, v_spec[par][lane], vx);
+        grp.sync(); /* A: boundary values, per-warp maxima, specials and the local D chains' ends */
+
+        if (lane == 0)
+        {
+            vm_prev = gw ? sh.vm_last[par][gw - 1] : NEG_INF;
+            vi_prev = gw ? sh.vi_last[par][gw - 1] : NEG_INF;
+        }
+        E = sh.e_warp[par][0];
+#pragma unroll
+        for (int w = 1; w < TW; ++w) E = fmaxf(E, sh.e_warp[par][w]);
+        vN = sh.v_spec[par][0], vJ = sh.v_spec[par][1], vC = sh.v_spec[par][2];
+
+        /* carries between warps: D of the warp's first node = max(V_M(left) + MD, D(left) + DD), then lazily on */
+        float din0 = NEG_INF; /* D of the last node of the warp to the left */
+        for (int round = 0;; ++round)
+        {
+            const int b = round & 1;
+            if (round > 0)
+            {
+                if (lane == 31) GRP_PUT(grp, d_last[b][gw], d[Q - 1]);
+                grp.sync(); /* B */
+            }
+            din0 = gw ? sh.d_last[b][gw - 1] : NEG_INF;
+            const float before = __shfl_sync(FULL, d[Q - 1], 31);
+            for (;;)
+            {
+                float old = d[Q - 1];
+                din = __shfl_up_sync(FULL, old, 1);
+                if (lane == 0) din = din0;
+                float x = lane == 0 ? fmaxf(vm_prev + p.MD[0], din0 + p.DD[0]) : din + p.DD[0];
+                d[0] = fmaxf(d[0], x);
+                x = d[0];
+#pragma unroll
+                for (int i = 1; i < Q; ++i)
+                {
+                    x = x + p.DD[i];
+                    d[i] = fmaxf(d[i], x);
+                    x = d[i];
+                }
+                if (!__any_sync(FULL, d[Q - 1] > old)) break;
+            }
+            /* two warps: the left warp has no carry-in, so the D it published at A was final, and nobody reads
+             * the right warp's -- no second round can happen and barrier C is not needed (M = 512: 457 -> 520 GCUPS) */
+            if (TW == 2) break;
+            const float after = __shfl_sync(FULL, d[Q - 1], 31);
+            if (!grp.any(after > before, sh.flag, CL == 2 ? grp.peer->flag : sh.flag, b)) break; /* C */
+        }
     }
 
     float B = max3(vN + NB, vJ + JB, E + EB);
@@ -680,6 +738,7 @@ k_score_mw(const float *__restrict__ emis, const float *__restrict__ trans, cons
     const int lane = threadIdx.x & 31, gw = grp.rank * W + (threadIdx.x >> 5);
     const unsigned long long n_items = (unsigned long long)n_class_profs * nseq;
     if (CL == 2) grp.sync(); /* both blocks' shared memory exists before the first remote store */
+    if constexpr (CL == 2) grp.exchange_init(W);
     for (;;)
     {
         if (grp.rank == 0 && threadIdx.x == 0)

@@ -152,6 +152,7 @@ __device__ __forceinline__ void load_emis(float (&em)[5][Q], const float *__rest
 /* group of warps sharing one pair: W warps of one block (CL = 1) or of a 2-block cluster     */
 /* ----------------------------------------------------------------------------------------- */
 #include <cooperative_groups.h>
+#include <cstddef>
 namespace cg = cooperative_groups;
 
 
@@ -180,6 +181,72 @@ struct Group
     {
         if (CL == 2) cg::this_cluster().sync();
         else __syncthreads();
+    }
+    /*
+     * 2-block groups, score kernel: barrier + all-to-all of a few floats per warp in one step, without the cluster
+     * barrier and without a fence (barrier.cluster.arrive.release costs MEMBAR.ALL.GPU, which also drains the
+     * emission loads in flight for the next row).  Lane 31 of every warp stores its 8 or 12 floats into its own block
+     * (st.shared) and into the peer block (st.async through DSMEM, SASS STAS.128: the bytes are counted on the peer's
+     * mbarrier as they land), then arrives on its own block's mbarrier expecting the bytes of its mirror warp.  The
+     * phase completes when the block's W warps have arrived and all bytes of the peer's W warps have landed.  Two
+     * mbarriers / buffers alternate; a block cannot be two exchanges ahead of its peer (each exchange needs the peer's
+     * bytes), so bytes of exchange n + 2 never reach a barrier that is still in exchange n.
+     * `Shared` provides `float xch[2][kMaxGroupWarps][8 or 12]` (16-byte aligned) and `unsigned long long xbar[2]`.
+     */
+    uint32_t me_s, peer_s, xstate; /* shared-window addresses of *me in this block / the peer; slot + parities */
+    __device__ __forceinline__ void exchange_init(int block_warps)
+    {
+        me_s = (uint32_t)__cvta_generic_to_shared(me);
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer_s) : "r"(me_s), "r"(rank ^ 1));
+        xstate = 0;
+        if (threadIdx.x == 0)
+        {
+            const uint32_t b = me_s + (uint32_t)offsetof(Shared, xbar);
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b), "r"(block_warps) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b + 8), "r"(block_warps) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        cg::this_cluster().sync();
+    }
+    /* the NF floats of v are taken from lane 31; returns the buffer index to read me->xch[..] from */
+    static constexpr int NF = (int)(sizeof(((Shared *)nullptr)->xch[0][0]) / sizeof(float)); /* floats per warp: 8, 12 */
+    __device__ __forceinline__ int exchange(int gw, int lane, const float (&v)[NF])
+    {
+        static_assert(NF % 4 == 0, "whole 16-byte stores");
+        const uint32_t s = xstate & 1u;
+        const uint32_t bar = me_s + (uint32_t)offsetof(Shared, xbar) + s * 8u;
+        if (lane == 31)
+        {
+            const uint32_t off = (uint32_t)offsetof(Shared, xch) + (s * kMaxGroupWarps + (uint32_t)gw) * (NF * 4u);
+            const uint32_t rbar = peer_s + (uint32_t)offsetof(Shared, xbar) + s * 8u;
+#pragma unroll
+            for (int q = 0; q < NF; q += 4)
+            {
+                asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(me_s + off + q * 4), "f"(v[q]), "f"(v[q + 1]),
+                             "f"(v[q + 2]), "f"(v[q + 3])
+                             : "memory");
+                asm volatile(
+                    "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                        peer_s + off + q * 4),
+                    "r"(__float_as_uint(v[q])), "r"(__float_as_uint(v[q + 1])), "r"(__float_as_uint(v[q + 2])),
+                    "r"(__float_as_uint(v[q + 3])), "r"(rbar)
+                    : "memory");
+            }
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(NF * 4u) : "memory");
+        }
+        const uint32_t parity = (xstate >> (1u + s)) & 1u;
+        uint32_t ok = 0;
+        for (uint32_t spin = 0; !ok; ++spin)
+        {
+            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+                         " selp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(ok)
+                         : "r"(bar), "r"(parity)
+                         : "memory");
+            if (spin > (1u << 24)) __trap(); /* a lost store must not hang the GPU */
+        }
+        xstate ^= (2u << s) | 1u;
+        return (int)s;
     }
     /* OR of a predicate over every thread of the group; `flag` = two ints per block, caller alternates slot */
     __device__ __forceinline__ bool any(bool pred, int (*flag)[2], int (*peer_flag)[2], int slot)

@@ -291,6 +291,8 @@ __global__ void __launch_bounds__(128) k_trace(const float *__restrict__ emis, c
 /* ----------------------------------------------------------------------------------------- */
 struct MwTraceShared
 {
+    alignas(16) float xch[2][kMaxGroupWarps][12]; /* 2-block groups: Group::exchange buffers ... */
+    unsigned long long xbar[2];                   /* ... and their mbarriers */
     float pM[2][kMaxGroupWarps][5], pI[2][kMaxGroupWarps][5]; /* the five sums of each warp's last node */
     float d_last[2][kMaxGroupWarps];
     float e_best[2][kMaxGroupWarps];
@@ -383,87 +385,157 @@ __device__ __forceinline__ void trace_row_mw(float (&tm)[5][8], float (&ti)[5][8
         }
         if (!__any_sync(FULL, d[Q - 1] > old)) break;
     }
-    if (lane == 31)
-    {
-#pragma unroll
-        for (int l = 0; l < 5; ++l)
-        {
-            GRP_PUT(grp, pM[par][warp][l], sM[Q - 1][l]);
-            GRP_PUT(grp, pI[par][warp][l], sI[Q - 1][l]);
-        }
-        GRP_PUT(grp, d_last[0][warp], d[Q - 1]);
-    }
-    grp.sync(); /* A: the five sums of each warp's last node and the end of its local D chain */
-    if (lane == 0 && warp)
-    {
-#pragma unroll
-        for (int l = 0; l < 5; ++l) pM0[l] = sh.pM[par][warp - 1][l], pI0[l] = sh.pI[par][warp - 1][l];
-        /* M_{k-1} -> D_k candidates of the warp's first node come first in the order; its D_{k-1} follows below */
-        first_max5(pM0, p.MD[0], 0, d[0], dcode[0]);
-    }
-
-    /* carries between warps, lazily; the per-warp E candidates ride on the same barrier (C): when no warp's last D
-     * rose, every D was final and so are the candidates published in that round */
-    float ew;
+#ifndef DCP_CLUSTER_XCH
+#define DCP_CLUSTER_XCH 1
+#endif
+    float E, ew;
     int ecode;
-    for (int round = 0;; ++round)
+    if constexpr (CL == 2 && DCP_CLUSTER_XCH)
     {
-        const int b = round & 1;
-        if (round > 0)
+        /* A: the five sums of each warp's last node and the end of its local D chain, one exchange (no cluster barrier) */
+        const float pay_a[12] = {sM[Q - 1][0], sM[Q - 1][1], sM[Q - 1][2], sM[Q - 1][3], sM[Q - 1][4], sI[Q - 1][0],
+                                 sI[Q - 1][1], sI[Q - 1][2], sI[Q - 1][3], sI[Q - 1][4], d[Q - 1],     0.0f};
+        int s = grp.exchange(warp, lane, pay_a);
+        if (lane == 0 && warp)
         {
-            if (lane == 31) GRP_PUT(grp, d_last[b][warp], d[Q - 1]);
-            grp.sync(); /* B */
+#pragma unroll
+            for (int l = 0; l < 5; ++l) pM0[l] = sh.xch[s][warp - 1][l], pI0[l] = sh.xch[s][warp - 1][5 + l];
+            first_max5(pM0, p.MD[0], 0, d[0], dcode[0]);
         }
-        const float din0 = warp ? sh.d_last[b][warp - 1] : NEG_INF;
-        const float before = __shfl_sync(FULL, d[Q - 1], 31);
+        float din0 = warp ? sh.xch[s][warp - 1][10] : NEG_INF;
         for (;;)
         {
-            float old = d[Q - 1];
-            din = __shfl_up_sync(FULL, old, 1);
-            if (lane == 0) din = din0;
-            float x = din;
+            const float before = __shfl_sync(FULL, d[Q - 1], 31);
+            for (;;)
+            {
+                float old = d[Q - 1];
+                din = __shfl_up_sync(FULL, old, 1);
+                if (lane == 0) din = din0;
+                float x = din;
+#pragma unroll
+                for (int i = 0; i < Q; ++i)
+                {
+                    x = x + p.DD[i];
+                    if (x > d[i]) d[i] = x, dcode[i] = 5;
+                    x = d[i];
+                }
+                if (!__any_sync(FULL, d[Q - 1] > old)) break;
+            }
+            /* E candidates of this warp with the D values of this round (final when no warp's last D rose) */
+            float ebest = NEG_INF;
+            ecode = 0;
 #pragma unroll
             for (int i = 0; i < Q; ++i)
             {
-                x = x + p.DD[i];
-                if (x > d[i]) d[i] = x, dcode[i] = 5;
-                x = d[i];
+                int k0 = warp * 256 + lane * Q + i; /* k - 1 */
+                float zero = 0.0f;
+                first_max5(sM[i], zero, k0 * 6, ebest, ecode);
+                if (k0 >= 1)
+                {
+                    float v = d[i] + zero;
+                    if (v > ebest) ebest = v, ecode = k0 * 6 + 5;
+                }
             }
-            if (!__any_sync(FULL, d[Q - 1] > old)) break;
-        }
-        const float after = __shfl_sync(FULL, d[Q - 1], 31);
-
-        /* E: first max over M_1, M_2, D_2, ... ; warps and lanes hold increasing k */
-        float ebest = NEG_INF;
-        ecode = 0;
+            ew = warp_max(ebest);
+            unsigned who = __ballot_sync(FULL, ebest == ew);
+            ecode = __shfl_sync(FULL, ecode, who ? __ffs(who) - 1 : 0);
+            const float pay_c[12] = {d[Q - 1] > before ? 1.0f : 0.0f, d[Q - 1], ew, __int_as_float(ecode), 0.0f, 0.0f, 0.0f,
+                                     0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+            s = grp.exchange(warp, lane, pay_c); /* C */
+            float rose = sh.xch[s][0][0];
 #pragma unroll
-        for (int i = 0; i < Q; ++i)
-        {
-            int k0 = warp * 256 + lane * Q + i; /* k - 1 */
-            float zero = 0.0f;
-            first_max5(sM[i], zero, k0 * 6, ebest, ecode);
-            if (k0 >= 1)
-            {
-                float v = d[i] + zero;
-                if (v > ebest) ebest = v, ecode = k0 * 6 + 5;
-            }
+            for (int w = 1; w < TW; ++w) rose = fmaxf(rose, sh.xch[s][w][0]);
+            if (rose == 0.0f) break;
+            din0 = warp ? sh.xch[s][warp - 1][1] : NEG_INF;
         }
-        ew = warp_max(ebest);
-        unsigned who = __ballot_sync(FULL, ebest == ew);
-        ecode = __shfl_sync(FULL, ecode, who ? __ffs(who) - 1 : 0);
-        if (lane == 0)
-        {
-            GRP_PUT(grp, e_best[par][warp], ew);
-            GRP_PUT(grp, e_code[par][warp], ecode);
-        }
-        /* round 0 already used the left warp's local chain end; a warp whose last D rose has to be re-read */
-        if (!grp.any(after > before, sh.flag, CL == 2 ? grp.peer->flag : sh.flag, b)) break; /* C */
+        E = sh.xch[s][0][2];
+        ecode = __float_as_int(sh.xch[s][0][3]);
+#pragma unroll
+        for (int w = 1; w < TW; ++w)
+            if (sh.xch[s][w][2] > E) E = sh.xch[s][w][2], ecode = __float_as_int(sh.xch[s][w][3]);
     }
-    float E = sh.e_best[par][0];
-    ecode = sh.e_code[par][0];
+    else
+    {
+        if (lane == 31)
+        {
 #pragma unroll
-    for (int w = 1; w < TW; ++w)
-        if (sh.e_best[par][w] > E) E = sh.e_best[par][w], ecode = sh.e_code[par][w];
+            for (int l = 0; l < 5; ++l)
+            {
+                GRP_PUT(grp, pM[par][warp][l], sM[Q - 1][l]);
+                GRP_PUT(grp, pI[par][warp][l], sI[Q - 1][l]);
+            }
+            GRP_PUT(grp, d_last[0][warp], d[Q - 1]);
+        }
+        grp.sync(); /* A: the five sums of each warp's last node and the end of its local D chain */
+        if (lane == 0 && warp)
+        {
+#pragma unroll
+            for (int l = 0; l < 5; ++l) pM0[l] = sh.pM[par][warp - 1][l], pI0[l] = sh.pI[par][warp - 1][l];
+            /* M_{k-1} -> D_k candidates of the warp's first node come first in the order; its D_{k-1} follows below */
+            first_max5(pM0, p.MD[0], 0, d[0], dcode[0]);
+        }
+
+        /* carries between warps, lazily; the per-warp E candidates ride on the same barrier (C): when no warp's last D
+         * rose, every D was final and so are the candidates published in that round */
+        for (int round = 0;; ++round)
+        {
+            const int b = round & 1;
+            if (round > 0)
+            {
+                if (lane == 31) GRP_PUT(grp, d_last[b][warp], d[Q - 1]);
+                grp.sync(); /* B */
+            }
+            const float din0 = warp ? sh.d_last[b][warp - 1] : NEG_INF;
+            const float before = __shfl_sync(FULL, d[Q - 1], 31);
+            for (;;)
+            {
+                float old = d[Q - 1];
+                din = __shfl_up_sync(FULL, old, 1);
+                if (lane == 0) din = din0;
+                float x = din;
+#pragma unroll
+                for (int i = 0; i < Q; ++i)
+                {
+                    x = x + p.DD[i];
+                    if (x > d[i]) d[i] = x, dcode[i] = 5;
+                    x = d[i];
+                }
+                if (!__any_sync(FULL, d[Q - 1] > old)) break;
+            }
+            const float after = __shfl_sync(FULL, d[Q - 1], 31);
+
+            /* E: first max over M_1, M_2, D_2, ... ; warps and lanes hold increasing k */
+            float ebest = NEG_INF;
+            ecode = 0;
+#pragma unroll
+            for (int i = 0; i < Q; ++i)
+            {
+                int k0 = warp * 256 + lane * Q + i; /* k - 1 */
+                float zero = 0.0f;
+                first_max5(sM[i], zero, k0 * 6, ebest, ecode);
+                if (k0 >= 1)
+                {
+                    float v = d[i] + zero;
+                    if (v > ebest) ebest = v, ecode = k0 * 6 + 5;
+                }
+            }
+            ew = warp_max(ebest);
+            unsigned who = __ballot_sync(FULL, ebest == ew);
+            ecode = __shfl_sync(FULL, ecode, who ? __ffs(who) - 1 : 0);
+            if (lane == 0)
+            {
+                GRP_PUT(grp, e_best[par][warp], ew);
+                GRP_PUT(grp, e_code[par][warp], ecode);
+            }
+            /* round 0 already used the left warp's local chain end; a warp whose last D rose has to be re-read */
+            if (!grp.any(after > before, sh.flag, CL == 2 ? grp.peer->flag : sh.flag, b)) break; /* C */
+        }
+        E = sh.e_best[par][0];
+        ecode = sh.e_code[par][0];
+#pragma unroll
+        for (int w = 1; w < TW; ++w)
+            if (sh.e_best[par][w] > E) E = sh.e_best[par][w], ecode = sh.e_code[par][w];
+    }
 
     /* specials: every warp keeps its own copy of the N/J/C rings (identical values) */
     float best;
@@ -538,6 +610,7 @@ __global__ void __launch_bounds__(W * 32) k_trace_mw(const float *__restrict__ e
     __shared__ MwTraceShared sh;
     Group<CL, MwTraceShared> grp;
     grp.init(&sh);
+    if constexpr (CL == 2) grp.exchange_init(W);
     const int lane = threadIdx.x & 31, warp = grp.rank * W + (threadIdx.x >> 5);
     const uint32_t job = blockIdx.x / CL;
     if (job >= njobs) return;
