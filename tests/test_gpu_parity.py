@@ -118,6 +118,27 @@ def test_long_plan7_profile_with_hit(pkg, o32):
     check_scan(pkg, o32, db, tw, [read, full[:900]], multi_hits=True, thr=10.0, flavour=1)
 
 
+@pytest.mark.parametrize("M,skip", [(1500, (600, 1100)), (3000, (1200, 1800)), (4096, (1700, 2700))])
+def test_deletion_run_across_whole_warps_and_blocks(pkg, o32, M, skip):
+    """The read matches the profile up to node skip[0] and again from skip[1]: the D chain between them runs through
+    whole warps (256 nodes each) and, above 2048 nodes, from one block of the cluster into the other, so the lazy
+    carry exchange needs several rounds in every row after the first matched stretch."""
+    rng = np.random.default_rng(M)
+    nl, ma, tr = plan7_profile_inputs(rng, M)
+    p = pkg.ProteinProfile.from_model(nl, ma, tr, pkg.protein_cfg(pkg.ENTRY_DIST_OCCUPANCY, 0.01), "DEL%d" % M)
+    db = pkg.Db(0)
+    db.add(p)
+    db.commit()
+    tw = [oracle_twin(o32, p, 0.01)]
+    full = sample_read(rng, ma, 3 * M, 0.0, 0.0)
+    a, b = skip
+    read = full[3 * (a - 250):3 * a] + full[3 * b:3 * (b + 150)]
+    for multi in (False, True):
+        res, ref = check_scan(pkg, o32, db, tw, [read, full[3 * (a - 100):3 * (a + 100)]], multi_hits=multi, thr=10.0,
+                              flavour=1, rows=False)
+        assert res.nhits == 2
+
+
 def test_plan7_profiles_with_real_hits(pkg, o32):
     """Pfam-shaped profiles, frameshifted coding reads drawn from them: real hits, long D/I stretches."""
     rng = np.random.default_rng(42)
