@@ -527,15 +527,14 @@ struct MwShared
     unsigned long long xbar[2];                  /* ... and their mbarriers */
 };
 
-template <int W, int CL, int R>
-__device__ __forceinline__ void mw_row(float (&tm)[5][8], float (&ti)[5][8], float (&tx)[5],
-                                       const NodeParams<8> &p, RowState<8> &rs,
+template <int W, int CL, int R, int Q>
+__device__ __forceinline__ void mw_row(float (&tm)[5][Q], float (&ti)[5][Q], float (&tx)[5],
+                                       const NodeParams<Q> &p, RowState<Q> &rs,
                                        const float *__restrict__ emis_lane, const RowRec *__restrict__ rec_next,
                                        const uint16_t *__restrict__ w_next2, int gw, int lane, int par,
                                        Group<CL, MwShared> &grp, float NB, float JB, float EB, float cE, float cX,
                                        float &E_out, float &vC_out)
 {
-    constexpr int Q = 8;
     constexpr int TW = W * CL;
     constexpr int ROW = 256 * TW;
     constexpr int S1 = (R + 4) % 5, S2 = (R + 3) % 5, S3 = (R + 2) % 5, S4 = (R + 1) % 5, S5 = R;
@@ -721,7 +720,7 @@ __device__ __forceinline__ void mw_row(float (&tm)[5][8], float (&ti)[5][8], flo
     vC_out = vC;
 }
 
-template <int W, int CL>
+template <int W, int CL, int Q = 8>
 __global__ void __launch_bounds__(W * 32, CL == 2 ? 1 : 8 / W)
 k_score_mw(const float *__restrict__ emis, const float *__restrict__ trans, const ProfMeta *__restrict__ metas,
            const uint32_t *__restrict__ class_profs, uint32_t n_class_profs, const SeqMeta *__restrict__ seqs,
@@ -729,7 +728,6 @@ k_score_mw(const float *__restrict__ emis, const float *__restrict__ trans, cons
            const uint16_t *__restrict__ wcodes, const float *__restrict__ spec, float *__restrict__ alt_out,
            uint32_t nprof, unsigned long long *__restrict__ counter, uint32_t seq_tile)
 {
-    constexpr int Q = 8;
     constexpr int TW = W * CL;
     constexpr int ROW = 256 * TW;
     __shared__ MwShared sh;
@@ -759,7 +757,7 @@ k_score_mw(const float *__restrict__ emis, const float *__restrict__ trans, cons
         const uint32_t s = tile * seq_tile + (uint32_t)(in_tile % seqs_here);
         const ProfMeta pm = metas[prof];
         NodeParams<Q> p;
-        load_params<Q>(p, trans + pm.trans_off, ROW, gw * 256 + lane * Q);
+        load_params<Q>(p, trans + pm.trans_off, 32 * Q * TW, gw * 32 * Q + lane * Q);
         const float *emis_lane = emis + pm.emis_off + gw * 256 + lane * 4;
         const SeqMeta sm = seqs[s];
         const RowRec *recs = rows + (size_t)pm.null_id * total_recs + sm.rec_off;
@@ -802,16 +800,16 @@ k_score_mw(const float *__restrict__ emis, const float *__restrict__ trans, cons
 #define MW_ARGS(jj) recs + min((uint32_t)(jj) + 1u, L), wc + min((uint32_t)(jj) + 3u, L), gw, lane, (int)((jj)&1u), grp
         for (; j + 4 <= L; j += 5)
         {
-            mw_row<W, CL, 0>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j), NB, JB, EB, cE, cX, E, vC);
-            mw_row<W, CL, 1>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 1), NB, JB, EB, cE, cX, E, vC);
-            mw_row<W, CL, 2>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 2), NB, JB, EB, cE, cX, E, vC);
-            mw_row<W, CL, 3>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 3), NB, JB, EB, cE, cX, E, vC);
-            mw_row<W, CL, 4>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 4), NB, JB, EB, cE, cX, E, vC);
+            mw_row<W, CL, 0, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j), NB, JB, EB, cE, cX, E, vC);
+            mw_row<W, CL, 1, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 1), NB, JB, EB, cE, cX, E, vC);
+            mw_row<W, CL, 2, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 2), NB, JB, EB, cE, cX, E, vC);
+            mw_row<W, CL, 3, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 3), NB, JB, EB, cE, cX, E, vC);
+            mw_row<W, CL, 4, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 4), NB, JB, EB, cE, cX, E, vC);
         }
-        if (j <= L) mw_row<W, CL, 0>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j), NB, JB, EB, cE, cX, E, vC);
-        if (j + 1 <= L) mw_row<W, CL, 1>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 1), NB, JB, EB, cE, cX, E, vC);
-        if (j + 2 <= L) mw_row<W, CL, 2>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 2), NB, JB, EB, cE, cX, E, vC);
-        if (j + 3 <= L) mw_row<W, CL, 3>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 3), NB, JB, EB, cE, cX, E, vC);
+        if (j <= L) mw_row<W, CL, 0, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j), NB, JB, EB, cE, cX, E, vC);
+        if (j + 1 <= L) mw_row<W, CL, 1, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 1), NB, JB, EB, cE, cX, E, vC);
+        if (j + 2 <= L) mw_row<W, CL, 2, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 2), NB, JB, EB, cE, cX, E, vC);
+        if (j + 3 <= L) mw_row<W, CL, 3, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 3), NB, JB, EB, cE, cX, E, vC);
 #undef MW_ARGS
         if (gw == 0 && lane == 0) alt_out[(size_t)s * nprof + prof] = fmaxf(E + ET, vC + CT);
     }
@@ -1002,6 +1000,9 @@ static enum rc db_take(struct dcpgpu_db *db, struct protein_profile *prof, bool 
     return RC_OK;
 }
 
+#ifndef DCP_W2Q7
+#define DCP_W2Q7 1
+#endif
 extern "C" enum rc dcpgpu_db_commit(struct dcpgpu_db *db)
 {
     if (db->committed) return dcp_error(RC_EFAIL, "database already committed");
@@ -1018,15 +1019,21 @@ extern "C" enum rc dcpgpu_db_commit(struct dcpgpu_db *db)
          * faster: 515 vs 489 GCUPS at M = 200.  Above 256 nodes W warps share one pair, 8 nodes per lane. */
         uint32_t Q = (M + 31) / 32, W = 1;
         if (Q == 7) Q = 8;
+        uint32_t cls = Q;
         if (Q > 8)
         {
             Q = 8, W = (M + 255) / 256;
             if (W > kMaxW) W = (W + 1) / 2 * 2; /* two blocks of W/2 warps (cluster) */
+            cls = kMaxQ + W;
+            /* two warps with 6 or 7 nodes per lane instead of 8: fewer padded nodes for 257..448 (M = 350:
+             * 357 -> 418 GCUPS; 5 nodes per lane for 257..320 gains only 2 %, 6 per lane is better there too) */
+            if (M <= 384) Q = 6, cls = kClsW2Q6;
+            else if (DCP_W2Q7 && M <= 448) Q = 7, cls = kClsW2Q7;
         }
         uint32_t QP = Q <= 4 ? 4 : 8;
         ProfMeta &m = db->metas[i];
         m.M = M, m.Q = Q, m.QP = QP, m.null_id = db->null_id[i];
-        m.W = W, m.cls = W == 1 ? Q : kMaxQ + W;
+        m.W = W, m.cls = cls;
         m.emis_off = emis_floats;
         m.trans_off = trans_floats;
         emis_floats += (uint64_t)kTab * 32 * QP * W;
@@ -1346,16 +1353,18 @@ extern "C" enum rc dcpgpu_scan_resident(struct dcpgpu_db *db, struct dcpgpu_seqs
         if (db->class_list[q].empty()) continue;
         uint32_t n_class = (uint32_t)db->class_list[q].size();
         unsigned long long *ctr = b_counter.as<unsigned long long>() + q;
-        const int tw = q - kMaxQ;              /* warps per pair: 2..8 one block, 10/12/14/16 two blocks */
+        const int tw = q > kMaxQ + kMaxGroupWarps ? 2 : q - kMaxQ; /* warps per pair: 2..8 one block, 10/12/14/16 two blocks */
         const int cl = tw > kMaxW ? 2 : 1, w = tw / cl;
         const unsigned blocks = cl == 2 ? (unsigned)(db->sm_count / 2 * 2) : (unsigned)(db->sm_count * (8 / w));
         cudaError_t le = cudaErrorInvalidValue;
-#define MW_LAUNCH(WW, CC)                                                                                     \
-    le = launch_group(k_score_mw<WW, CC>, CC, blocks, WW * 32, st, db->d_emis, db->d_trans, db->d_metas,      \
+#define MW_LAUNCH(WW, CC, ...)                                                                                \
+    le = launch_group(k_score_mw<WW, CC, ##__VA_ARGS__>, CC, blocks, WW * 32, st, db->d_emis, db->d_trans, db->d_metas, \
                       db->d_class[q], n_class, sq->d_metas, nseq, total_recs, b_rows.as<RowRec>(),            \
                       b_wcodes.as<uint16_t>(), b_spec.as<float>(), res->d_alt, nprof, ctr, seq_tile)
-        switch (tw)
+        switch (q == kClsW2Q6 ? -6 : q == kClsW2Q7 ? -7 : tw)
         {
+        case -6: MW_LAUNCH(2, 1, 6); break;
+        case -7: MW_LAUNCH(2, 1, 7); break;
         case 2: MW_LAUNCH(2, 1); break;
         case 3: MW_LAUNCH(3, 1); break;
         case 4: MW_LAUNCH(4, 1); break;

@@ -301,16 +301,15 @@ struct MwTraceShared
 };
 
 /* cell backpointers of a row: [sub-node][warp][lane] */
-template <int W, int CL, int R>
-__device__ __forceinline__ void trace_row_mw(float (&tm)[5][8], float (&ti)[5][8], float (&tn)[5], float (&tj)[5],
-                                             float (&tc)[5], const NodeParams<8> &p,
+template <int W, int CL, int R, int Q>
+__device__ __forceinline__ void trace_row_mw(float (&tm)[5][Q], float (&ti)[5][Q], float (&tn)[5], float (&tj)[5],
+                                             float (&tc)[5], const NodeParams<Q> &p,
                                              const float *__restrict__ emis_lane, const RowRec *__restrict__ rec,
                                              uint32_t wcode, int warp, int lane, int par,
                                              Group<CL, MwTraceShared> &grp,
                                              const float *__restrict__ sp, uint16_t *__restrict__ cell_bp,
                                              uint32_t *__restrict__ row_bp, float &T_out)
 {
-    constexpr int Q = 8;
     constexpr int TW = W * CL; /* `warp` is the warp's index in the whole group, 0..TW-1 */
     constexpr int ROW = 256 * TW;
     constexpr int S[5] = {(R + 4) % 5, (R + 3) % 5, (R + 2) % 5, (R + 1) % 5, R};
@@ -427,7 +426,7 @@ __device__ __forceinline__ void trace_row_mw(float (&tm)[5][8], float (&ti)[5][8
 #pragma unroll
             for (int i = 0; i < Q; ++i)
             {
-                int k0 = warp * 256 + lane * Q + i; /* k - 1 */
+                int k0 = warp * 32 * Q + lane * Q + i; /* k - 1 */
                 float zero = 0.0f;
                 first_max5(sM[i], zero, k0 * 6, ebest, ecode);
                 if (k0 >= 1)
@@ -510,7 +509,7 @@ __device__ __forceinline__ void trace_row_mw(float (&tm)[5][8], float (&ti)[5][8
 #pragma unroll
             for (int i = 0; i < Q; ++i)
             {
-                int k0 = warp * 256 + lane * Q + i; /* k - 1 */
+                int k0 = warp * 32 * Q + lane * Q + i; /* k - 1 */
                 float zero = 0.0f;
                 first_max5(sM[i], zero, k0 * 6, ebest, ecode);
                 if (k0 >= 1)
@@ -594,7 +593,7 @@ __device__ __forceinline__ void trace_row_mw(float (&tm)[5][8], float (&ti)[5][8
     }
 }
 
-template <int W, int CL>
+template <int W, int CL, int Q = 8>
 __global__ void __launch_bounds__(W * 32) k_trace_mw(const float *__restrict__ emis, const float *__restrict__ trans,
                                                      const ProfMeta *__restrict__ metas,
                                                      const SeqMeta *__restrict__ seqs, uint64_t total_rows,
@@ -605,7 +604,6 @@ __global__ void __launch_bounds__(W * 32) k_trace_mw(const float *__restrict__ e
                                                      uint16_t *__restrict__ cell_bp, uint32_t *__restrict__ row_bp,
                                                      float *__restrict__ alt_out)
 {
-    constexpr int Q = 8;
     constexpr int TW = W * CL;
     __shared__ MwTraceShared sh;
     Group<CL, MwTraceShared> grp;
@@ -618,7 +616,7 @@ __global__ void __launch_bounds__(W * 32) k_trace_mw(const float *__restrict__ e
     ProfMeta pm = metas[tj_.prof];
     SeqMeta sm = seqs[tj_.seq];
     NodeParams<Q> p;
-    load_params<Q>(p, trans + pm.trans_off, 256 * TW, warp * 256 + lane * Q);
+    load_params<Q>(p, trans + pm.trans_off, 32 * Q * TW, warp * 32 * Q + lane * Q);
     const float *emis_lane = emis + pm.emis_off + warp * 256 + lane * 4;
     const RowRec *r = rows + (size_t)pm.null_id * total_rows + sm.rec_off; /* r[j] = record of row j */
     const uint16_t *wc = wcodes + sm.rec_off;
@@ -653,7 +651,7 @@ __global__ void __launch_bounds__(W * 32) k_trace_mw(const float *__restrict__ e
 #pragma unroll 1
     for (; j <= L; ++j)
     {
-        trace_row_mw<W, CL, 0>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j));
+        trace_row_mw<W, CL, 0, Q>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j));
         ring_rotate<Q>(tm, ti, tn, tjr, tc);
     }
 #undef TR_ARGS
@@ -866,17 +864,18 @@ enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const
         launch_trace<QQ>(st, b - a, db, sq, d_rows, d_wcodes, d_spec, b_jobs.as<TraceJob>() + a,                  \
                          b_cells.as<uint16_t>(), b_rows.as<uint32_t>(), b_alt.as<float>() + a);                  \
         break;
-#define LTW(TWW, WW, CC)                                                                                         \
-    case kMaxQ + TWW:                                                                                            \
-        launch_group(k_trace_mw<WW, CC>, CC, (b - a) * CC, WW * 32, st, db->d_emis, db->d_trans, db->d_metas,     \
+#define LTW(TWW, WW, CC, ...)                                                                                    \
+    case TWW:                                                                                                    \
+        launch_group(k_trace_mw<WW, CC, ##__VA_ARGS__>, CC, (b - a) * CC, WW * 32, st, db->d_emis, db->d_trans, db->d_metas,     \
                      sq->d_metas, sq->total + sq->nseq, d_rows, d_wcodes, d_spec, b_jobs.as<TraceJob>() + a,     \
                      b - a, b_cells.as<uint16_t>(), b_rows.as<uint32_t>(), b_alt.as<float>() + a);               \
         break;
             switch (cls)
             {
                 LT(1) LT(2) LT(3) LT(4) LT(5) LT(6) LT(7) LT(8)
-                LTW(2, 2, 1) LTW(3, 3, 1) LTW(4, 4, 1) LTW(5, 5, 1) LTW(6, 6, 1) LTW(7, 7, 1) LTW(8, 8, 1)
-                LTW(10, 5, 2) LTW(12, 6, 2) LTW(14, 7, 2) LTW(16, 8, 2)
+                LTW(kMaxQ + 2, 2, 1) LTW(kMaxQ + 3, 3, 1) LTW(kMaxQ + 4, 4, 1) LTW(kMaxQ + 5, 5, 1) LTW(kMaxQ + 6, 6, 1)
+                LTW(kMaxQ + 7, 7, 1) LTW(kMaxQ + 8, 8, 1) LTW(kMaxQ + 10, 5, 2) LTW(kMaxQ + 12, 6, 2)
+                LTW(kMaxQ + 14, 7, 2) LTW(kMaxQ + 16, 8, 2) LTW(kClsW2Q6, 2, 1, 6) LTW(kClsW2Q7, 2, 1, 7)
             }
 #undef LT
 #undef LTW
