@@ -1029,6 +1029,8 @@ extern "C" enum rc dcpgpu_db_commit(struct dcpgpu_db *db)
              * 357 -> 418 GCUPS; 5 nodes per lane for 257..320 gains only 2 %, 6 per lane is better there too) */
             if (M <= 384) Q = 6, cls = kClsW2Q6;
             else if (DCP_W2Q7 && M <= 448) Q = 7, cls = kClsW2Q7;
+            else if (M > 512 && M <= 576) Q = 6, cls = kClsW3Q6;
+            else if (M > 576 && M <= 672) Q = 7, cls = kClsW3Q7;
         }
         uint32_t QP = Q <= 4 ? 4 : 8;
         ProfMeta &m = db->metas[i];
@@ -1353,7 +1355,8 @@ extern "C" enum rc dcpgpu_scan_resident(struct dcpgpu_db *db, struct dcpgpu_seqs
         if (db->class_list[q].empty()) continue;
         uint32_t n_class = (uint32_t)db->class_list[q].size();
         unsigned long long *ctr = b_counter.as<unsigned long long>() + q;
-        const int tw = q > kMaxQ + kMaxGroupWarps ? 2 : q - kMaxQ; /* warps per pair: 2..8 one block, 10/12/14/16 two blocks */
+        /* warps per pair: 2..8 one block, 10/12/14/16 two blocks */
+        const int tw = q >= kClsW3Q6 ? 3 : q > kMaxQ + kMaxGroupWarps ? 2 : q - kMaxQ;
         const int cl = tw > kMaxW ? 2 : 1, w = tw / cl;
         const unsigned blocks = cl == 2 ? (unsigned)(db->sm_count / 2 * 2) : (unsigned)(db->sm_count * (8 / w));
         cudaError_t le = cudaErrorInvalidValue;
@@ -1361,10 +1364,12 @@ extern "C" enum rc dcpgpu_scan_resident(struct dcpgpu_db *db, struct dcpgpu_seqs
     le = launch_group(k_score_mw<WW, CC, ##__VA_ARGS__>, CC, blocks, WW * 32, st, db->d_emis, db->d_trans, db->d_metas, \
                       db->d_class[q], n_class, sq->d_metas, nseq, total_recs, b_rows.as<RowRec>(),            \
                       b_wcodes.as<uint16_t>(), b_spec.as<float>(), res->d_alt, nprof, ctr, seq_tile)
-        switch (q == kClsW2Q6 ? -6 : q == kClsW2Q7 ? -7 : tw)
+        switch (q > kMaxQ + kMaxGroupWarps ? -q : tw)
         {
-        case -6: MW_LAUNCH(2, 1, 6); break;
-        case -7: MW_LAUNCH(2, 1, 7); break;
+        case -kClsW2Q6: MW_LAUNCH(2, 1, 6); break;
+        case -kClsW2Q7: MW_LAUNCH(2, 1, 7); break;
+        case -kClsW3Q6: MW_LAUNCH(3, 1, 6); break;
+        case -kClsW3Q7: MW_LAUNCH(3, 1, 7); break;
         case 2: MW_LAUNCH(2, 1); break;
         case 3: MW_LAUNCH(3, 1); break;
         case 4: MW_LAUNCH(4, 1); break;

@@ -19,7 +19,9 @@ constexpr int kMaxW = 8;          /* warps per block in the multi-warp classes: 
 constexpr int kMaxGroupWarps = 16; /* two blocks (a cluster) per pair above 2048 nodes: M <= 4096 */
 constexpr int kClsW2Q6 = kMaxQ + kMaxGroupWarps + 1; /* 257..384 nodes: two warps, 6 nodes per lane */
 constexpr int kClsW2Q7 = kMaxQ + kMaxGroupWarps + 2; /* 385..448 nodes: two warps, 7 nodes per lane */
-constexpr int kNumClasses = kClsW2Q7; /* class c: 1..8 = one warp, Q = c; 8 + TW = TW warps per pair, Q = 8
+constexpr int kClsW3Q6 = kMaxQ + kMaxGroupWarps + 3; /* 513..576 nodes: three warps, 6 nodes per lane */
+constexpr int kClsW3Q7 = kMaxQ + kMaxGroupWarps + 4; /* 577..672 nodes: three warps, 7 nodes per lane */
+constexpr int kNumClasses = kClsW3Q7; /* class c: 1..8 = one warp, Q = c; 8 + TW = TW warps per pair, Q = 8
                                        * (TW = 2..8 one block; 10, 12, 14, 16 two blocks); then the two above */
 constexpr int kWarpsPerBlock = 8; /* k_score block = 8 independent warps */
 /* independent warps per SM in k_score<Q>: 8 nodes per lane need 254 registers (two warps per scheduler);

@@ -876,6 +876,7 @@ enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const
                 LTW(kMaxQ + 2, 2, 1) LTW(kMaxQ + 3, 3, 1) LTW(kMaxQ + 4, 4, 1) LTW(kMaxQ + 5, 5, 1) LTW(kMaxQ + 6, 6, 1)
                 LTW(kMaxQ + 7, 7, 1) LTW(kMaxQ + 8, 8, 1) LTW(kMaxQ + 10, 5, 2) LTW(kMaxQ + 12, 6, 2)
                 LTW(kMaxQ + 14, 7, 2) LTW(kMaxQ + 16, 8, 2) LTW(kClsW2Q6, 2, 1, 6) LTW(kClsW2Q7, 2, 1, 7)
+                LTW(kClsW3Q6, 3, 1, 6) LTW(kClsW3Q7, 3, 1, 7)
             }
 #undef LT
 #undef LTW

@@ -87,7 +87,7 @@ def test_every_lane_layout(pkg, o32, M):
     check_scan(pkg, o32, db, twins, seqs, thr=-1e30, rows=False)
 
 
-@pytest.mark.parametrize("M", [257, 300, 320, 321, 350, 384, 385, 512, 513, 777, 1024, 1500, 2048, 2049, 2561, 3000, 3585, 4096])
+@pytest.mark.parametrize("M", [257, 300, 320, 321, 350, 384, 385, 448, 449, 512, 513, 576, 577, 672, 673, 777, 1024, 1500, 2048, 2049, 2561, 3000, 3585, 4096])
 def test_multi_warp_profiles(pkg, o32, M):
     """Profiles above 256 nodes: several warps per pair, carries exchanged through shared memory."""
     db, twins = make_db(pkg, o32, [(M, M, 2), (M + 1, 40, 2)], 0.01)
