@@ -28,7 +28,10 @@ constexpr int kWarpsPerBlock = 8; /* k_score block = 8 independent warps */
  * up to 4 nodes per lane the state fits 168 registers (three per scheduler), up to 2 it fits 128 (four).
  * Measured: M = 128: 550 vs 463 GCUPS, M = 64: 345 vs 269 with 12 instead of 8 warps. */
 constexpr int score_warps(int Q) { return Q <= 2 ? 16 : Q <= 4 ? 12 : kWarpsPerBlock; } /* Q = 5 at 12 warps: no gain */
-constexpr int kSeqChunk = 4;      /* sequences per work item */
+#ifndef DCP_SEQ_CHUNK
+#define DCP_SEQ_CHUNK 4
+#endif
+constexpr int kSeqChunk = DCP_SEQ_CHUNK; /* sequences per work item */
 
 #define CU_TRY(expr)                                                                           \
     do                                                                                         \
