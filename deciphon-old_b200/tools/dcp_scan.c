@@ -201,6 +201,14 @@ int main(int argc, char **argv)
         return 1;
     }
     dcpgpu_prod_fwrite_header(stdout);
+    /* a batch holds two floats and a flag per (sequence, profile) pair on both sides of the bus: keep it under
+     * 2^30 pairs (9 GB) whatever --batch says */
+    {
+        unsigned long long np = dcpgpu_db_nprofiles(db);
+        unsigned long long cap = (1ull << 30) / (np ? np : 1);
+        if (cap < 256) cap = 256;
+        if (batch > cap) batch = (unsigned)cap;
+    }
     int64_t next_id = 1;
     int pending = 0, more = 1;
     uint64_t total_hits = 0, total_seqs = 0;
