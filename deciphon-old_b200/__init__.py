@@ -36,7 +36,7 @@ EXPORTS = [
     "dcpgpu_db_del", "dcpgpu_seqs_new", "dcpgpu_seqs_del", "dcpgpu_scan_resident", "dcpgpu_scan",
     "dcpgpu_result_nseqs", "dcpgpu_result_nprofiles", "dcpgpu_result_null_loglik", "dcpgpu_result_alt_loglik",
     "dcpgpu_result_hit", "dcpgpu_result_nhits", "dcpgpu_result_hit_at", "dcpgpu_result_timing",
-    "dcpgpu_result_del", "dcpgpu_shard_profiles", "dcpgpu_prod_fwrite_header", "dcpgpu_prod_fwrite",
+    "dcpgpu_result_del", "dcpgpu_shard_profiles", "dcpgpu_kernel_shape", "dcpgpu_prod_fwrite_header", "dcpgpu_prod_fwrite",
     "dcpgpu_prod_row", "dcpgpu_microbench_alu", "dcpgpu_last_error",
 ]
 
@@ -135,6 +135,8 @@ def lib():
     L.dcpgpu_result_timing.argtypes = [vp, C.POINTER(Timing)]
     L.dcpgpu_result_del.argtypes = [vp]
     L.dcpgpu_shard_profiles.argtypes = [u, vp, u, vp]
+    L.dcpgpu_kernel_shape.argtypes = [u, vp, vp, vp]
+    L.dcpgpu_kernel_shape.restype = C.c_int
     L.dcpgpu_prod_row.restype = C.c_long
     L.dcpgpu_prod_row.argtypes = [vp, vp, C.c_uint64, C.c_int64, C.c_int64, C.c_char_p, C.c_char_p, C.c_long]
     L.dcpgpu_microbench_alu.argtypes = [i, vp]
@@ -197,6 +199,13 @@ def microbench_alu(device=0):
     out = np.zeros(4)
     _check(lib().dcpgpu_microbench_alu(device, out.ctypes.data))
     return {"fadd_ginst": out[0], "fmnmx3_ginst": out[1], "mix_ginst": out[2], "sms": int(out[3])}
+
+
+def kernel_shape(core_size):
+    """(warps per pair, nodes per lane, blocks per pair) the engine uses for a profile of `core_size` nodes."""
+    w, q, b = C.c_uint(), C.c_uint(), C.c_uint()
+    _check(lib().dcpgpu_kernel_shape(core_size, C.byref(w), C.byref(q), C.byref(b)))
+    return w.value, q.value, b.value
 
 
 def shard_profiles(core_sizes, nshards):

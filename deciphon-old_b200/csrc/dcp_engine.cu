@@ -1003,6 +1003,41 @@ static enum rc db_take(struct dcpgpu_db *db, struct protein_profile *prof, bool 
 #ifndef DCP_W2Q7
 #define DCP_W2Q7 1
 #endif
+/* profile length -> (nodes per lane, warps per pair, kernel class) */
+static void kernel_shape(uint32_t M, uint32_t &Q, uint32_t &W, uint32_t &cls)
+{
+    /* nodes per lane.  193..224 nodes would fit 7 per lane, but k_score<7> does not fit the
+     * register file without spilling in its straight-line form; 8 per lane (7 idle lanes) measured
+     * faster: 515 vs 489 GCUPS at M = 200.  Above 256 nodes W warps share one pair, 8 nodes per lane. */
+    Q = (M + 31) / 32, W = 1;
+    if (Q == 7) Q = 8;
+    cls = Q;
+    if (Q > 8)
+    {
+        Q = 8, W = (M + 255) / 256;
+        if (W > kMaxW) W = (W + 1) / 2 * 2; /* two blocks of W/2 warps (cluster) */
+        cls = kMaxQ + W;
+        /* two / three warps with 6 or 7 nodes per lane instead of 8: fewer padded nodes for 257..448 and 513..672
+         * (M = 350: 357 -> 418 GCUPS; 5 nodes per lane for 257..320 gains only 2 %, 6 per lane is better there too) */
+        if (M <= 384) Q = 6, cls = kClsW2Q6;
+        else if (DCP_W2Q7 && M <= 448) Q = 7, cls = kClsW2Q7;
+        else if (M > 512 && M <= 576) Q = 6, cls = kClsW3Q6;
+        else if (M > 576 && M <= 672) Q = 7, cls = kClsW3Q7;
+    }
+}
+
+extern "C" enum rc dcpgpu_kernel_shape(unsigned core_size, unsigned *warps, unsigned *nodes_per_lane, unsigned *blocks)
+{
+    if (core_size == 0 || core_size > DCP_PROTEIN_MODEL_CORE_SIZE_MAX)
+        return dcp_error(RC_EINVAL, "core size out of range");
+    uint32_t Q, W, cls;
+    kernel_shape(core_size, Q, W, cls);
+    if (warps) *warps = W;
+    if (nodes_per_lane) *nodes_per_lane = Q;
+    if (blocks) *blocks = W > (uint32_t)kMaxW ? 2 : 1;
+    return RC_OK;
+}
+
 extern "C" enum rc dcpgpu_db_commit(struct dcpgpu_db *db)
 {
     if (db->committed) return dcp_error(RC_EFAIL, "database already committed");
@@ -1014,24 +1049,8 @@ extern "C" enum rc dcpgpu_db_commit(struct dcpgpu_db *db)
     for (size_t i = 0; i < nprof; ++i)
     {
         uint32_t M = db->profs[i]->core_size;
-        /* nodes per lane.  193..224 nodes would fit 7 per lane, but k_score<7> does not fit the
-         * register file without spilling in its straight-line form; 8 per lane (7 idle lanes) measured
-         * faster: 515 vs 489 GCUPS at M = 200.  Above 256 nodes W warps share one pair, 8 nodes per lane. */
-        uint32_t Q = (M + 31) / 32, W = 1;
-        if (Q == 7) Q = 8;
-        uint32_t cls = Q;
-        if (Q > 8)
-        {
-            Q = 8, W = (M + 255) / 256;
-            if (W > kMaxW) W = (W + 1) / 2 * 2; /* two blocks of W/2 warps (cluster) */
-            cls = kMaxQ + W;
-            /* two warps with 6 or 7 nodes per lane instead of 8: fewer padded nodes for 257..448 (M = 350:
-             * 357 -> 418 GCUPS; 5 nodes per lane for 257..320 gains only 2 %, 6 per lane is better there too) */
-            if (M <= 384) Q = 6, cls = kClsW2Q6;
-            else if (DCP_W2Q7 && M <= 448) Q = 7, cls = kClsW2Q7;
-            else if (M > 512 && M <= 576) Q = 6, cls = kClsW3Q6;
-            else if (M > 576 && M <= 672) Q = 7, cls = kClsW3Q7;
-        }
+        uint32_t Q, W, cls;
+        kernel_shape(M, Q, W, cls);
         uint32_t QP = Q <= 4 ? 4 : 8;
         ProfMeta &m = db->metas[i];
         m.M = M, m.Q = Q, m.QP = QP, m.null_id = db->null_id[i];

@@ -276,6 +276,11 @@ void dcpgpu_result_del(struct dcpgpu_result *);
 enum rc dcpgpu_shard_profiles(unsigned nprofiles, unsigned const *core_sizes, unsigned nshards,
                               unsigned *shard_of);
 
+/* How the engine maps a profile of `core_size` nodes (1..4096, limits.h:11) onto the GPU: `warps` per
+ * (sequence, profile) pair, `nodes_per_lane`, and 1 or 2 thread blocks (a cluster) per pair; warps * 32 *
+ * nodes_per_lane >= core_size is the padded width the kernels compute.  Pure function (no device needed). */
+enum rc dcpgpu_kernel_shape(unsigned core_size, unsigned *warps, unsigned *nodes_per_lane, unsigned *blocks);
+
 /* ------------------------------------------------------------------------- */
 /* Part 3 -- products.  src/server/prod.c:13-41,106-181, protein_match.c:21-56 */
 /* ------------------------------------------------------------------------- */

@@ -137,6 +137,29 @@ def test_shard_profiles(pkg):
         pkg.shard_profiles(sizes, 0)
 
 
+def test_kernel_shape_covers_every_core_size(pkg):
+    """Profile length -> (warps, nodes per lane, blocks): the padded width always holds the profile, one warp up
+    to 256 nodes, one block up to 2048, a 2-block cluster up to 4096 (limits.h:11), never more than 50 % padding
+    above 96 nodes."""
+    for M in range(1, 4097):
+        w, q, b = pkg.kernel_shape(M)
+        assert 1 <= q <= 8 and 1 <= w <= 16 and b in (1, 2)
+        assert w * 32 * q >= M, (M, w, q)
+        assert (w == 1) == (M <= 256)
+        assert (b == 2) == (M > 2048)
+        if b == 2:
+            assert w % 2 == 0 and w // 2 <= 8
+        if M > 96:
+            assert w * 32 * q <= 1.5 * M, (M, w, q)
+    assert pkg.kernel_shape(200) == (1, 8, 1)       # 7 per lane spills: 8 per lane (DESIGN.md 6)
+    assert pkg.kernel_shape(300) == (2, 6, 1) and pkg.kernel_shape(448) == (2, 7, 1)
+    assert pkg.kernel_shape(512) == (2, 8, 1) and pkg.kernel_shape(600) == (3, 7, 1)
+    assert pkg.kernel_shape(3000) == (12, 8, 2)
+    for bad in (0, 4097):
+        with pytest.raises(pkg.DcpError):
+            pkg.kernel_shape(bad)
+
+
 def test_no_cpu_fallback(pkg):
     """Without a CUDA device the engine refuses to exist (there is no CPU path to fall back to)."""
     import torch
