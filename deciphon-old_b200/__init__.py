@@ -35,8 +35,12 @@ EXPORTS = [
     "dcpgpu_db_new", "dcpgpu_db_add", "dcpgpu_db_commit", "dcpgpu_db_nprofiles", "dcpgpu_db_device_bytes",
     "dcpgpu_db_del", "dcpgpu_seqs_new", "dcpgpu_seqs_del", "dcpgpu_scan_resident", "dcpgpu_scan",
     "dcpgpu_result_nseqs", "dcpgpu_result_nprofiles", "dcpgpu_result_null_loglik", "dcpgpu_result_alt_loglik",
-    "dcpgpu_result_hit", "dcpgpu_result_nhits", "dcpgpu_result_hit_at", "dcpgpu_result_timing",
-    "dcpgpu_result_del", "dcpgpu_shard_profiles", "dcpgpu_kernel_shape", "dcpgpu_prod_fwrite_header", "dcpgpu_prod_fwrite",
+    "dcpgpu_result_hit", "dcpgpu_result_nhits", "dcpgpu_result_hit_at", "dcpgpu_result_hits", "dcpgpu_result_steps",
+    "dcpgpu_result_timing",
+    "dcpgpu_result_del", "dcpgpu_shard_profiles", "dcpgpu_kernel_shape", "dcpgpu_profile_cost", "dcpgpu_shard_sequences",
+    "dcpgpu_mdb_new", "dcpgpu_mdb_add", "dcpgpu_mdb_commit", "dcpgpu_mdb_view", "dcpgpu_mdb_ndevices",
+    "dcpgpu_mdb_nprofiles", "dcpgpu_mdb_axis", "dcpgpu_mdb_imbalance", "dcpgpu_mdb_device_of", "dcpgpu_mdb_device_bytes",
+    "dcpgpu_mdb_scan", "dcpgpu_mdb_del", "dcpgpu_result_nparts", "dcpgpu_result_part_timing", "dcpgpu_prod_fwrite_header", "dcpgpu_prod_fwrite",
     "dcpgpu_prod_row", "dcpgpu_microbench_alu", "dcpgpu_last_error",
 ]
 
@@ -55,9 +59,12 @@ class _Trans(C.Structure):
     _fields_ = [("data", C.c_float * 7)]
 
 
+PROGRESS_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_uint64)
+
+
 class _Params(C.Structure):
     _fields_ = [("multi_hits", C.c_bool), ("hmmer3_compat", C.c_bool), ("lrt_threshold", C.c_double),
-                ("want_paths", C.c_bool)]
+                ("want_paths", C.c_bool), ("progress", PROGRESS_FN), ("user", C.c_void_p)]
 
 
 class _Step(C.Structure):
@@ -132,11 +139,35 @@ def lib():
     L.dcpgpu_result_nhits.argtypes = [vp]
     L.dcpgpu_result_hit_at.argtypes = [vp, C.c_uint64, C.POINTER(u), C.POINTER(u), C.POINTER(C.POINTER(_Step)),
                                        C.POINTER(u)]
+    L.dcpgpu_result_hits.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.dcpgpu_result_steps.restype = C.c_uint64
+    L.dcpgpu_result_steps.argtypes = [vp, C.POINTER(C.POINTER(_Step))]
     L.dcpgpu_result_timing.argtypes = [vp, C.POINTER(Timing)]
     L.dcpgpu_result_del.argtypes = [vp]
     L.dcpgpu_shard_profiles.argtypes = [u, vp, u, vp]
     L.dcpgpu_kernel_shape.argtypes = [u, vp, vp, vp]
     L.dcpgpu_kernel_shape.restype = C.c_int
+    L.dcpgpu_profile_cost.argtypes = [u]
+    L.dcpgpu_profile_cost.restype = C.c_double
+    L.dcpgpu_shard_sequences.argtypes = [u, vp, u, vp]
+    L.dcpgpu_mdb_new.argtypes = [C.POINTER(vp), u, vp]
+    L.dcpgpu_mdb_add.argtypes = [vp, vp]
+    L.dcpgpu_mdb_commit.argtypes = [vp, i]
+    L.dcpgpu_mdb_view.restype = vp
+    L.dcpgpu_mdb_view.argtypes = [vp]
+    L.dcpgpu_mdb_ndevices.argtypes = [vp]
+    L.dcpgpu_mdb_nprofiles.argtypes = [vp]
+    L.dcpgpu_mdb_axis.argtypes = [vp]
+    L.dcpgpu_mdb_imbalance.restype = C.c_double
+    L.dcpgpu_mdb_imbalance.argtypes = [vp]
+    L.dcpgpu_mdb_device_of.argtypes = [vp, u]
+    L.dcpgpu_mdb_device_of.restype = i
+    L.dcpgpu_mdb_device_bytes.restype = C.c_uint64
+    L.dcpgpu_mdb_device_bytes.argtypes = [vp, u]
+    L.dcpgpu_mdb_scan.argtypes = [vp, u, vp, vp, C.POINTER(_Params), C.POINTER(vp)]
+    L.dcpgpu_mdb_del.argtypes = [vp]
+    L.dcpgpu_result_nparts.argtypes = [vp]
+    L.dcpgpu_result_part_timing.argtypes = [vp, u, C.POINTER(i), C.POINTER(Timing)]
     L.dcpgpu_prod_row.restype = C.c_long
     L.dcpgpu_prod_row.argtypes = [vp, vp, C.c_uint64, C.c_int64, C.c_int64, C.c_char_p, C.c_char_p, C.c_long]
     L.dcpgpu_microbench_alu.argtypes = [i, vp]
@@ -209,9 +240,23 @@ def kernel_shape(core_size):
 
 
 def shard_profiles(core_sizes, nshards):
+    """Device index of every profile: longest-processing-time partition by modelled cost."""
     cs = np.ascontiguousarray(core_sizes, np.uint32)
     out = np.zeros(len(cs), np.uint32)
     _check(lib().dcpgpu_shard_profiles(len(cs), cs.ctypes.data, nshards, out.ctypes.data))
+    return out
+
+
+def profile_cost(core_size):
+    """Modelled score-pass time of one sequence row against a profile of `core_size` nodes (ns on one B200)."""
+    return float(lib().dcpgpu_profile_cost(int(core_size)))
+
+
+def shard_sequences(lens, nshards):
+    """nshards + 1 bounds of contiguous sequence ranges with about equal nucleotide totals."""
+    ln = np.ascontiguousarray(lens, np.uint32)
+    out = np.zeros(nshards + 1, np.uint32)
+    _check(lib().dcpgpu_shard_sequences(len(ln), ln.ctypes.data, nshards, out.ctypes.data))
     return out
 
 
@@ -441,6 +486,29 @@ class Result:
         path = [(steps[k].state_id, steps[k].seqlen) for k in range(n.value)] if steps else []
         return si.value, pi.value, path
 
+    def hits(self):
+        """The hit list as arrays: (seq u32, prof u32, alt f32, null f32, nsteps u32), in (sequence, profile) order."""
+        n = self.nhits
+        seq, prof, ns = np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+        alt, null = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        _check(lib().dcpgpu_result_hits(self.h, seq.ctypes.data, prof.ctypes.data, alt.ctypes.data, null.ctypes.data,
+                                        ns.ctypes.data))
+        return seq, prof, alt, null, ns
+
+    def steps(self):
+        """All paths back to back as an (nsteps_total, 2) uint16 array of (state_id, seqlen)."""
+        ptr = C.POINTER(_Step)()
+        n = int(lib().dcpgpu_result_steps(self.h, C.byref(ptr)))
+        if n == 0:
+            return np.zeros((0, 2), np.uint16)
+        raw = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint16)), shape=(n, 2)).copy()
+        raw[:, 1] &= 0xFF  # seqlen is one byte; the other is struct padding
+        return raw
+
+    def hit_scores(self, i):
+        s = self.hits()
+        return float(s[2][i]), float(s[3][i])
+
     def product_row(self, i, scan_id=0, seq_id=None):
         si, _, path = self.hit_at(i)
         cap = 64 * (len(path) + 8) + 512
@@ -456,6 +524,16 @@ class Result:
         t = Timing()
         lib().dcpgpu_result_timing(self.h, C.byref(t))
         return t
+
+    @property
+    def part_timings(self):
+        """[(device, Timing)] of the launch sets a merged (tiled or multi-device) result was built from."""
+        out = []
+        for k in range(lib().dcpgpu_result_nparts(self.h)):
+            t, dev = Timing(), C.c_int()
+            _check(lib().dcpgpu_result_part_timing(self.h, k, C.byref(dev), C.byref(t)))
+            out.append((dev.value, t))
+        return out
 
 
 class Db:
@@ -499,8 +577,9 @@ class Db:
     device_bytes = property(lambda s: int(lib().dcpgpu_db_device_bytes(s.h)))
 
     @staticmethod
-    def _params(multi_hits, hmmer3_compat, lrt_threshold, want_paths):
-        return _Params(multi_hits, hmmer3_compat, float(lrt_threshold), want_paths)
+    def _params(multi_hits, hmmer3_compat, lrt_threshold, want_paths, progress=None):
+        cb = PROGRESS_FN(lambda user, pairs: progress(int(pairs))) if progress else PROGRESS_FN()
+        return _Params(multi_hits, hmmer3_compat, float(lrt_threshold), want_paths, cb, None)
 
     def stage(self, seqs):
         return Seqs(self, seqs)
@@ -511,10 +590,60 @@ class Db:
         _check(lib().dcpgpu_scan_resident(self.h, staged.h, C.byref(prm), C.byref(out)))
         return Result(self, out, staged.bytes)
 
-    def scan(self, seqs, multi_hits=True, hmmer3_compat=False, lrt_threshold=10.0, want_paths=True):
+    def scan(self, seqs, multi_hits=True, hmmer3_compat=False, lrt_threshold=10.0, want_paths=True, progress=None):
         """thread_run's loop for every (sequence, profile) pair, from host buffers."""
         bs, arr, lens = _seq_arrays(seqs)
-        prm = self._params(multi_hits, hmmer3_compat, lrt_threshold, want_paths)
+        prm = self._params(multi_hits, hmmer3_compat, lrt_threshold, want_paths, progress)
         out = C.c_void_p()
         _check(lib().dcpgpu_scan(self.h, len(bs), arr, lens.ctypes.data, C.byref(prm), C.byref(out)))
         return Result(self, out, bs)
+
+
+AXIS_AUTO, AXIS_PROFILES, AXIS_SEQUENCES = range(3)
+
+
+class _View:
+    """dcpgpu_mdb_view: the global profile list (what product rows are written against)."""
+
+    def __init__(self, h):
+        self.h = h
+
+
+class Mdb:
+    """A database over several GPUs of one box (replaces scan_run's omp partitions, scan.c:239-250)."""
+
+    def __init__(self, devices):
+        dv = np.ascontiguousarray(devices, np.int32)
+        self.h = C.c_void_p()
+        _check(lib().dcpgpu_mdb_new(C.byref(self.h), len(dv), dv.ctypes.data))
+        self.view = _View(lib().dcpgpu_mdb_view(self.h))
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().dcpgpu_mdb_del(self.h)
+        except Exception:
+            pass
+
+    def add(self, prof):
+        _check(lib().dcpgpu_mdb_add(self.h, prof.h))
+
+    def commit(self, axis=AXIS_AUTO):
+        _check(lib().dcpgpu_mdb_commit(self.h, axis))
+
+    ndevices = property(lambda s: lib().dcpgpu_mdb_ndevices(s.h))
+    nprofiles = property(lambda s: lib().dcpgpu_mdb_nprofiles(s.h))
+    axis = property(lambda s: lib().dcpgpu_mdb_axis(s.h))
+    imbalance = property(lambda s: lib().dcpgpu_mdb_imbalance(s.h))
+
+    def device_of(self, profile):
+        return lib().dcpgpu_mdb_device_of(self.h, profile)
+
+    def scan(self, seqs, multi_hits=True, hmmer3_compat=False, lrt_threshold=10.0, want_paths=True, progress=None):
+        bs, arr, lens = _seq_arrays(seqs)
+        prm = Db._params(multi_hits, hmmer3_compat, lrt_threshold, want_paths, progress)
+        out = C.c_void_p()
+        _check(lib().dcpgpu_mdb_scan(self.h, len(bs), arr, lens.ctypes.data, C.byref(prm), C.byref(out)))
+        r = Result(self.view, out, bs)
+        r._keep = self  # the merged result refers to the mdb's shard maps
+        return r

@@ -14,15 +14,10 @@
 #define FULL 0xffffffffu
 
 constexpr int kTab = DCP_FRAME_TABLE_SIZE;
-constexpr int kMaxQ = 8;          /* nodes per lane, single-warp classes cover M <= 256 */
-constexpr int kMaxW = 8;          /* warps per block in the multi-warp classes: M <= 8 * 256 = 2048 per block */
-constexpr int kMaxGroupWarps = 16; /* two blocks (a cluster) per pair above 2048 nodes: M <= 4096 */
-constexpr int kClsW2Q6 = kMaxQ + kMaxGroupWarps + 1; /* 257..384 nodes: two warps, 6 nodes per lane */
-constexpr int kClsW2Q7 = kMaxQ + kMaxGroupWarps + 2; /* 385..448 nodes: two warps, 7 nodes per lane */
-constexpr int kClsW3Q6 = kMaxQ + kMaxGroupWarps + 3; /* 513..576 nodes: three warps, 6 nodes per lane */
-constexpr int kClsW3Q7 = kMaxQ + kMaxGroupWarps + 4; /* 577..672 nodes: three warps, 7 nodes per lane */
-constexpr int kNumClasses = kClsW3Q7; /* class c: 1..8 = one warp, Q = c; 8 + TW = TW warps per pair, Q = 8
-                                       * (TW = 2..8 one block; 10, 12, 14, 16 two blocks); then the two above */
+constexpr int kMaxQ = DCP_MAX_Q;          /* nodes per lane, single-warp classes cover M <= 256 */
+constexpr int kMaxW = DCP_MAX_W;          /* warps per block in the multi-warp classes: M <= 8 * 256 = 2048 per block */
+constexpr int kMaxGroupWarps = DCP_MAX_GROUP_WARPS; /* two blocks (a cluster) per pair above 2048 nodes: M <= 4096 */
+constexpr int kMaxClasses = DCP_MAX_CLASSES; /* rows of the kernel class table (dcp_classes.h) */
 constexpr int kWarpsPerBlock = 8; /* k_score block = 8 independent warps */
 /* independent warps per SM in k_score<Q>: 8 nodes per lane need 254 registers (two warps per scheduler);
  * up to 4 nodes per lane the state fits 168 registers (three per scheduler), up to 2 it fits 128 (four).
@@ -63,7 +58,7 @@ static_assert(sizeof(RowRec) == 64, "row record is one 64-byte line");
 struct ProfMeta
 {
     uint32_t M, Q, QP, null_id;
-    uint32_t W, cls; /* warps per pair; kernel class */
+    uint32_t W, cls; /* warps per pair; kernel class (row of the class table) */
     uint64_t emis_off;  /* floats into d_emis */
     uint64_t trans_off; /* floats into d_trans */
 };
@@ -79,19 +74,22 @@ struct SeqMeta
 
 struct dcpgpu_db
 {
-    int device = 0;
+    int device = 0; /* -1: host-only view (the global profile list of a multi-device database) */
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    cudaMemPool_t pool = nullptr; /* the engine's own stream-ordered pool (scratch of scans, results) */
     bool committed = false;
+    bool owns_profs = true;        /* false: shard of a dcpgpu_mdb, profiles belong to its view */
+    bool keep_host_tables = false; /* shard of a replicated database: the owner frees the host tables */
     float epsilon = -1.0f;
     std::vector<protein_profile *> profs; /* deep copies, host side (decode, products) */
     std::vector<std::vector<float>> null_tabs;
     std::vector<uint32_t> null_id;
     std::vector<ProfMeta> metas;
-    std::vector<uint32_t> class_list[kNumClasses + 1]; /* profile ids by kernel class */
+    std::vector<uint32_t> class_list[kMaxClasses]; /* profile ids by kernel class */
     float *d_emis = nullptr, *d_trans = nullptr, *d_null_tabs = nullptr, *d_ins_tab = nullptr;
     ProfMeta *d_metas = nullptr;
-    uint32_t *d_class[kNumClasses + 1] = {nullptr};
+    uint32_t *d_class[kMaxClasses] = {nullptr};
     uint64_t device_bytes = 0;
     void *h_stage = nullptr; /* pinned staging for sequence uploads (grow-only) */
     size_t h_stage_cap = 0;
@@ -118,6 +116,12 @@ struct HitRec
 struct dcpgpu_result
 {
     dcpgpu_db *db = nullptr;
+    /* merged result of a multi-device scan: the per-device results it was built from (owned) and, for each,
+     * the global profile index of its local profiles / the first global sequence index */
+    std::vector<dcpgpu_result *> parts;
+    std::vector<const std::vector<uint32_t> *> part_profs;
+    std::vector<uint32_t> part_seq0;
+    std::vector<int> part_device;
     uint32_t nseq = 0, nprof = 0, n_null = 0;
     float *d_alt = nullptr, *d_null = nullptr;
     uint8_t *d_hit = nullptr;
@@ -132,17 +136,17 @@ struct dcpgpu_result
 };
 
 
-/* Scratch device buffer of one scan: stream-ordered allocation from the device's default memory
- * pool (release threshold raised at dcpgpu_db_new, so repeated scans reuse the same blocks and
- * never pay cudaMalloc/cudaFree). */
+/* Scratch device buffer of one scan: stream-ordered allocation from the database's own memory pool
+ * (created at dcpgpu_db_new with its release threshold raised, so repeated scans reuse the same blocks
+ * and never pay cudaMalloc/cudaFree; the device's default pool, which torch and others share, is left alone). */
 struct DevBuf
 {
     void *p = nullptr;
     cudaStream_t st = nullptr;
-    cudaError_t alloc(size_t bytes, cudaStream_t stream)
+    cudaError_t alloc(size_t bytes, dcpgpu_db *db)
     {
-        st = stream;
-        return cudaMallocAsync(&p, bytes ? bytes : 1, stream);
+        st = db->stream;
+        return cudaMallocFromPoolAsync(&p, bytes ? bytes : 1, db->pool, st);
     }
     ~DevBuf()
     {
@@ -152,10 +156,34 @@ struct DevBuf
     T *as() { return (T *)p; }
 };
 
+/* arguments of a score-pass launch for one kernel class (dcp_score_sw.cu, dcp_score_mw.cu) */
+struct ScoreArgs
+{
+    const float *emis, *trans;
+    const ProfMeta *metas;
+    const uint32_t *class_profs; /* profile ids of the class */
+    uint32_t n_class;
+    const SeqMeta *seqs;
+    uint32_t nseq;
+    uint64_t total_recs;
+    const RowRec *rows;
+    const uint16_t *wcodes;
+    const float *spec;
+    float *alt;
+    uint32_t nprof;
+    unsigned long long *counter; /* work queue cursor of this launch (zeroed) */
+    uint32_t seq_tile;           /* sequences per L2 tile */
+};
+cudaError_t dcp_launch_score(const dcp_class &c, int sm_count, cudaStream_t st, const ScoreArgs &a);    /* tw = 1 */
+cudaError_t dcp_launch_score_mw(const dcp_class &c, int sm_count, cudaStream_t st, const ScoreArgs &a); /* tw > 1 */
+
 /* dcp_trace.cu */
 enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const RowRec *d_rows,
                        const uint16_t *d_wcodes, const float *d_spec, uint64_t *launches);
 const protein_profile *dcp_db_profile(struct dcpgpu_db const *db, unsigned i);
 enum rc dcp_db_adopt(struct dcpgpu_db *db, struct protein_profile *prof); /* takes ownership, no copy */
+enum rc dcp_db_borrow(struct dcpgpu_db *db, struct protein_profile *prof); /* no copy, no ownership (mdb shards) */
+struct dcpgpu_db *dcp_db_new_host(void); /* device = -1: profile list only */
+enum rc dcp_result_fetch(dcpgpu_result *r);
 
 #endif

@@ -55,6 +55,30 @@ void dcp_specials(unsigned seq_size, bool multi_hits, bool hmmer3_compat, float 
 int dcp_nuclt_index(char c);
 char dcp_gc_decode(int a, int b, int c);
 
+/*
+ * How the engine maps a profile onto the GPU (dcp_shape.c, dcp_classes.h): a kernel class is a row of the
+ * class table -- warps per (sequence, profile) pair, nodes per lane, resident blocks per SM, measured rate.
+ */
+enum
+{
+    DCP_MAX_Q = 8,            /* nodes per lane; one warp holds M <= 256 */
+    DCP_MAX_W = 8,            /* warps per block in the multi-warp classes: M <= 2048 per block */
+    DCP_MAX_GROUP_WARPS = 16, /* two blocks (a cluster) per pair above 2048 nodes: M <= 4096 */
+    DCP_MAX_CLASSES = 64,
+};
+struct dcp_class
+{
+    unsigned tw, q, bps;
+    double rate;
+};
+unsigned dcp_num_classes(void);
+struct dcp_class const *dcp_class_at(unsigned cls);
+/* the class a profile of `core_size` nodes runs in (index into the table) */
+unsigned dcp_kernel_class(unsigned core_size);
+/* modelled score-pass time of one sequence row against a profile of `core_size` nodes, in ns of one whole
+ * B200 (padded nodes / measured padded-node rate of the profile's kernel class); the shard weights */
+double dcp_profile_cost(unsigned core_size);
+
 /* error reporting: message kept per thread, code returned (logging.h:32-72 convention) */
 void dcp_set_error(char const *msg);
 enum rc dcp_error(enum rc rc, char const *msg);

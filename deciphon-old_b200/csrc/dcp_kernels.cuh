@@ -76,6 +76,9 @@ __device__ __forceinline__ void load_row_special(const RowRec *__restrict__ r, f
 #ifndef DCP_POLICY
 #define DCP_POLICY 0
 #endif
+#ifndef DCP_Q7_LOAD8
+#define DCP_Q7_LOAD8 0
+#endif
 /* L1 policy experiments for the emission lines, by window length l (0..4 = 1..5 nt):
  * 0 default everywhere; 1: 5-nt lines no_allocate; 2: 4- and 5-nt lines no_allocate;
  * 3: 1..3-nt lines evict_last, 5-nt no_allocate; 4: 1..3 evict_last, 4..5 no_allocate */
@@ -125,9 +128,15 @@ __device__ __forceinline__ void load_emis_part(float (&em)[5][Q], const float *_
         }
         else if (Q == 7)
         {
+#if DCP_Q7_LOAD8
+            /* one 16-byte load (the lane's fourth float is padding) instead of an 8- and a 4-byte one */
+            float4 b = ldg4(src + 128, l);
+            em[l][4 % Q] = b.x, em[l][5 % Q] = b.y, em[l][6 % Q] = b.z;
+#else
             float2 b = __ldg(reinterpret_cast<const float2 *>(src + 128));
             float c = __ldg(src + 130);
             em[l][4 % Q] = b.x, em[l][5 % Q] = b.y, em[l][6 % Q] = c;
+#endif
         }
         else if (Q == 6)
         {

@@ -658,39 +658,3 @@ enum rc protein_profile_nuclt_dist(struct protein_profile const *p, int which, d
     memcpy(out + 4, nd->codonm, sizeof nd->codonm);
     return RC_OK;
 }
-
-/* LPT greedy partition by core size; replaces the equal-count split of profile_reader.c:54-72 */
-enum rc dcpgpu_shard_profiles(unsigned nprofiles, unsigned const *core_sizes, unsigned nshards, unsigned *shard_of)
-{
-    if (nshards == 0) return dcp_error(RC_EINVAL, "nshards must be positive");
-    unsigned *order = malloc((nprofiles ? nprofiles : 1) * sizeof *order);
-    uint64_t *load = calloc(nshards, sizeof *load);
-    if (!order || !load)
-    {
-        free(order), free(load);
-        return dcp_error(RC_ENOMEM, "alloc shard tables");
-    }
-    /* counting sort by descending core size (sizes are <= 4096), stable in profile order */
-    unsigned *head = calloc(DCP_PROTEIN_MODEL_CORE_SIZE_MAX + 2, sizeof *head);
-    for (unsigned i = 0; i < nprofiles; ++i)
-    {
-        unsigned m = core_sizes[i] > DCP_PROTEIN_MODEL_CORE_SIZE_MAX ? DCP_PROTEIN_MODEL_CORE_SIZE_MAX : core_sizes[i];
-        head[DCP_PROTEIN_MODEL_CORE_SIZE_MAX - m + 1]++;
-    }
-    for (unsigned i = 1; i <= DCP_PROTEIN_MODEL_CORE_SIZE_MAX + 1; ++i) head[i] += head[i - 1];
-    for (unsigned i = 0; i < nprofiles; ++i)
-    {
-        unsigned m = core_sizes[i] > DCP_PROTEIN_MODEL_CORE_SIZE_MAX ? DCP_PROTEIN_MODEL_CORE_SIZE_MAX : core_sizes[i];
-        order[head[DCP_PROTEIN_MODEL_CORE_SIZE_MAX - m]++] = i;
-    }
-    for (unsigned r = 0; r < nprofiles; ++r)
-    {
-        unsigned best = 0;
-        for (unsigned s = 1; s < nshards; ++s)
-            if (load[s] < load[best]) best = s;
-        shard_of[order[r]] = best;
-        load[best] += core_sizes[order[r]];
-    }
-    free(head), free(order), free(load);
-    return RC_OK;
-}

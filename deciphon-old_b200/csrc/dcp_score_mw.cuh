@@ -1,0 +1,329 @@
+/*
+ * dcp_score_mw.cuh -- alt Viterbi score pass for profiles of 257..4096 nodes: a group of warps (one block, or
+ * the two blocks of a cluster) per (sequence, profile) pair.
+ */
+#ifndef DCP_SCORE_MW_CUH
+#define DCP_SCORE_MW_CUH
+#include "dcp_score.cuh"
+
+namespace
+{
+/* ----------------------------------------------------------------------------------------- */
+/* alt Viterbi, score pass, profiles of 257..4096 nodes: a group of warps per pair            */
+/* ----------------------------------------------------------------------------------------- */
+/*
+ * Same recurrence, same fp32 operation order and the same lane layout as k_score<8>; node
+ * k-1 = gwarp * 256 + lane * 8 + sub.  257..2048 nodes: W warps of one block (CL = 1);
+ * 2049..4096 nodes: W warps in each block of a 2-block cluster (CL = 2, 255 registers x 16 warps do
+ * not fit one SM), exchanging through distributed shared memory.  What a single warp exchanges with
+ * shuffles is exchanged between warps through shared memory, two group barriers per row:
+ *   A   V_M / V_I / D of each warp's last node (D from the warp-local chain), per-warp max of V_M (-> E),
+ *       V_N / V_J / V_C of warp 0
+ *   C   group-wide OR: did any warp's last D rise when the left neighbour's values came in?
+ *       (if so publish the new D, barrier B, and repeat -- exact lazy propagation, as inside a warp)
+ * Measured alternatives that were not faster: keeping 8 warps per SM with 5 or 6 nodes per lane
+ * (M = 600: 252 vs 267 GCUPS) -- the barriers, not the occupancy, bound these kernels.
+ */
+struct MwShared
+{
+    float vm_last[2][kMaxGroupWarps], vi_last[2][kMaxGroupWarps], e_warp[2][kMaxGroupWarps];
+    float d_last[2][kMaxGroupWarps];
+    float v_spec[2][4]; /* V_N, V_J, V_C of the row */
+    int flag[2][2];
+    unsigned long long item;
+    alignas(16) float xch[2][kMaxGroupWarps][8]; /* 2-block groups: Group::exchange buffers ... */
+    unsigned long long xbar[2];                  /* ... and their mbarriers */
+};
+
+template <int W, int CL, int R, int Q>
+__device__ __forceinline__ void mw_row(float (&tm)[5][Q], float (&ti)[5][Q], float (&tx)[5],
+                                       const NodeParams<Q> &p, RowState<Q> &rs,
+                                       const float *__restrict__ emis_lane, const RowRec *__restrict__ rec_next,
+                                       const uint16_t *__restrict__ w_next2, int gw, int lane, int par,
+                                       Group<CL, MwShared> &grp, float NB, float JB, float EB, float cE, float cX,
+                                       float &E_out, float &vC_out)
+{
+    constexpr int TW = W * CL;
+    constexpr int ROW = 256 * TW;
+    constexpr int S1 = (R + 4) % 5, S2 = (R + 3) % 5, S3 = (R + 2) % 5, S4 = (R + 1) % 5, S5 = R;
+    MwShared &sh = *grp.me;
+
+    float vm[Q], vi[Q];
+#pragma unroll
+    for (int i = 0; i < Q; ++i)
+        vm[i] = fmaxf(max3(tm[S1][i] + rs.em[0][i], tm[S2][i] + rs.em[1][i], tm[S3][i] + rs.em[2][i]),
+                      fmaxf(tm[S4][i] + rs.em[3][i], tm[S5][i] + rs.em[4][i]));
+#pragma unroll
+    for (int i = 0; i < Q; ++i)
+        vi[i] = fmaxf(max3(ti[S1][i] + rs.eI[0], ti[S2][i] + rs.eI[1], ti[S3][i] + rs.eI[2]),
+                      fmaxf(ti[S4][i] + rs.eI[3], ti[S5][i] + rs.eI[4]));
+    /* N, J, C live in lanes 0..2 of the group's first warp */
+    float vx = fmaxf(max3(tx[S1] + rs.eN[0], tx[S2] + rs.eN[1], tx[S3] + rs.eN[2]),
+                     fmaxf(tx[S4] + rs.eN[3], tx[S5] + rs.eN[4]));
+
+    /* next row's loads (same software pipeline as the single-warp kernel) */
+    uint32_t code[5];
+    codes_of(rs.w1, code);
+    load_emis_part<Q, 3, 5, ROW>(rs.em, emis_lane, code);
+    load_row_insert(rec_next, rs.eI);
+    if (gw == 0 && lane < 3) load_row_special(rec_next, rs.eN);
+    rs.w1 = rs.w2;
+    rs.w2 = __ldg(w_next2);
+
+    float eloc = vm[0];
+#pragma unroll
+    for (int i = 1; i < Q; ++i) eloc = fmaxf(eloc, vm[i]);
+    float ew = warp_max(eloc);
+    float vm_prev = __shfl_up_sync(FULL, vm[Q - 1], 1);
+    float vi_prev = __shfl_up_sync(FULL, vi[Q - 1], 1);
+    load_emis_part<Q, 0, 3, ROW>(rs.em, emis_lane, code);
+
+    /* D chain inside the warp, nothing from the warp to the left yet: the warp's first node starts at -inf
+     * (its M->D and D->D sources both live in the left warp and arrive together after barrier A) */
+    float d[Q];
+    d[0] = lane == 0 ? NEG_INF : vm_prev + p.MD[0];
+#pragma unroll
+    for (int i = 1; i < Q; ++i) d[i] = fmaxf(vm[i - 1] + p.MD[i], d[i - 1] + p.DD[i]);
+    float din;
+    for (;;)
+    {
+        float old = d[Q - 1];
+        din = __shfl_up_sync(FULL, old, 1);
+        float x = lane == 0 ? NEG_INF : din + p.DD[0];
+        d[0] = fmaxf(d[0], x);
+        x = d[0];
+#pragma unroll
+        for (int i = 1; i < Q; ++i)
+        {
+            x = x + p.DD[i];
+            d[i] = fmaxf(d[i], x);
+            x = d[i];
+        }
+        if (!__any_sync(FULL, d[Q - 1] > old)) break;
+    }
+#ifndef DCP_CLUSTER_XCH
+#define DCP_CLUSTER_XCH 1
+#endif
+    float E, vN, vJ, vC;
+    if constexpr (CL == 2 && DCP_CLUSTER_XCH)
+    {
+        /* A: boundary values, per-warp maxima, the local D chains' ends and the specials, one exchange */
+        const float xN = __shfl_sync(FULL, vx, 0), xJ = __shfl_sync(FULL, vx, 1), xC = __shfl_sync(FULL, vx, 2);
+        const float pay_a[8] = {vm[Q - 1], vi[Q - 1], ew, d[Q - 1], xN, xJ, xC, 0.0f};
+        int s = grp.exchange(gw, lane, pay_a);
+        {
+            const float(*x)[8] = sh.xch[s];
+            if (lane == 0)
+            {
+                vm_prev = gw ? x[gw - 1][0] : NEG_INF;
+                vi_prev = gw ? x[gw - 1][1] : NEG_INF;
+            }
+            E = x[0][2];
+#pragma unroll
+            for (int w = 1; w < TW; ++w) E = fmaxf(E, x[w][2]);
+            vN = x[0][4], vJ = x[0][5], vC = x[0][6];
+        }
+        float din0 = gw ? sh.xch[s][gw - 1][3] : NEG_INF;
+        /* carries between warps, lazily: every round ends with an exchange of (did my last D rise, my last D) */
+        for (;;)
+        {
+            const float before = __shfl_sync(FULL, d[Q - 1], 31);
+            for (;;)
+            {
+                float old = d[Q - 1];
+                din = __shfl_up_sync(FULL, old, 1);
+                if (lane == 0) din = din0;
+                float x = lane == 0 ? fmaxf(vm_prev + p.MD[0], din0 + p.DD[0]) : din + p.DD[0];
+                d[0] = fmaxf(d[0], x);
+                x = d[0];
+#pragma unroll
+                for (int i = 1; i < Q; ++i)
+                {
+                    x = x + p.DD[i];
+                    d[i] = fmaxf(d[i], x);
+                    x = d[i];
+                }
+                if (!__any_sync(FULL, d[Q - 1] > old)) break;
+            }
+            const float pay_c[8] = {d[Q - 1] > before ? 1.0f : 0.0f, d[Q - 1], 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+            s = grp.exchange(gw, lane, pay_c);
+            float rose = sh.xch[s][0][0];
+#pragma unroll
+            for (int w = 1; w < TW; ++w) rose = fmaxf(rose, sh.xch[s][w][0]);
+            if (rose == 0.0f) break; /* C */
+            din0 = gw ? sh.xch[s][gw - 1][1] : NEG_INF;
+        }
+    }
+    else
+    {
+        if (lane == 31)
+        {
+            GRP_PUT(grp, vm_last[par][gw], vm[Q - 1]);
+            GRP_PUT(grp, vi_last[par][gw], vi[Q - 1]);
+            GRP_PUT(grp, e_warp[par][gw], ew);
+            GRP_PUT(grp, d_last[0][gw], d[Q - 1]);
+        }
+        if (gw == 0 && lane < 3) GRP_PUT(grp, v_spec[par][lane], vx);
+        grp.sync(); /* A: boundary values, per-warp maxima, specials and the local D chains' ends */
+
+        if (lane == 0)
+        {
+            vm_prev = gw ? sh.vm_last[par][gw - 1] : NEG_INF;
+            vi_prev = gw ? sh.vi_last[par][gw - 1] : NEG_INF;
+        }
+        E = sh.e_warp[par][0];
+#pragma unroll
+        for (int w = 1; w < TW; ++w) E = fmaxf(E, sh.e_warp[par][w]);
+        vN = sh.v_spec[par][0], vJ = sh.v_spec[par][1], vC = sh.v_spec[par][2];
+
+        /* carries between warps: D of the warp's first node = max(V_M(left) + MD, D(left) + DD), then lazily on */
+        float din0 = NEG_INF; /* D of the last node of the warp to the left */
+        for (int round = 0;; ++round)
+        {
+            const int b = round & 1;
+            if (round > 0)
+            {
+                if (lane == 31) GRP_PUT(grp, d_last[b][gw], d[Q - 1]);
+                grp.sync(); /* B */
+            }
+            din0 = gw ? sh.d_last[b][gw - 1] : NEG_INF;
+            const float before = __shfl_sync(FULL, d[Q - 1], 31);
+            for (;;)
+            {
+                float old = d[Q - 1];
+                din = __shfl_up_sync(FULL, old, 1);
+                if (lane == 0) din = din0;
+                float x = lane == 0 ? fmaxf(vm_prev + p.MD[0], din0 + p.DD[0]) : din + p.DD[0];
+                d[0] = fmaxf(d[0], x);
+                x = d[0];
+#pragma unroll
+                for (int i = 1; i < Q; ++i)
+                {
+                    x = x + p.DD[i];
+                    d[i] = fmaxf(d[i], x);
+                    x = d[i];
+                }
+                if (!__any_sync(FULL, d[Q - 1] > old)) break;
+            }
+            /* two warps: the left warp has no carry-in, so the D it published at A was final, and nobody reads
+             * the right warp's -- no second round can happen and barrier C is not needed (M = 512: 457 -> 520 GCUPS) */
+            if (TW == 2) break;
+            const float after = __shfl_sync(FULL, d[Q - 1], 31);
+            if (!grp.any(after > before, sh.flag, CL == 2 ? grp.peer->flag : sh.flag, b)) break; /* C */
+        }
+    }
+
+    float B = max3(vN + NB, vJ + JB, E + EB);
+    tx[R] = fmaxf(E + cE, vx + cX);
+#pragma unroll
+    for (int i = 0; i < Q; ++i)
+    {
+        float pm = i == 0 ? vm_prev : vm[i - 1];
+        float pi = i == 0 ? vi_prev : vi[i - 1];
+        float pd = i == 0 ? din : d[i - 1];
+        tm[R][i] = fmaxf(fmaxf(B + p.ent[i], pm + p.MM[i]), fmaxf(pi + p.IM[i], pd + p.DM[i]));
+        ti[R][i] = fmaxf(vm[i] + p.MI[i], vi[i] + p.II[i]);
+    }
+    E_out = E;
+    vC_out = vC;
+}
+
+/* BPS = resident blocks per SM the kernel is compiled for (class table): W * BPS warps per SM, i.e. 255 registers
+ * a thread for 8 warps, 168 for 12 */
+template <int W, int CL, int Q, int BPS>
+__global__ void __launch_bounds__(W * 32, CL == 2 ? 1 : BPS)
+k_score_mw(const float *__restrict__ emis, const float *__restrict__ trans, const ProfMeta *__restrict__ metas,
+           const uint32_t *__restrict__ class_profs, uint32_t n_class_profs, const SeqMeta *__restrict__ seqs,
+           uint32_t nseq, uint64_t total_recs, const RowRec *__restrict__ rows,
+           const uint16_t *__restrict__ wcodes, const float *__restrict__ spec, float *__restrict__ alt_out,
+           uint32_t nprof, unsigned long long *__restrict__ counter, uint32_t seq_tile)
+{
+    constexpr int TW = W * CL;
+    constexpr int ROW = 256 * TW;
+    __shared__ MwShared sh;
+    Group<CL, MwShared> grp;
+    grp.init(&sh);
+    const int lane = threadIdx.x & 31, gw = grp.rank * W + (threadIdx.x >> 5);
+    const unsigned long long n_items = (unsigned long long)n_class_profs * nseq;
+    if (CL == 2) grp.sync(); /* both blocks' shared memory exists before the first remote store */
+    if constexpr (CL == 2) grp.exchange_init(W);
+    for (;;)
+    {
+        if (grp.rank == 0 && threadIdx.x == 0)
+        {
+            unsigned long long it = atomicAdd(counter, 1ULL);
+            GRP_PUT(grp, item, it);
+        }
+        grp.sync();
+        const unsigned long long item = sh.item;
+        grp.sync();
+        if (item >= n_items) break;
+        /* (sequence tile, profile, sequence in tile), as in k_score */
+        const unsigned long long per_full_tile = (unsigned long long)seq_tile * n_class_profs;
+        const uint32_t tile = (uint32_t)(item / per_full_tile);
+        const unsigned long long in_tile = item - (unsigned long long)tile * per_full_tile;
+        const uint32_t seqs_here = min(seq_tile, nseq - tile * seq_tile);
+        const uint32_t prof = class_profs[in_tile / seqs_here];
+        const uint32_t s = tile * seq_tile + (uint32_t)(in_tile % seqs_here);
+        const ProfMeta pm = metas[prof];
+        NodeParams<Q> p;
+        load_params<Q>(p, trans + pm.trans_off, 32 * Q * TW, gw * 32 * Q + lane * Q);
+        const float *emis_lane = emis + pm.emis_off + gw * 256 + lane * 4;
+        const SeqMeta sm = seqs[s];
+        const RowRec *recs = rows + (size_t)pm.null_id * total_recs + sm.rec_off;
+        const uint16_t *wc = wcodes + sm.rec_off;
+        const float *sp = spec + (size_t)s * 16;
+        const uint32_t L = sm.len;
+
+        const float NN = sp[0], CC = sp[1], JJ = sp[2], NB = sp[3], CT = sp[4], JB = sp[5];
+        const float ET = sp[9], ECC = sp[10], EB = sp[11], EJJ = sp[12];
+        const float cE = lane == 0 ? NEG_INF : (lane == 1 ? EJJ : ECC);
+        const float cX = lane == 0 ? NN : (lane == 1 ? JJ : CC);
+
+        float tm[5][Q], ti[5][Q], tx[5];
+#pragma unroll
+        for (int r = 0; r < 5; ++r)
+        {
+            tx[r] = NEG_INF;
+#pragma unroll
+            for (int i = 0; i < Q; ++i) tm[r][i] = NEG_INF, ti[r][i] = NEG_INF;
+        }
+#pragma unroll
+        for (int i = 0; i < Q; ++i) tm[4][i] = NB + p.ent[i];
+        tx[4] = (gw == 0 && lane == 0) ? NN : NEG_INF;
+
+        RowState<Q> rs;
+#pragma unroll
+        for (int l = 0; l < 5; ++l) rs.eN[l] = NEG_INF;
+        {
+            uint32_t code[5];
+            codes_of(__ldg(wc + 1), code);
+            load_emis<Q, ROW>(rs.em, emis_lane, code);
+        }
+        load_row_insert(recs + 1, rs.eI);
+        if (gw == 0 && lane < 3) load_row_special(recs + 1, rs.eN);
+        rs.w1 = __ldg(wc + min(2u, L));
+        rs.w2 = __ldg(wc + min(3u, L));
+
+        float E = NEG_INF, vC = NEG_INF;
+        uint32_t j = 1;
+#define MW_ARGS(jj) recs + min((uint32_t)(jj) + 1u, L), wc + min((uint32_t)(jj) + 3u, L), gw, lane, (int)((jj)&1u), grp
+        for (; j + 4 <= L; j += 5)
+        {
+            mw_row<W, CL, 0, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j), NB, JB, EB, cE, cX, E, vC);
+            mw_row<W, CL, 1, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 1), NB, JB, EB, cE, cX, E, vC);
+            mw_row<W, CL, 2, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 2), NB, JB, EB, cE, cX, E, vC);
+            mw_row<W, CL, 3, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 3), NB, JB, EB, cE, cX, E, vC);
+            mw_row<W, CL, 4, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 4), NB, JB, EB, cE, cX, E, vC);
+        }
+        if (j <= L) mw_row<W, CL, 0, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j), NB, JB, EB, cE, cX, E, vC);
+        if (j + 1 <= L) mw_row<W, CL, 1, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 1), NB, JB, EB, cE, cX, E, vC);
+        if (j + 2 <= L) mw_row<W, CL, 2, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 2), NB, JB, EB, cE, cX, E, vC);
+        if (j + 3 <= L) mw_row<W, CL, 3, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 3), NB, JB, EB, cE, cX, E, vC);
+#undef MW_ARGS
+        if (gw == 0 && lane == 0) alt_out[(size_t)s * nprof + prof] = fmaxf(E + ET, vC + CT);
+    }
+}
+
+} // namespace
+#endif

@@ -1,0 +1,45 @@
+/* dcp_score_sw.cu -- launches of the one-warp-per-pair score kernels k_score<Q> (kernel classes 1..8). */
+#include "dcp_classes.h"
+#include "dcp_score.cuh"
+
+#include <cstdlib>
+
+namespace
+{
+template <int Q>
+cudaError_t launch_score(int nblocks, cudaStream_t st, const ScoreArgs &a)
+{
+    static const bool use_tma = getenv("DCPGPU_TMA") && atoi(getenv("DCPGPU_TMA")) != 0;
+    if (use_tma)
+    {
+        /* experiment: 4/5-nt emission lines through cp.async.bulk + mbarrier into a per-warp shared ring */
+        const int warps = score_warps(Q), LINE = 32 * (Q <= 4 ? 4 : 8);
+        const size_t smem = (size_t)warps * 4 * LINE * sizeof(float) + (size_t)warps * 2 * sizeof(uint64_t);
+        cudaFuncSetAttribute(k_score<Q, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_score<Q, true><<<nblocks, warps * 32, smem, st>>>(a.emis, a.trans, a.metas, a.class_profs, a.n_class, a.seqs,
+                                                            a.nseq, a.total_recs, a.rows, a.wcodes, a.spec, a.alt,
+                                                            a.nprof, a.counter, a.seq_tile);
+        return cudaGetLastError();
+    }
+    /* no shared memory: give the whole unified array to L1 (emission lines, row records) */
+    cudaFuncSetAttribute(k_score<Q, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    k_score<Q, false><<<nblocks, score_warps(Q) * 32, 0, st>>>(a.emis, a.trans, a.metas, a.class_profs, a.n_class,
+                                                               a.seqs, a.nseq, a.total_recs, a.rows, a.wcodes, a.spec,
+                                                               a.alt, a.nprof, a.counter, a.seq_tile);
+    return cudaGetLastError();
+}
+} // namespace
+
+cudaError_t dcp_launch_score(const dcp_class &c, int sm_count, cudaStream_t st, const ScoreArgs &a)
+{
+    const int nblocks = sm_count; /* persistent: one block per SM (as many warps as the register file holds) */
+#define X(TW, Q, BPS, RATE)                                                                                 \
+    if (TW == 1 && c.q == Q)                                                                                \
+    {                                                                                                       \
+        static_assert(TW != 1 || BPS == score_warps(Q), "class table: warps per block of k_score<Q>");      \
+        return launch_score<(TW == 1 ? Q : 1)>(nblocks, st, a);                                             \
+    }
+    DCP_CLASS_TABLE(X)
+#undef X
+    return cudaErrorInvalidValue;
+}

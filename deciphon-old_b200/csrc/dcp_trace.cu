@@ -17,6 +17,7 @@
  * [row][sub-node][lane] (64-byte coalesced stores) and one uint32 per row for the specials
  * [ecode:15 | n:3 | b:4 | j:3 | c:3 | t:3].
  */
+#include "dcp_classes.h"
 #include "dcp_kernels.cuh"
 
 #include <algorithm>
@@ -593,7 +594,7 @@ __device__ __forceinline__ void trace_row_mw(float (&tm)[5][Q], float (&ti)[5][Q
     }
 }
 
-template <int W, int CL, int Q = 8>
+template <int W, int CL, int Q>
 __global__ void __launch_bounds__(W * 32) k_trace_mw(const float *__restrict__ emis, const float *__restrict__ trans,
                                                      const ProfMeta *__restrict__ metas,
                                                      const SeqMeta *__restrict__ seqs, uint64_t total_rows,
@@ -803,6 +804,22 @@ void launch_trace(cudaStream_t st, uint32_t njobs, const dcpgpu_db *db, const dc
                                                 wcodes, spec, jobs, njobs, cell_bp, row_bp, alt);
 }
 
+/* one warp per hit (TW = 1) or a group of TW warps, one block or the two blocks of a cluster */
+template <int TW, int Q>
+void launch_trace_class(cudaStream_t st, uint32_t njobs, const dcpgpu_db *db, const dcpgpu_seqs *sq, const RowRec *rows,
+                        const uint16_t *wcodes, const float *spec, const TraceJob *jobs, uint16_t *cell_bp,
+                        uint32_t *row_bp, float *alt)
+{
+    if constexpr (TW == 1)
+        launch_trace<Q>(st, njobs, db, sq, rows, wcodes, spec, jobs, cell_bp, row_bp, alt);
+    else
+    {
+        constexpr int CL = TW > kMaxW ? 2 : 1, W = TW / CL;
+        launch_group(k_trace_mw<W, CL, Q>, CL, njobs * CL, W * 32, st, db->d_emis, db->d_trans, db->d_metas, sq->d_metas,
+                     sq->total + sq->nseq, rows, wcodes, spec, jobs, njobs, cell_bp, row_bp, alt);
+    }
+}
+
 } // namespace
 
 enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const RowRec *d_rows,
@@ -846,40 +863,34 @@ enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const
         for (uint32_t i = 0; i < nj; ++i) sorted[i] = jobs[order[i]];
 
         DevBuf b_jobs, b_cells, b_rows, b_alt, b_n, b_off, b_err, b_steps;
-        CU_TRY(b_jobs.alloc(nj * sizeof(TraceJob), st));
-        CU_TRY(b_cells.alloc(cells * sizeof(uint16_t), st));
-        CU_TRY(b_rows.alloc(rowsz * sizeof(uint32_t), st));
-        CU_TRY(b_alt.alloc(nj * sizeof(float), st));
-        CU_TRY(b_n.alloc(nj * sizeof(uint32_t), st));
-        CU_TRY(b_off.alloc(nj * sizeof(uint64_t), st));
-        CU_TRY(b_err.alloc(sizeof(uint32_t), st));
+        CU_TRY(b_jobs.alloc(nj * sizeof(TraceJob), db));
+        CU_TRY(b_cells.alloc(cells * sizeof(uint16_t), db));
+        CU_TRY(b_rows.alloc(rowsz * sizeof(uint32_t), db));
+        CU_TRY(b_alt.alloc(nj * sizeof(float), db));
+        CU_TRY(b_n.alloc(nj * sizeof(uint32_t), db));
+        CU_TRY(b_off.alloc(nj * sizeof(uint64_t), db));
+        CU_TRY(b_err.alloc(sizeof(uint32_t), db));
         CU_TRY(cudaMemcpyAsync(b_jobs.p, sorted.data(), nj * sizeof(TraceJob), cudaMemcpyHostToDevice, st));
         CU_TRY(cudaMemsetAsync(b_err.p, 0, sizeof(uint32_t), st));
         for (uint32_t a = 0; a < nj;)
         {
             uint32_t cls = db->metas[sorted[a].prof].cls, b = a;
             while (b < nj && db->metas[sorted[b].prof].cls == cls) ++b;
-#define LT(QQ)                                                                                                   \
-    case QQ:                                                                                                     \
-        launch_trace<QQ>(st, b - a, db, sq, d_rows, d_wcodes, d_spec, b_jobs.as<TraceJob>() + a,                  \
-                         b_cells.as<uint16_t>(), b_rows.as<uint32_t>(), b_alt.as<float>() + a);                  \
-        break;
-#define LTW(TWW, WW, CC, ...)                                                                                    \
-    case TWW:                                                                                                    \
-        launch_group(k_trace_mw<WW, CC, ##__VA_ARGS__>, CC, (b - a) * CC, WW * 32, st, db->d_emis, db->d_trans, db->d_metas,     \
-                     sq->d_metas, sq->total + sq->nseq, d_rows, d_wcodes, d_spec, b_jobs.as<TraceJob>() + a,     \
-                     b - a, b_cells.as<uint16_t>(), b_rows.as<uint32_t>(), b_alt.as<float>() + a);               \
-        break;
-            switch (cls)
             {
-                LT(1) LT(2) LT(3) LT(4) LT(5) LT(6) LT(7) LT(8)
-                LTW(kMaxQ + 2, 2, 1) LTW(kMaxQ + 3, 3, 1) LTW(kMaxQ + 4, 4, 1) LTW(kMaxQ + 5, 5, 1) LTW(kMaxQ + 6, 6, 1)
-                LTW(kMaxQ + 7, 7, 1) LTW(kMaxQ + 8, 8, 1) LTW(kMaxQ + 10, 5, 2) LTW(kMaxQ + 12, 6, 2)
-                LTW(kMaxQ + 14, 7, 2) LTW(kMaxQ + 16, 8, 2) LTW(kClsW2Q6, 2, 1, 6) LTW(kClsW2Q7, 2, 1, 7)
-                LTW(kClsW3Q6, 3, 1, 6) LTW(kClsW3Q7, 3, 1, 7)
+                const dcp_class &kc = *dcp_class_at(cls);
+                bool launched = false;
+                /* the trace kernels depend on (warps per pair, nodes per lane) only, not on the occupancy variant */
+#define X(TW, Q, BPS, RATE)                                                                                       \
+    if (!launched && kc.tw == TW && kc.q == Q)                                                                    \
+    {                                                                                                             \
+        launch_trace_class<TW, Q>(st, b - a, db, sq, d_rows, d_wcodes, d_spec, b_jobs.as<TraceJob>() + a,         \
+                                  b_cells.as<uint16_t>(), b_rows.as<uint32_t>(), b_alt.as<float>() + a);          \
+        launched = true;                                                                                          \
+    }
+                DCP_CLASS_TABLE(X)
+#undef X
+                if (!launched) return dcp_error(RC_EFAIL, "no trace kernel for this kernel class");
             }
-#undef LT
-#undef LTW
             (*launches)++;
             a = b;
         }
@@ -905,7 +916,7 @@ enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const
             if (memcmp(&talt[i], &score_alt[hit], sizeof(float)) != 0)
                 return dcp_error(RC_EFAIL, "trace pass and score pass disagree on the alt log-likelihood");
         }
-        CU_TRY(b_steps.alloc(std::max<uint64_t>(tot, 1) * sizeof(dcp_step), st));
+        CU_TRY(b_steps.alloc(std::max<uint64_t>(tot, 1) * sizeof(dcp_step), db));
         CU_TRY(cudaMemcpyAsync(b_off.p, off.data(), nj * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
         k_walk<<<(nj + 63) / 64, 64, 0, st>>>(db->d_metas, sq->d_metas, b_jobs.as<TraceJob>(), nj,
                                               b_cells.as<uint16_t>(), b_rows.as<uint32_t>(), 1, b_n.as<uint32_t>(),

@@ -4,10 +4,13 @@
  * Stands in for the REST-driven scan_run (src/server/scan.c:215-269), which needs a live
  * deciphon-sched: press the .hmm in memory (hmm_press, src/server/hmm.c:120-178), scan every
  * sequence against every profile on the GPU, write prod_fclose's header and one prod_fwrite row
- * per hit (src/server/prod.c:106-181).  Sequence ids are 1-based file order.
+ * per hit (src/server/prod.c:106-181).  Sequence ids are 1-based file order.  With --devices the database is
+ * sharded over several GPUs (dcpgpu_mdb_*, the counterpart of scan_run's thread partitions, scan.c:239-250);
+ * the output is byte-identical whatever the device count.
  *
  *   dcp-scan [--single-hit] [--hmmer3-compat] [--lrt X] [--epsilon E] [--uniform-entry]
- *            [--device N] [--scan-id N] [--batch N] profiles.{hmm,dcp} sequences.fasta > products.tsv
+ *            [--device N | --devices A,B,...] [--axis auto|profiles|sequences] [--scan-id N] [--batch N]
+ *            profiles.{hmm,dcp} sequences.fasta > products.tsv
  *   dcp-scan --press [--epsilon E] [--uniform-entry] profiles.hmm database.dcp       (hmm_press to a file)
  */
 #include "dcpgpu.h"
@@ -145,7 +148,8 @@ static enum rc load_dcp(struct dcpgpu_db *db, FILE *fp, unsigned *nprof)
 static void usage(void)
 {
     fputs("usage: dcp-scan [--single-hit] [--hmmer3-compat] [--lrt X] [--epsilon E] [--uniform-entry]\n"
-          "                [--device N] [--scan-id N] [--batch N] profiles.{hmm,dcp} sequences.fasta > products.tsv\n"
+          "                [--device N | --devices A,B,...] [--axis auto|profiles|sequences] [--scan-id N] [--batch N]\n"
+          "                profiles.{hmm,dcp} sequences.fasta > products.tsv\n"
           "       dcp-scan --press [--epsilon E] [--uniform-entry] profiles.hmm database.dcp\n",
           stderr);
 }
@@ -154,7 +158,9 @@ int main(int argc, char **argv)
 {
     struct dcpgpu_params prm = {.multi_hits = true, .hmmer3_compat = false, .lrt_threshold = 10.0, .want_paths = true};
     struct protein_cfg cfg = {ENTRY_DIST_OCCUPANCY, 0.01f}; /* PROTEIN_CFG_DEFAULT */
-    int device = 0;
+    int devices[64] = {0};
+    unsigned ndev = 1;
+    enum dcpgpu_axis axis = DCPGPU_AXIS_AUTO;
     int64_t scan_id = 1;
     unsigned batch = 65536;
     int do_press = 0;
@@ -167,7 +173,24 @@ int main(int argc, char **argv)
         else if (!strcmp(argv[i], "--uniform-entry")) cfg.entry_dist = ENTRY_DIST_UNIFORM;
         else if (!strcmp(argv[i], "--lrt") && i + 1 < argc) prm.lrt_threshold = atof(argv[++i]);
         else if (!strcmp(argv[i], "--epsilon") && i + 1 < argc) cfg.epsilon = (float)atof(argv[++i]);
-        else if (!strcmp(argv[i], "--device") && i + 1 < argc) device = atoi(argv[++i]);
+        else if (!strcmp(argv[i], "--device") && i + 1 < argc) devices[0] = atoi(argv[++i]), ndev = 1;
+        else if (!strcmp(argv[i], "--devices") && i + 1 < argc)
+        {
+            ndev = 0;
+            for (char *t = strtok(argv[++i], ","); t && ndev < 64; t = strtok(NULL, ",")) devices[ndev++] = atoi(t);
+            if (ndev == 0)
+            {
+                usage();
+                return 2;
+            }
+        }
+        else if (!strcmp(argv[i], "--axis") && i + 1 < argc)
+        {
+            ++i;
+            if (!strcmp(argv[i], "profiles")) axis = DCPGPU_AXIS_PROFILES;
+            else if (!strcmp(argv[i], "sequences")) axis = DCPGPU_AXIS_SEQUENCES;
+            else axis = DCPGPU_AXIS_AUTO;
+        }
         else if (!strcmp(argv[i], "--scan-id") && i + 1 < argc) scan_id = atoll(argv[++i]);
         else if (!strcmp(argv[i], "--batch") && i + 1 < argc) batch = (unsigned)atoi(argv[++i]);
         else
@@ -189,11 +212,14 @@ int main(int argc, char **argv)
         fprintf(stderr, "dcp-scan: cannot open %s\n", hmm ? argv[i + 1] : argv[i]);
         return 1;
     }
+    /* one device: a plain database; several: a multi-device one whose view takes the profiles */
     struct dcpgpu_db *db = NULL;
-    enum rc rc = dcpgpu_db_new(&db, device);
+    struct dcpgpu_mdb *mdb = NULL;
+    enum rc rc = ndev > 1 ? dcpgpu_mdb_new(&mdb, ndev, devices) : dcpgpu_db_new(&db, devices[0]);
+    if (!rc && mdb) db = dcpgpu_mdb_view(mdb);
     unsigned nprof = 0;
     if (!rc) rc = ends_with(argv[i], ".dcp") ? load_dcp(db, hmm, &nprof) : dcpgpu_press_hmm(db, hmm, cfg, &nprof);
-    if (!rc) rc = dcpgpu_db_commit(db);
+    if (!rc) rc = mdb ? dcpgpu_mdb_commit(mdb, axis) : dcpgpu_db_commit(db);
     fclose(hmm);
     if (rc)
     {
@@ -201,14 +227,10 @@ int main(int argc, char **argv)
         return 1;
     }
     dcpgpu_prod_fwrite_header(stdout);
-    /* a batch holds two floats and a flag per (sequence, profile) pair on both sides of the bus: keep it under
-     * 2^30 pairs (9 GB) whatever --batch says */
-    {
-        unsigned long long np = dcpgpu_db_nprofiles(db);
-        unsigned long long cap = (1ull << 30) / (np ? np : 1);
-        if (cap < 256) cap = 256;
-        if (batch > cap) batch = (unsigned)cap;
-    }
+    if (mdb)
+        fprintf(stderr, "dcp-scan: %u devices, %s axis, modelled shard imbalance %.3f\n", ndev,
+                dcpgpu_mdb_axis(mdb) == DCPGPU_AXIS_PROFILES ? "profile" : "sequence", dcpgpu_mdb_imbalance(mdb));
+    /* --batch bounds the host memory of a FASTA chunk; the library tiles a chunk further by device memory */
     int64_t next_id = 1;
     int pending = 0, more = 1;
     uint64_t total_hits = 0, total_seqs = 0;
@@ -224,7 +246,8 @@ int main(int argc, char **argv)
         if (s.n)
         {
             struct dcpgpu_result *res = NULL;
-            rc = dcpgpu_scan(db, s.n, (char const *const *)s.seq, s.len, &prm, &res);
+            rc = mdb ? dcpgpu_mdb_scan(mdb, s.n, (char const *const *)s.seq, s.len, &prm, &res)
+                     : dcpgpu_scan(db, s.n, (char const *const *)s.seq, s.len, &prm, &res);
             if (!rc) rc = dcpgpu_prod_fwrite(res, db, stdout, scan_id, s.id, s.n, (char const *const *)s.seq);
             if (rc)
             {
@@ -241,6 +264,7 @@ int main(int argc, char **argv)
     fclose(fa);
     fprintf(stderr, "dcp-scan: %u profiles x %llu sequences, %llu hits\n", nprof, (unsigned long long)total_seqs,
             (unsigned long long)total_hits);
-    dcpgpu_db_del(db);
+    if (mdb) dcpgpu_mdb_del(mdb);
+    else dcpgpu_db_del(db);
     return 0;
 }

@@ -209,6 +209,11 @@ struct dcpgpu_params
     bool hmmer3_compat;
     double lrt_threshold;
     bool want_paths; /* false: scores + hit flags only (no traceback pass) */
+    /* progress_consume (src/server/scan_thread.c:120, src/core/progress.c:70-90): called with the number of
+     * (sequence, profile) pairs just finished -- once per launch set, i.e. per memory-sized tile of the batch
+     * and per device; calls are serialised.  May be NULL. */
+    void (*progress)(void *user, uint64_t pairs_consumed);
+    void *user;
 };
 
 /* Create an empty database bound to CUDA device `device`.  RC_EFAIL if there is no usable
@@ -242,7 +247,11 @@ void dcpgpu_seqs_del(struct dcpgpu_seqs *);
  * sequence-major, profile-minor, independent of how the GPU scheduled the pairs. */
 enum rc dcpgpu_scan_resident(struct dcpgpu_db *, struct dcpgpu_seqs *, struct dcpgpu_params const *,
                              struct dcpgpu_result **out);
-/* Same, from host buffers: stages the sequences, scans, copies results back. */
+/* Same, from host buffers: stages the sequences, scans, copies results back.  A batch whose row records and
+ * pair scores would not fit the device's free memory is run as several launch sets (64 B per nucleotide and
+ * null table, 5 B per pair, at most 2^30 pairs each) and the results are merged, so nseqs is not bounded by
+ * HBM.  A non-ACGT symbol fails the whole batch with RC_EINVAL, as an imm_seq error fails the reference's
+ * whole job (scan.c:229-231, 244-256). */
 enum rc dcpgpu_scan(struct dcpgpu_db *, unsigned nseqs, char const *const *seqs,
                     unsigned const *lens, struct dcpgpu_params const *, struct dcpgpu_result **out);
 
@@ -257,6 +266,12 @@ uint64_t dcpgpu_result_nhits(struct dcpgpu_result const *);
  * (imm_path_nsteps / imm_path_step, prod.c:162-176). */
 enum rc dcpgpu_result_hit_at(struct dcpgpu_result const *, uint64_t i, unsigned *seq_idx,
                              unsigned *prof_idx, struct dcp_step const **steps, unsigned *nsteps);
+/* The whole hit list at once, (sequence, profile) order: nhits entries per array (any may be NULL); alt / null are
+ * the fp32 log-likelihoods prod.c prints.  _steps: all paths back to back in hit order (hit i owns nsteps[i] of
+ * them); the pointer stays valid until dcpgpu_result_del. */
+enum rc dcpgpu_result_hits(struct dcpgpu_result const *, unsigned *seq_idx, unsigned *prof_idx, float *alt_loglik,
+                           float *null_loglik, unsigned *nsteps);
+uint64_t dcpgpu_result_steps(struct dcpgpu_result const *, struct dcp_step const **steps);
 /* device time of the kernels of the last scan on this db, by phase (ms, CUDA events) */
 struct dcpgpu_timing
 {
@@ -269,12 +284,53 @@ struct dcpgpu_timing
     uint64_t h2d_bytes, d2h_bytes;
 };
 void dcpgpu_result_timing(struct dcpgpu_result const *, struct dcpgpu_timing *);
+enum rc dcpgpu_result_part_timing(struct dcpgpu_result const *, unsigned part, int *device, struct dcpgpu_timing *);
 void dcpgpu_result_del(struct dcpgpu_result *);
 
-/* Longest-processing-time partition of profiles over `nshards` devices by core size
- * (replaces the equal-count partition of src/db/profile_reader.c:54-72). */
+/* ------------------------------------------------------------------------- */
+/* Part 2b -- multi-device.  Replaces scan_run's omp-parallel-for over profile  */
+/* partitions (scan.c:239-250, profile_reader.c:54-72) and the ordered          */
+/* concatenation of per-thread products (prod.c:106-145): a partition is a GPU. */
+/* ------------------------------------------------------------------------- */
+/* Longest-processing-time partition of profiles over `nshards` devices by MODELLED COST: padded width of the
+ * profile's kernel class / measured rate of that class (replaces the equal-count partition of
+ * src/db/profile_reader.c:54-72).  Deterministic. */
 enum rc dcpgpu_shard_profiles(unsigned nprofiles, unsigned const *core_sizes, unsigned nshards,
                               unsigned *shard_of);
+/* modelled score-pass time of one sequence row against a profile of `core_size` nodes (ns on one B200) */
+double dcpgpu_profile_cost(unsigned core_size);
+/* contiguous ranges of sequences with about equal nucleotide totals; bounds has nshards + 1 entries */
+enum rc dcpgpu_shard_sequences(unsigned nseqs, unsigned const *lens, unsigned nshards, unsigned *bounds);
+
+struct dcpgpu_mdb; /* a database sharded (or replicated) over several GPUs of one box */
+enum dcpgpu_axis
+{
+    DCPGPU_AXIS_AUTO,      /* profiles when their modelled costs balance within 10 %, else sequences */
+    DCPGPU_AXIS_PROFILES,  /* each device holds a cost-balanced shard of the profiles, scans all sequences */
+    DCPGPU_AXIS_SEQUENCES, /* each device holds every profile, scans a contiguous range of the sequences */
+};
+/* devices: CUDA device ordinals, one shard each (an ordinal may repeat: its shards then share that GPU) */
+enum rc dcpgpu_mdb_new(struct dcpgpu_mdb **out, unsigned ndevices, int const *devices);
+enum rc dcpgpu_mdb_add(struct dcpgpu_mdb *, struct protein_profile const *prof);
+/* shard, upload (one host thread per device) and release the host tables */
+enum rc dcpgpu_mdb_commit(struct dcpgpu_mdb *, enum dcpgpu_axis axis);
+/* every profile in global order: pass it to dcpgpu_press_hmm before the commit, and to dcpgpu_prod_* /
+ * dcpgpu_db_accession with the results of dcpgpu_mdb_scan */
+struct dcpgpu_db *dcpgpu_mdb_view(struct dcpgpu_mdb *);
+unsigned dcpgpu_mdb_ndevices(struct dcpgpu_mdb const *);
+unsigned dcpgpu_mdb_nprofiles(struct dcpgpu_mdb const *);
+enum dcpgpu_axis dcpgpu_mdb_axis(struct dcpgpu_mdb const *);
+double dcpgpu_mdb_imbalance(struct dcpgpu_mdb const *); /* modelled max / mean shard cost */
+int dcpgpu_mdb_device_of(struct dcpgpu_mdb const *, unsigned profile); /* -1 when replicated */
+uint64_t dcpgpu_mdb_device_bytes(struct dcpgpu_mdb const *, unsigned shard);
+/* dcpgpu_scan over all devices; hits come back merged in (sequence, global profile) order, bit-identical to a
+ * single-device scan of the same database whatever the device count or axis */
+enum rc dcpgpu_mdb_scan(struct dcpgpu_mdb *, unsigned nseqs, char const *const *seqs, unsigned const *lens,
+                        struct dcpgpu_params const *, struct dcpgpu_result **out); /* delete `out` before the mdb */
+void dcpgpu_mdb_del(struct dcpgpu_mdb *);
+/* launch sets a (merged) result was built from, and the device / phase times of each: the per-device busy
+ * times of a multi-device scan (their spread is the shard imbalance) */
+unsigned dcpgpu_result_nparts(struct dcpgpu_result const *);
 
 /* How the engine maps a profile of `core_size` nodes (1..4096, limits.h:11) onto the GPU: `warps` per
  * (sequence, profile) pair, `nodes_per_lane`, and 1 or 2 thread blocks (a cluster) per pair; warps * 32 *

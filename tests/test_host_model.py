@@ -131,10 +131,16 @@ def test_shard_profiles(pkg):
     sizes = np.clip(np.exp(rng.normal(np.log(130), 0.7, 5000)), 50, 2000).astype(np.uint32)
     for n in (1, 2, 4, 8):
         sh = pkg.shard_profiles(sizes, n)
-        loads = np.bincount(sh, weights=sizes, minlength=n)
-        assert sh.max() < n and loads.max() - loads.min() <= sizes.max()
+        # balanced by MODELLED COST (padded width / measured class rate), not by nominal length
+        cost = np.array([pkg.profile_cost(m) for m in sizes])
+        loads = np.bincount(sh, weights=cost, minlength=n)
+        assert sh.max() < n and loads.max() - loads.min() <= cost.max()
+        assert loads.max() * n <= 1.01 * loads.sum()
     with pytest.raises(pkg.DcpError):
         pkg.shard_profiles(sizes, 0)
+    # cost per node differs between kernel classes: a 3000-node profile (two-block groups) costs more per node
+    assert pkg.profile_cost(3000) / 3000 > 2 * pkg.profile_cost(256) / 256
+    assert pkg.profile_cost(200) == pkg.profile_cost(256)  # same padded width, same class
 
 
 def test_kernel_shape_covers_every_core_size(pkg):

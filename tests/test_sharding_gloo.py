@@ -42,7 +42,7 @@ def _worker(rank, world, port, q):
         fp = ref_paths(full, len(sizes))
         want = [(s, p, float(full["alt"][s, p]), float(full["null"][s, p]), fp[(s, p)])
                 for s in range(len(seqs)) for p in range(len(sizes)) if full["hit"][s, p]]
-        loads = [sum(sizes[i] for i in own) for own in owners]
+        loads = [sum(pkg.profile_cost(sizes[i]) for i in own) for own in owners]
         q.put((merged == want, sorted(sum(owners, [])) == list(range(len(sizes))), loads))
     dist.barrier()
     dist.destroy_process_group()
@@ -53,14 +53,19 @@ def test_axis_choice(pkg):
     sharding = importlib.import_module("deciphon_old_b200.sharding")
     rng = np.random.default_rng(0)
     many = np.clip(np.exp(rng.normal(np.log(130), 0.7, 2000)), 50, 2000).astype(int)
-    axis, shard = sharding.plan(pkg, many, 100000, 8)
+    axis, shard = sharding.plan(pkg, many, [1500] * 1000, 8)
     assert axis == "profiles" and len(shard) == 2000 and shard.max() == 7
-    # config 4: 50 long profiles of unequal length over 8 GPUs do not balance -> shard the contigs instead
+    # config 4: few long profiles of unequal length over 8 GPUs do not balance -> shard the contigs instead,
+    # by cumulative length (dcpgpu_shard_sequences): equal lengths split evenly, ragged ones by nucleotides
     few = [3000] * 3 + [2000] * 2
-    axis, parts = sharding.plan(pkg, few, 10001, 8)
-    assert axis == "sequences" and parts[0] == (0, 1251) and parts[-1][1] == 10001
-    assert sum(hi - lo for lo, hi in parts) == 10001
-    assert sharding.plan(pkg, few, 10, 1)[0] == "profiles"
+    axis, bounds = sharding.plan(pkg, few, [10000] * 10001, 8)
+    assert axis == "sequences" and bounds[0] == 0 and bounds[-1] == 10001 and len(bounds) == 9
+    assert all(1250 <= b - a <= 1251 for a, b in zip(bounds[:-1], bounds[1:]))
+    lens = [100] * 90 + [9100]
+    b2 = pkg.shard_sequences(lens, 2)
+    assert list(b2) == [0, 90, 91]  # 9000 nt | 9100 nt
+    assert list(pkg.shard_sequences([5, 5, 5], 8))[-1] == 3  # more shards than sequences: empty tails
+    assert sharding.plan(pkg, few, [10] * 10, 1)[0] == "profiles"
 
 
 def test_two_rank_shard_and_merge():
@@ -75,4 +80,5 @@ def test_two_rank_shard_and_merge():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert same and complete
-    assert abs(loads[0] - loads[1]) <= 64  # LPT balance: within one largest profile
+    import __graft_entry__ as ge
+    assert abs(loads[0] - loads[1]) <= ge.load_pkg().profile_cost(64) + 1e-9  # LPT balance: within one largest profile
