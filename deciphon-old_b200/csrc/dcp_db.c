@@ -3,7 +3,7 @@
  *
  * Follows the layout the reference's code writes (src/db/writer.c:95-117,153-175,
  * src/db/protein_writer.c:56-96, src/model/protein_profile.c:338-400, src/model/nuclt_dist.c:5-23):
- *   map(2) { "header":   map(8) { magic_number=0xC6F0, profile_typeid=2, float_size=4, entry_dist,
+ *   map(2) { "header":   map(8) { magic_number=0xC6F1 (reference: 0xC6F0), profile_typeid=2, float_size=4, entry_dist,
  *                                 epsilon, abc, amino, profile_sizes },
  *            "profiles": array(N) of map(16) { accession, null, alt, core_size, consensus,
  *                                 R, S, N, B, E, J, C, T, null_ndist, alt_insert_ndist, alt_match_ndist } }
@@ -14,14 +14,19 @@
  * reference tree.  Here those four values are self-describing instead: the alphabets are strings, and
  * "null"/"alt" carry the explicit DP-level arrays the kernels consume (emission tables, the 7 transition
  * scores per node, entry scores).  profile_sizes is a plain array of uint32.  Files written here are read
- * back bit-exactly by this reader; they are not interchangeable with files pressed by the C reference.
+ * back bit-exactly by this reader; they are not interchangeable with files pressed by the C reference, and
+ * say so themselves: magic_number is 0xC6F1 here, and a file with the reference's 0xC6F0 is refused with
+ * RC_EPARSE and a message naming the imm blobs.
  */
 #include "dcp_internal.h"
 
 #include <stdlib.h>
 #include <string.h>
 
-enum { DCP_MAGIC = 0xC6F0, DCP_PROFILE_PROTEIN = 2 };
+/* 0xC6F0 is the reference's magic (include/deciphon/db/types.h:11).  Files written here carry explicit arrays where
+ * the reference stores imm blobs, so they get their own magic: each reader rejects the other's files at the first
+ * header key instead of failing somewhere inside a profile. */
+enum { DCP_MAGIC_REFERENCE = 0xC6F0, DCP_MAGIC = 0xC6F1, DCP_PROFILE_PROTEIN = 2 };
 
 /* ---------------------------- MessagePack subset ---------------------------- */
 static bool put(FILE *fp, void const *p, size_t n) { return fwrite(p, 1, n, fp) == n; }
@@ -272,7 +277,14 @@ enum rc protein_db_reader_open(struct protein_db_reader **out, FILE *fp)
     enum rc rc = RC_EPARSE;
     char const *why = "bad database header";
     if (!r_map(fp, &n) || n != 2 || !expect_key(fp, "header") || !r_map(fp, &n) || n != 8) goto fail;
-    if (!expect_key(fp, "magic_number") || !r_uint(fp, &v) || v != DCP_MAGIC) { why = "wrong magic number"; goto fail; }
+    if (!expect_key(fp, "magic_number") || !r_uint(fp, &v)) goto fail;
+    if (v == DCP_MAGIC_REFERENCE)
+    {
+        why = "database pressed by the C reference (imm_abc / imm_dp blobs): not supported, press the .hmm again with "
+              "dcp-scan --press";
+        goto fail;
+    }
+    if (v != DCP_MAGIC) { why = "wrong magic number"; goto fail; }
     if (!expect_key(fp, "profile_typeid") || !r_uint(fp, &v) || v != DCP_PROFILE_PROTEIN) { why = "not a protein database"; goto fail; }
     if (!expect_key(fp, "float_size") || !r_uint(fp, &v) || v != sizeof(float)) { why = "float_size must be 4"; goto fail; }
     if (!expect_key(fp, "entry_dist") || !r_uint(fp, &v)) goto fail;

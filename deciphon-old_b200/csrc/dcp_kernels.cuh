@@ -129,8 +129,11 @@ __device__ __forceinline__ void load_emis_part(float (&em)[5][Q], const float *_
         else if (Q == 7)
         {
 #if DCP_Q7_LOAD8
-            /* one 16-byte load (the lane's fourth float is padding) instead of an 8- and a 4-byte one */
-            float4 b = ldg4(src + 128, l);
+            /* one 16-byte load (the lane's fourth float is padding).  volatile: ptxas otherwise narrows a v4 load
+             * with a dead component into three 4-byte loads (25 instead of 15 loads per row) */
+            float4 b;
+            asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
+                         : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(src + 128));
             em[l][4 % Q] = b.x, em[l][5 % Q] = b.y, em[l][6 % Q] = b.z;
 #else
             float2 b = __ldg(reinterpret_cast<const float2 *>(src + 128));

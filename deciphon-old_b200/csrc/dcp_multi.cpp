@@ -51,8 +51,7 @@ void drop(std::vector<Part> &parts)
 size_t scan_bytes(const dcpgpu_db *db, size_t S, size_t T)
 {
     const size_t P = db->profs.size(), n_null = db->null_tabs.size(), recs = T + S;
-    return n_null * recs * sizeof(RowRec) + recs * 2 + T + S * (sizeof(SeqMeta) + 64 + n_null * 4) + P * S * 5 +
-           ((size_t)64 << 20);
+    return n_null * recs * sizeof(RowRec) + recs * 2 + T + S * (sizeof(SeqMeta) + 64 + n_null * 4) + P * S * 5;
 }
 
 /*
@@ -70,8 +69,9 @@ enum rc scan_range(dcpgpu_db *db, const std::vector<uint32_t> *gprofs, uint32_t 
     cudaMemPoolGetAttribute(db->pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
     cudaMemPoolGetAttribute(db->pool, cudaMemPoolAttrUsedMemCurrent, &used);
     const size_t avail = free_b + (size_t)(reserved > used ? reserved - used : 0);
-    size_t budget = std::max<size_t>((size_t)(0.4 * (double)avail), (size_t)256 << 20);
-    if (const char *e = getenv("DCPGPU_SCAN_BUDGET_MB")) budget = (size_t)std::max(1.0, atof(e)) << 20; /* test knob */
+    /* 40 % of what is free, less 64 MB for the small buffers of a scan; the traceback pass sizes itself later */
+    size_t budget = std::max<size_t>((size_t)(0.4 * (double)avail), (size_t)320 << 20) - ((size_t)64 << 20);
+    if (const char *e = getenv("DCPGPU_SCAN_BUDGET_KB")) budget = (size_t)std::max(1.0, atof(e)) << 10; /* test knob */
     const size_t max_pairs = (size_t)1 << 30, P = db->profs.size();
     uint32_t a = lo;
     while (a < hi)

@@ -691,6 +691,17 @@ static struct gmodel *gmodel_alt(const struct orc_profile *p, const struct xtran
     return g;
 }
 
+/* imm_dp_change_trans x12 (protein_profile.c:190-214): the length-dependent scores of an existing graph */
+static void gmodel_alt_specials(struct gmodel *g, const struct xtrans *x)
+{
+    g->st[GS_N].inc[0].score = x->NN, g->st[GS_N].inc[1].score = x->NN;
+    g->st[GS_B].inc[0].score = x->NB, g->st[GS_B].inc[1].score = x->NB;
+    g->st[GS_B].inc[2].score = x->JB, g->st[GS_B].inc[3].score = x->EB;
+    g->st[GS_J].inc[0].score = x->EJJ, g->st[GS_J].inc[1].score = x->JJ;
+    g->st[GS_C].inc[0].score = x->ECC, g->st[GS_C].inc[1].score = x->CC;
+    g->st[GS_T].inc[0].score = x->ET, g->st[GS_T].inc[1].score = x->CT;
+}
+
 static struct gmodel *gmodel_null(const struct orc_profile *p, const struct xtrans *x)
 {
     struct gmodel *g = calloc(1, sizeof *g);
@@ -720,14 +731,25 @@ static int gviterbi(const struct gmodel *g, const uint8_t *seq, int L, ofloat *l
 {
     int n = g->n;
     size_t rows = (size_t)L + 1;
-    ofloat *W = malloc(sizeof(ofloat) * rows * n * 6);
-    int32_t *bt = malloc(sizeof(int32_t) * rows * n);
-    uint8_t *bl = malloc(rows * n);
-    if (!W || !bt || !bl) {
-        free(W); free(bt); free(bl);
-        return RC_ENOMEM;
+    /* DP matrix and backpointers are per-thread and grow-only, like the imm_task a scan thread keeps and
+     * resets between pairs (scan_thread.c:40-55); every entry that is read has been written in the same call
+     * (W[r'][s][l] is read at row r' + l <= L and written at row r' iff r' + l <= L), so nothing is cleared */
+    static _Thread_local struct { ofloat *W; int32_t *bt; uint8_t *bl; size_t cap; } scr;
+    if (scr.cap < rows * n) {
+        free(scr.W); free(scr.bt); free(scr.bl);
+        scr.cap = rows * n + rows * n / 4;
+        scr.W = malloc(sizeof(ofloat) * scr.cap * 6);
+        scr.bt = malloc(sizeof(int32_t) * scr.cap);
+        scr.bl = malloc(scr.cap);
+        if (!scr.W || !scr.bt || !scr.bl) {
+            free(scr.W); free(scr.bt); free(scr.bl);
+            scr.W = NULL, scr.bt = NULL, scr.bl = NULL, scr.cap = 0;
+            return RC_ENOMEM;
+        }
     }
-    for (size_t i = 0; i < rows * n * 6; ++i) W[i] = NEGINF;
+    ofloat *W = scr.W;
+    int32_t *bt = scr.bt;
+    uint8_t *bl = scr.bl;
 #define WW(r, s, l) W[((size_t)(r)*n + (s)) * 6 + (l)]
     for (int r = 0; r <= L; ++r) {
         for (int oi = 0; oi < n; ++oi) {
@@ -806,7 +828,6 @@ static int gviterbi(const struct gmodel *g, const uint8_t *seq, int L, ofloat *l
         }
     }
 #undef WW
-    free(W); free(bt); free(bl);
     return rc;
 }
 
@@ -1099,6 +1120,12 @@ int orc_scan(int nprof, struct orc_profile *const *profs, int nseq, const char *
 #pragma omp parallel for schedule(static, 1) collapse(1)
     for (int pi = 0; pi < nprof; ++pi) {
         const struct orc_profile *p = profs[pi];
+        /* flavour 0: the profile's two DPs are compiled once (the reference unpacks them once per pair from
+         * disk, scan_thread.c:99; holding them in RAM is a deviation in the CPU's favour) and only the
+         * length-dependent transitions change per sequence, as protein_profile_setup does */
+        struct gmodel *g_alt = NULL, *g_null = NULL;
+        uint8_t *enc = NULL;
+        int enc_cap = 0;
         for (int si = 0; si < nseq; ++si) {
             long idx = (long)si * nprof + pi;
             int L = lens[si];
@@ -1111,9 +1138,20 @@ int orc_scan(int nprof, struct orc_profile *const *profs, int nseq, const char *
             if (flavour == 0) {
                 ss = malloc(sizeof(uint16_t) * maxst);
                 sl = malloc(maxst);
-                rc = orc_viterbi_null(p, seqs[si], L, multi_hits, hmmer3_compat, &nl, NULL, NULL, NULL, 0);
-                if (!rc)
-                    rc = orc_viterbi_alt(p, seqs[si], L, multi_hits, hmmer3_compat, &al, ss, sl, &ns, maxst);
+                struct xtrans x;
+                rc = specials((unsigned)L, multi_hits, hmmer3_compat, &x);
+                if (!rc && L > enc_cap) {
+                    free(enc);
+                    enc = malloc(L), enc_cap = L;
+                }
+                if (!rc) rc = encode_seq(seqs[si], L, enc);
+                if (!rc) {
+                    if (!g_alt) g_alt = gmodel_alt(p, &x), g_null = gmodel_null(p, &x);
+                    gmodel_alt_specials(g_alt, &x);
+                    g_null->st[0].inc[0].score = x.RR;
+                    rc = gviterbi(g_null, enc, L, &nl, NULL, NULL, NULL, 0);
+                }
+                if (!rc) rc = gviterbi(g_alt, enc, L, &al, ss, sl, &ns, maxst);
             } else {
                 rc = orc_scores_fast(p, seqs[si], L, multi_hits, hmmer3_compat, &nl, &al);
             }
@@ -1146,6 +1184,9 @@ int orc_scan(int nprof, struct orc_profile *const *profs, int nseq, const char *
                 free(ss); free(sl);
             }
         }
+        if (g_alt) gmodel_del(g_alt);
+        if (g_null) gmodel_del(g_null);
+        free(enc);
     }
     if (path_off) {
         long off = 0;

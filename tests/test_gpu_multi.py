@@ -107,7 +107,7 @@ def test_auto_axis_follows_the_cost_model(pkg, o32):
 
 def test_scan_tiled_by_device_memory_equals_one_launch(pkg, o32):
     """dcpgpu_scan splits a batch that would not fit the device's free memory into several launch sets
-    (DCPGPU_SCAN_BUDGET_MB forces it here) and merges them; progress is reported per launch set."""
+    (DCPGPU_SCAN_BUDGET_KB forces it here) and merges them; progress is reported per launch set."""
     sizes = [33, 150, 280]
     rng, models, profs, twins = build(pkg, o32, sizes, seed=8)
     seqs = [sample_read(rng, models[i % 3][1], int(rng.integers(100, 500)), 0.02, 0.01) for i in range(40)]
@@ -118,11 +118,11 @@ def test_scan_tiled_by_device_memory_equals_one_launch(pkg, o32):
     one = db.scan(seqs)
     assert len(one.part_timings) == 0
     calls = []
-    os.environ["DCPGPU_SCAN_BUDGET_MB"] = "65"  # 64 MB fixed part + ~1 MB: a few sequences per launch set
+    os.environ["DCPGPU_SCAN_BUDGET_KB"] = "100"  # row records are 64 B per nucleotide: a few sequences per launch set
     try:
         tiled = db.scan(seqs, progress=calls.append)
     finally:
-        del os.environ["DCPGPU_SCAN_BUDGET_MB"]
+        del os.environ["DCPGPU_SCAN_BUDGET_KB"]
     assert len(tiled.part_timings) > 3 and len(calls) == len(tiled.part_timings)
     assert sum(calls) == len(seqs) * len(sizes)
     assert snapshot(tiled) == snapshot(one)

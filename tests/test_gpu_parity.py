@@ -286,6 +286,57 @@ def test_dcp_scan_driver_matches_reference_product_rows(pkg, o32, tmp_path):
     assert out.returncode == 1 and "ACGT" in out.stderr
 
 
+def test_scan_from_a_pressed_dcp_database(pkg, o32, tmp_path):
+    """hmm_press to a .dcp file (src/server/hmm.c:120-178), then the scan loads the database from it
+    (protein_db_reader_open + profile_reader_next, src/db/profile_reader.c): rows are byte-identical to the scan of the
+    .hmm itself and to the oracle's product rows; the library path (read_dcp -> dcpgpu_db_add) agrees too."""
+    import os
+    import subprocess
+    from common import write_hmm
+    rng = np.random.default_rng(31)
+    models = []
+    for i, M in enumerate((45, 130, 260, 520)):
+        _, ma, tr = plan7_profile_inputs(rng, M)
+        models.append(("dom%d" % i, "PF7%04d.2" % i, ma, tr))
+    hmm = str(tmp_path / "fam.hmm")
+    seen = write_hmm(hmm, models)
+    seqs = [sample_read(rng, seen[i % 4][0], int(rng.integers(300, 1200)), 0.02, 0.01) for i in range(10)]
+    seqs.append(random_seq(rng, 500))
+    fasta = tmp_path / "reads.fasta"
+    fasta.write_text("".join(">s%d\n%s\n" % (i, s) for i, s in enumerate(seqs)))
+    exe = os.path.join(os.path.dirname(pkg.__file__), "dcp-scan")
+    dcp = str(tmp_path / "fam.dcp")
+    out = subprocess.run([exe, "--press", hmm, dcp], capture_output=True, text=True)
+    assert out.returncode == 0 and "pressed 4 profiles" in out.stderr, out.stderr
+    from_hmm = subprocess.run([exe, "--scan-id", "9", hmm, str(fasta)], capture_output=True, text=True)
+    from_dcp = subprocess.run([exe, "--scan-id", "9", dcp, str(fasta)], capture_output=True, text=True)
+    assert from_hmm.returncode == 0 and from_dcp.returncode == 0, from_dcp.stderr
+    assert from_dcp.stdout == from_hmm.stdout and len(from_dcp.stdout.splitlines()) >= 9
+    # the oracle's rows for the same database
+    cfg, profs = pkg.read_dcp(dcp)
+    assert cfg.entry_dist == pkg.ENTRY_DIST_OCCUPANCY and [p.core_size for p in profs] == [45, 130, 260, 520]
+    twins = [oracle_twin(o32, p, 0.01) for p in profs]
+    ref = o32.scan(twins, seqs, True, False, 10.0, 1, True)
+    paths = ref_paths(ref, 4)
+    want = [twins[p].product_row(9, s + 1, profs[p].accession, float(ref["alt"][s, p]), float(ref["null"][s, p]),
+                                 seqs[s], paths[(s, p)])
+            for s in range(len(seqs)) for p in range(4) if ref["hit"][s, p]]
+    assert from_dcp.stdout.splitlines(keepends=True)[1:] == want
+    # library path: profiles unpacked from the file go straight into a device database
+    db = pkg.Db(0)
+    for p in profs:
+        db.add(p)
+    db.commit()
+    res = db.scan(seqs)
+    assert np.array_equal(res.alt_loglik, ref["alt"]) and np.array_equal(res.hit, ref["hit"])
+    # a file with the reference's magic number is refused with a parse error, not scanned
+    raw = open(dcp, "rb").read()
+    ref_like = str(tmp_path / "ref.dcp")
+    open(ref_like, "wb").write(raw.replace(b"\xcd\xc6\xf1", b"\xcd\xc6\xf0", 1))
+    out = subprocess.run([exe, ref_like, str(fasta)], capture_output=True, text=True)
+    assert out.returncode == 1 and "imm" in out.stderr
+
+
 def test_fp32_path_within_reference_tolerance_of_double_oracle(pkg, o32, o64):
     """The reference's CI runs float and double builds against the same goldens with rel. tolerance 5e-5 for float
     (test/hope_support.h:26).  The fp32 GPU scores must sit within that tolerance of the DOUBLE oracle fed the

@@ -80,7 +80,7 @@ def build_db(pkg, rng, sizes, eps=0.01):
     return db, profs, models
 
 
-def check_properties(pkg, db, profs, seqs, res, nsample, rng, o32=None, multi_hits=True):
+def check_properties(pkg, db, profs, seqs, res, nsample, rng, o32=None, multi_hits=True, noracle=6, npaths=0):
     alt, null, hit = res.alt_loglik, res.null_loglik, res.hit
     lrt = np.float32(-2) * (null - alt)
     assert np.array_equal(hit.astype(bool), np.isfinite(lrt) & ~(lrt.astype(np.float64) < 10.0))  # scan_thread.c:121-123
@@ -98,11 +98,25 @@ def check_properties(pkg, db, profs, seqs, res, nsample, rng, o32=None, multi_hi
         assert sum(l for _, l in path) == len(seqs[s])
         got = rescore(pkg, profs[p], seqs[s], path, multi_hits)
         assert got == alt[s, p], (s, p, got, alt[s, p])
-    if o32 is not None:  # a few pairs against the oracle itself, hits and non-hits alike
-        for _ in range(6):
-            s, p = int(rng.integers(0, len(seqs))), int(rng.integers(0, len(profs)))
-            rc, nl, al = oracle_twin(o32, profs[p], 0.01).scores_fast(seqs[s], multi_hits, False)
-            assert rc == 0 and np.float32(nl) == null[s, p] and np.float32(al) == alt[s, p]
+    if o32 is not None:
+        # pairs against the oracle itself, bit for bit: random ones (mostly misses) and as many hits
+        twins = {}
+        pairs = [(int(rng.integers(0, len(seqs))), int(rng.integers(0, len(profs)))) for _ in range(noracle)]
+        if res.nhits:
+            hs, hp = res.hits()[0], res.hits()[1]
+            pairs += [(int(hs[i]), int(hp[i])) for i in rng.choice(res.nhits, size=min(noracle, res.nhits), replace=False)]
+        for s, p in pairs:
+            if p not in twins:
+                twins[p] = oracle_twin(o32, profs[p], 0.01)
+            rc, nl, al = twins[p].scores_fast(seqs[s], multi_hits, False)
+            assert rc == 0 and np.float32(nl) == null[s, p] and np.float32(al) == alt[s, p], (s, p)
+        # full decoded paths of a few hits against the imm-shaped generic interpreter (first-max tie order included)
+        for i in (rng.choice(res.nhits, size=min(npaths, res.nhits), replace=False) if res.nhits else []):
+            s, p, path = res.hit_at(int(i))
+            if p not in twins:
+                twins[p] = oracle_twin(o32, profs[p], 0.01)
+            rc, al, want = twins[p].viterbi_alt(seqs[s], multi_hits, False)
+            assert rc == 0 and np.float32(al) == alt[s, p] and path == want, (s, p)
 
 
 def test_config2_full_size(pkg, o32):
@@ -114,7 +128,7 @@ def test_config2_full_size(pkg, o32):
     staged = db.stage(reads)
     res = db.scan_resident(staged)
     assert res.timing.alt_cells == 2 * 10 ** 12
-    check_properties(pkg, db, profs, reads, res, 300, rng, o32)
+    check_properties(pkg, db, profs, reads, res, 300, rng, o32, noracle=48, npaths=8)
     assert res.nhits >= 9000  # every read was drawn from one of the profiles
     res2 = db.scan(reads)  # host-buffer path, second run: identical
     assert np.array_equal(res.alt_loglik, res2.alt_loglik) and res.nhits == res2.nhits
@@ -128,12 +142,13 @@ def test_config3_shape_pfam_lengths(pkg, o32):
     db, profs, models = build_db(pkg, rng, sizes)
     reads = [sample_read(rng, models[int(rng.integers(0, len(models)))][1], 1500, 0.02, 0.01) for _ in range(96)]
     res = db.scan(reads)
-    check_properties(pkg, db, profs, reads, res, 60, rng, o32)
+    check_properties(pkg, db, profs, reads, res, 60, rng, o32, noracle=24, npaths=6)
     assert res.nhits >= 60
 
 
-def test_config4_shape_long_profiles_long_contigs(pkg):
-    """configs[3] shape: long profiles (M ~ 3000) x 10 kbp contigs: two-block cluster kernels, large traceback."""
+def test_config4_shape_long_profiles_long_contigs(pkg, o32):
+    """configs[3] shape: long profiles (M ~ 3000) x 10 kbp contigs: two-block cluster kernels, large traceback.
+    Scores of twelve (M ~ 3000, L = 10 kbp) pairs and one full decoded path are compared with the oracle."""
     rng = np.random.default_rng(4)
     db, profs, models = build_db(pkg, rng, [3000, 2900, 2100])
     contigs = []
@@ -142,7 +157,7 @@ def test_config4_shape_long_profiles_long_contigs(pkg):
         pad = 10000 - len(core)
         contigs.append(random_seq(rng, pad // 2) + core + random_seq(rng, pad - pad // 2))
     res = db.scan(contigs)
-    check_properties(pkg, db, profs, contigs, res, 18, rng)
+    check_properties(pkg, db, profs, contigs, res, 18, rng, o32, noracle=6, npaths=1)
     assert res.nhits >= 6
 
 
@@ -153,5 +168,5 @@ def test_config5_shape_short_reads(pkg, o32):
     db, profs, models = build_db(pkg, rng, sizes)
     reads = [sample_read(rng, models[int(rng.integers(0, len(models)))][1], 150, 1e-4, 0.005) for _ in range(4000)]
     res = db.scan(reads)
-    check_properties(pkg, db, profs, reads, res, 200, rng, o32)
+    check_properties(pkg, db, profs, reads, res, 200, rng, o32, noracle=32, npaths=12)
     assert res.timing.alt_cells == sum(sizes) * 150 * 4000

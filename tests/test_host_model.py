@@ -157,10 +157,11 @@ def test_kernel_shape_covers_every_core_size(pkg):
             assert w % 2 == 0 and w // 2 <= 8
         if M > 96:
             assert w * 32 * q <= 1.5 * M, (M, w, q)
-    assert pkg.kernel_shape(200) == (1, 8, 1)       # 7 per lane spills: 8 per lane
-    assert pkg.kernel_shape(300) == (2, 6, 1) and pkg.kernel_shape(448) == (2, 7, 1)
-    assert pkg.kernel_shape(512) == (2, 8, 1) and pkg.kernel_shape(600) == (3, 7, 1)
-    assert pkg.kernel_shape(3000) == (12, 8, 2)
+    # the chooser minimises padded width / measured rate over the class table (dcp_classes.h): the cost never
+    # decreases with the profile length, and a profile never lands in a class it does not fit
+    costs = [pkg.profile_cost(M) for M in range(1, 4097)]
+    assert all(b >= a for a, b in zip(costs, costs[1:]))
+    assert pkg.kernel_shape(256) == (1, 8, 1) and pkg.kernel_shape(512)[0] == 2 and pkg.kernel_shape(4096) == (16, 8, 2)
     for bad in (0, 4097):
         with pytest.raises(pkg.DcpError):
             pkg.kernel_shape(bad)
@@ -229,7 +230,8 @@ def test_dcp_database_round_trip(pkg, tmp_path):
     path = str(tmp_path / "db.dcp")
     pkg.write_dcp(path, profs, cfg)
     raw = open(path, "rb").read()
-    assert raw[0] == 0x82 and raw[1:8] == b"\xa6header" and b"\xcd\xc6\xf0" in raw[:40]  # map(2), magic 0xC6F0
+    # map(2), own magic 0xC6F1: the four imm blobs of a reference file (magic 0xC6F0) are explicit arrays here
+    assert raw[0] == 0x82 and raw[1:8] == b"\xa6header" and b"\xcd\xc6\xf1" in raw[:40]
     rcfg, back = pkg.read_dcp(path)
     assert rcfg.entry_dist == cfg.entry_dist and rcfg.epsilon == cfg.epsilon
     assert len(back) == 3  # EQ(db.nprofiles, 2) in the reference's test
@@ -246,8 +248,14 @@ def test_dcp_database_round_trip(pkg, tmp_path):
     with pytest.raises(pkg.DcpError) as e:
         pkg.read_dcp(bad)
     assert e.value.rc == pkg.RC_EPARSE
-    open(bad, "wb").write(raw.replace(b"\xcd\xc6\xf0", b"\xcd\xc6\xf1", 1))
-    with pytest.raises(pkg.DcpError):
+    # a file carrying the reference's magic is refused up front, naming the reason
+    open(bad, "wb").write(raw.replace(b"\xcd\xc6\xf1", b"\xcd\xc6\xf0", 1))
+    with pytest.raises(pkg.DcpError) as e:
         pkg.read_dcp(bad)
+    assert e.value.rc == pkg.RC_EPARSE and "imm" in str(e.value) and "reference" in str(e.value)
+    open(bad, "wb").write(raw.replace(b"\xcd\xc6\xf1", b"\xcd\xc6\xf2", 1))
+    with pytest.raises(pkg.DcpError) as e:
+        pkg.read_dcp(bad)
+    assert e.value.rc == pkg.RC_EPARSE and "magic" in str(e.value)
     with pytest.raises(pkg.DcpError):
         pkg.write_dcp(str(tmp_path / "x.dcp"), [pkg.ProteinProfile.sample(1, 2, pkg.protein_cfg(2, 0.02))], cfg)

@@ -30,7 +30,10 @@ def table_rows():
     src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "deciphon-old_b200", "csrc",
                             "dcp_classes.h")).read()
     body = src[src.index("#define DCP_CLASS_TABLE"):]
-    return [tuple(int(x) for x in m.groups()[:3]) for m in re.finditer(r"X\((\d+), (\d+), (\d+), (\d+)\)", body)]
+    rows = [tuple(int(x) for x in m.groups()) for m in re.finditer(r"X\((\d+), (\d+), (\d+), (\d+)\)", body)]
+    if "--unmeasured" in sys.argv:  # only the candidates whose rate is still 0
+        rows = [r for r in rows if r[3] == 0]
+    return [r[:3] for r in rows]
 
 
 def main():
