@@ -574,8 +574,13 @@ def main():
                      "kernel_gcups": k_gcups, "kernel_ms": k_ms,
                      "peak_source": "measured live: dcpgpu_microbench_alu 2:1 FADD:FMNMX3 mix = %.0f G lane-instr/s "
                                     "(FADD %.0f, FMNMX3 %.0f), x33/27 ops per instruction; peak_hard = %d SMs x 128 lanes x "
-                                    "%.0f MHz x33/27 (no mix, no dual-issue limits)" % (
-                                        alu["mix_ginst"], alu["fadd_ginst"], alu["fmnmx3_ginst"], alu["sms"], sm_mhz),
+                                    "%.0f MHz x33/27 (no mix, no dual-issue limits); inside the microbenchmark the SM "
+                                    "clock was %.0f MHz (mix) / %.0f MHz (FADD): %.1f / %.1f lane-instr per SM and clock "
+                                    "of 128" % (
+                                        alu["mix_ginst"], alu["fadd_ginst"], alu["fmnmx3_ginst"], alu["sms"], sm_mhz,
+                                        alu["mix_clock_mhz"], alu["fadd_clock_mhz"],
+                                        alu["mix_ginst"] * 1e3 / (alu["sms"] * max(alu["mix_clock_mhz"], 1.0)),
+                                        alu["fadd_ginst"] * 1e3 / (alu["sms"] * max(alu["fadd_clock_mhz"], 1.0))),
                      "hbm": {"bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                              "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak,
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"}},

@@ -227,9 +227,10 @@ def xmath_lrt(null, alt):
 
 def microbench_alu(device=0):
     """Measured FP32 issue peaks: dict of 1e9 lane-instructions/s for FADD, FMNMX3 and the DP-cell mix."""
-    out = np.zeros(4)
+    out = np.zeros(6)
     _check(lib().dcpgpu_microbench_alu(device, out.ctypes.data))
-    return {"fadd_ginst": out[0], "fmnmx3_ginst": out[1], "mix_ginst": out[2], "sms": int(out[3])}
+    return {"fadd_ginst": out[0], "fmnmx3_ginst": out[1], "mix_ginst": out[2], "sms": int(out[3]),
+            "mix_clock_mhz": out[4], "fadd_clock_mhz": out[5]}
 
 
 def kernel_shape(core_size):

@@ -21,22 +21,23 @@
 
 #define DCP_CLASS_TABLE(X)                                                                                      \
     /* one warp per pair: 16 / 12 / 8 resident warps per SM */                                                  \
-    X(1, 2, 16, 407) X(1, 4, 12, 596) X(1, 5, 8, 574) X(1, 6, 8, 644) X(1, 8, 8, 726)                           \
+    X(1, 2, 16, 406) X(1, 4, 12, 596) X(1, 5, 8, 573) X(1, 6, 8, 644) X(1, 8, 8, 726)                           \
     /* two warps: 12 resident warps per SM with 5 nodes per lane (168 registers, no spills), else 8 */          \
-    X(2, 5, 6, 432) X(2, 6, 4, 458) X(2, 7, 4, 479) X(2, 8, 4, 520)                                             \
-    /* three warps: 12 resident warps (6 at 255 registers leave the schedulers idle: 294) */                    \
-    X(3, 6, 4, 315)                                                                                             \
+    X(2, 5, 6, 452) X(2, 6, 4, 485) X(2, 7, 4, 515) X(2, 8, 4, 560)                                             \
+    /* three warps: 12 resident warps (6 at 255 registers leave the schedulers idle) */                         \
+    X(3, 6, 4, 339)                                                                                             \
     /* four warps */                                                                                            \
-    X(4, 5, 3, 320) X(4, 6, 2, 373) X(4, 7, 2, 401) X(4, 8, 2, 431)                                             \
+    X(4, 5, 3, 343) X(4, 6, 2, 399) X(4, 7, 2, 430) X(4, 8, 2, 468)                                             \
     /* five to eight warps: a block of 8 warps fills the SM, fewer leave issue slots idle */                    \
-    X(6, 6, 2, 287) X(5, 8, 1, 271) X(8, 6, 1, 323) X(8, 7, 1, 358) X(8, 8, 1, 387)                             \
+    X(6, 6, 2, 312) X(5, 8, 1, 285) X(8, 6, 1, 340) X(8, 7, 1, 385) X(8, 8, 1, 417)                             \
     /* two blocks of a cluster */                                                                               \
-    X(10, 8, 1, 170) X(16, 6, 1, 199) X(14, 8, 1, 216) X(16, 8, 1, 230)
+    X(16, 6, 1, 257) X(14, 8, 1, 256) X(16, 8, 1, 272)
 
-/* Measured and left out (rate in parentheses; each loses to a neighbour in padded width / rate):
+/* Measured and left out (rates before the straight-line row layout, which lifted every multi-warp class by 5..30 %;
+ * each loses to a neighbour in padded width / rate):
  * (1,1,16: 193) (1,3,12: 437) (1,7,8: 618 -- 7 nodes per lane runs no faster per row than 8) (2,5,4: 332) (2,6,6: 408,
  * spills) (3,5,4: 311) (3,6,2: 294) (3,7,2: 315) (3,8,2: 342) (4,5,2: 269) (4,6,3: 311, spills) (5,5,2: 315)
- * (5,6,2: 286) (6,5,2: 286) (6,8,1: 320) (7,8,1: 352) (8,5,1: 259) (12,8: 195) (16,5: 171) (16,7: 211);
+ * (5,6,2: 286) (6,5,2: 286) (6,8,1: 320) (7,8,1: 352) (8,5,1: 259) (10,8: 197 with the new layout) (12,8: 195) (16,5: 171) (16,7: 211);
  * profiles/r02_class_sweep_table.jsonl */
 
 #endif

@@ -339,7 +339,7 @@ enum rc db_commit(dcpgpu_db *db)
         m.emis_off = emis_floats;
         m.trans_off = trans_floats;
         emis_floats += (uint64_t)kTab * 32 * QP * W;
-        trans_floats += (uint64_t)8 * 32 * Q * W;
+        trans_floats += (uint64_t)8 * 32 * Q * W + 3 * W; /* + the carry bounds of the W warps (dcp_score_mw.cuh) */
         db->class_list[m.cls].push_back((uint32_t)i);
         max_M = std::max(max_M, M);
     }
@@ -393,6 +393,17 @@ enum rc db_commit(dcpgpu_db *db)
                 tr[5 * NP + n] = t.MI, tr[6 * NP + n] = t.II;
             }
             tr[7 * NP + n] = p->entry[k - 1];
+        }
+        /* carry bound per warp: S = sum of D->D over the warp's nodes after its first, rounded up; the M->D and
+         * D->D scores into its first node */
+        float *cbnd = tr + 8 * NP;
+        for (uint32_t w = 0; w < m.W; ++w)
+        {
+            const uint32_t n0 = w * 32 * m.Q;
+            double sum = 0.0;
+            for (uint32_t n = n0 + 1; n < n0 + 32 * m.Q; ++n) sum += (double)tr[4 * NP + n];
+            cbnd[w] = std::isinf(sum) ? NEG_INF : std::nextafterf((float)sum, INFINITY);
+            cbnd[m.W + w] = tr[3 * NP + n0], cbnd[2 * m.W + w] = tr[4 * NP + n0];
         }
     }
     CU_TRY(cudaGetLastError());

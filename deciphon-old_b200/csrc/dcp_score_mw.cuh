@@ -24,8 +24,38 @@ namespace
  * Measured alternatives that were not faster: keeping 8 warps per SM with 5 or 6 nodes per lane
  * (M = 600: 252 vs 267 GCUPS) -- the barriers, not the occupancy, bound these kernels.
  */
+/*
+ * Carry bound of one warp of a group (lane w holds warp w's): S = an upper bound of the sum of the D->D scores of
+ * the warp's nodes after its first (host, dcp_engine.cu), md0 / dd0 = M->D and D->D into its first node.  A carry
+ * that enters warp w cannot lift the warp's last D above  max(V_M(left) + md0, D(left) + dd0) + S: when that is
+ * below the end of the warp's own chain for every warp, the D values exchanged at A are final and the second
+ * rendezvous of the row (C) is skipped -- every warp evaluates the same test on the same exchanged values, so no
+ * communication is needed to agree on it.  Otherwise the exact lazy rounds run as before.
+ */
+struct CarryBound
+{
+    float S, md0, dd0;
+};
+#ifndef DCP_CARRY_BOUND
+#define DCP_CARRY_BOUND 1
+#endif
+
+/* vm_left / d_left / d_own: V_M and local D end of warp w - 1, local D end of warp w, for w = clamp(lane, 1, TW - 1)
+ * (every lane evaluates, lanes outside 1..TW-1 are masked: no divergence on the row's critical path) */
+template <int TW>
+__device__ __forceinline__ bool carry_cannot_rise(const CarryBound &cb, int lane, float vm_left, float d_left,
+                                                  float d_own)
+{
+    const float cin = fmaxf(vm_left + cb.md0, d_left + cb.dd0);
+    /* the chain is rounded at every node: 2^-13 relative slack covers 256 roundings of 2^-24 four times over */
+    const float bound = cin + cb.S + (9.8e-4f + 1.22e-4f * (fabsf(cin) + fabsf(cb.S)));
+    const bool bad = (lane >= 1) & (lane < TW) & (cin > NEG_INF) & (cb.S > NEG_INF) & !(bound <= d_own);
+    return !__any_sync(FULL, bad);
+}
+
 struct MwShared
 {
+    float d_loc[2][kMaxGroupWarps]; /* ends of the warps' own D chains, by row parity */
     float vm_last[2][kMaxGroupWarps], vi_last[2][kMaxGroupWarps], e_warp[2][kMaxGroupWarps];
     float d_last[2][kMaxGroupWarps];
     float v_spec[2][4]; /* V_N, V_J, V_C of the row */
@@ -41,7 +71,7 @@ __device__ __forceinline__ void mw_row(float (&tm)[5][Q], float (&ti)[5][Q], flo
                                        const float *__restrict__ emis_lane, const RowRec *__restrict__ rec_next,
                                        const uint16_t *__restrict__ w_next2, int gw, int lane, int par,
                                        Group<CL, MwShared> &grp, float NB, float JB, float EB, float cE, float cX,
-                                       float &E_out, float &vC_out)
+                                       const CarryBound &cb, float &E_out, float &vC_out)
 {
     constexpr int TW = W * CL;
     constexpr int ROW = 256 * TW;
@@ -124,6 +154,12 @@ __device__ __forceinline__ void mw_row(float (&tm)[5][Q], float (&ti)[5][Q], flo
             vN = x[0][4], vJ = x[0][5], vC = x[0][6];
         }
         float din0 = gw ? sh.xch[s][gw - 1][3] : NEG_INF;
+        bool final_d = false;
+        if (DCP_CARRY_BOUND)
+        {
+            const int w = min(max(lane, 1), TW - 1);
+            final_d = carry_cannot_rise<TW>(cb, lane, sh.xch[s][w - 1][0], sh.xch[s][w - 1][3], sh.xch[s][w][3]);
+        }
         /* carries between warps, lazily: every round ends with an exchange of (did my last D rise, my last D) */
         for (;;)
         {
@@ -145,6 +181,7 @@ __device__ __forceinline__ void mw_row(float (&tm)[5][Q], float (&ti)[5][Q], flo
                 }
                 if (!__any_sync(FULL, d[Q - 1] > old)) break;
             }
+            if (final_d) break; /* no warp's last D can have risen: the values exchanged at A were final */
             const float pay_c[8] = {d[Q - 1] > before ? 1.0f : 0.0f, d[Q - 1], 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
             s = grp.exchange(gw, lane, pay_c);
             float rose = sh.xch[s][0][0];
@@ -161,7 +198,7 @@ __device__ __forceinline__ void mw_row(float (&tm)[5][Q], float (&ti)[5][Q], flo
             GRP_PUT(grp, vm_last[par][gw], vm[Q - 1]);
             GRP_PUT(grp, vi_last[par][gw], vi[Q - 1]);
             GRP_PUT(grp, e_warp[par][gw], ew);
-            GRP_PUT(grp, d_last[0][gw], d[Q - 1]);
+            GRP_PUT(grp, d_loc[par][gw], d[Q - 1]);
         }
         if (gw == 0 && lane < 3) GRP_PUT(grp, v_spec[par][lane], vx);
         grp.sync(); /* A: boundary values, per-warp maxima, specials and the local D chains' ends */
@@ -176,6 +213,12 @@ __device__ __forceinline__ void mw_row(float (&tm)[5][Q], float (&ti)[5][Q], flo
         for (int w = 1; w < TW; ++w) E = fmaxf(E, sh.e_warp[par][w]);
         vN = sh.v_spec[par][0], vJ = sh.v_spec[par][1], vC = sh.v_spec[par][2];
 
+        bool final_d = TW == 2;
+        if (DCP_CARRY_BOUND && TW > 2)
+        {
+            const int w = min(max(lane, 1), TW - 1);
+            final_d = carry_cannot_rise<TW>(cb, lane, sh.vm_last[par][w - 1], sh.d_loc[par][w - 1], sh.d_loc[par][w]);
+        }
         /* carries between warps: D of the warp's first node = max(V_M(left) + MD, D(left) + DD), then lazily on */
         float din0 = NEG_INF; /* D of the last node of the warp to the left */
         for (int round = 0;; ++round)
@@ -186,7 +229,7 @@ __device__ __forceinline__ void mw_row(float (&tm)[5][Q], float (&ti)[5][Q], flo
                 if (lane == 31) GRP_PUT(grp, d_last[b][gw], d[Q - 1]);
                 grp.sync(); /* B */
             }
-            din0 = gw ? sh.d_last[b][gw - 1] : NEG_INF;
+            din0 = gw ? (round == 0 ? sh.d_loc[par][gw - 1] : sh.d_last[b][gw - 1]) : NEG_INF;
             const float before = __shfl_sync(FULL, d[Q - 1], 31);
             for (;;)
             {
@@ -206,8 +249,9 @@ __device__ __forceinline__ void mw_row(float (&tm)[5][Q], float (&ti)[5][Q], flo
                 if (!__any_sync(FULL, d[Q - 1] > old)) break;
             }
             /* two warps: the left warp has no carry-in, so the D it published at A was final, and nobody reads
-             * the right warp's -- no second round can happen and barrier C is not needed (M = 512: 457 -> 520 GCUPS) */
-            if (TW == 2) break;
+             * the right warp's -- no second round can happen and barrier C is not needed (M = 512: 457 -> 520 GCUPS).
+             * More warps: the same holds whenever the carry bound shows that no warp's last D can rise. */
+            if (final_d) break;
             const float after = __shfl_sync(FULL, d[Q - 1], 31);
             if (!grp.any(after > before, sh.flag, CL == 2 ? grp.peer->flag : sh.flag, b)) break; /* C */
         }
@@ -223,6 +267,247 @@ __device__ __forceinline__ void mw_row(float (&tm)[5][Q], float (&ti)[5][Q], flo
         float pd = i == 0 ? din : d[i - 1];
         tm[R][i] = fmaxf(fmaxf(B + p.ent[i], pm + p.MM[i]), fmaxf(pi + p.IM[i], pd + p.DM[i]));
         ti[R][i] = fmaxf(vm[i] + p.MI[i], vi[i] + p.II[i]);
+    }
+    E_out = E;
+    vC_out = vC;
+}
+
+#ifndef DCP_MW_V2
+#define DCP_MW_V2 1
+#endif
+#ifndef DCP_CARRY_BOUND_CL1
+#define DCP_CARRY_BOUND_CL1 0 /* one-block groups: skipping their second barrier measured no gain */
+#endif
+/*
+ * mw_row2: the same row as mw_row, laid out for the instruction scheduler.  ptxas schedules inside basic blocks, and
+ * the lazy carry loops of mw_row are blocks of their own that hold nothing but one dependent add/max chain.  Here the
+ * first carry round on either side of the rendezvous is straight-line code (a further round is a rare loop after
+ * it), and the work that does not depend on the D chain -- Tin_I, the M->M / I->M part of Tin_M before the
+ * rendezvous, the B->M part after it -- sits in the same block, so it fills the chain's latency.  Values are
+ * bit-identical: only maxima are re-associated, every sum is still (V_src + t).
+ */
+template <int W, int CL, int R, int Q>
+__device__ __forceinline__ void mw_row2(float (&tm)[5][Q], float (&ti)[5][Q], float (&tx)[5],
+                                        const NodeParams<Q> &p, RowState<Q> &rs,
+                                        const float *__restrict__ emis_lane, const RowRec *__restrict__ rec_next,
+                                        const uint16_t *__restrict__ w_next2, int gw, int lane, int par,
+                                        Group<CL, MwShared> &grp, float NB, float JB, float EB, float cE, float cX,
+                                        const CarryBound &cb, float &E_out, float &vC_out)
+{
+    constexpr int TW = W * CL;
+    constexpr int ROW = 256 * TW;
+    constexpr int S1 = (R + 4) % 5, S2 = (R + 3) % 5, S3 = (R + 2) % 5, S4 = (R + 1) % 5, S5 = R;
+    MwShared &sh = *grp.me;
+
+    float vm[Q], vi[Q];
+#pragma unroll
+    for (int i = 0; i < Q; ++i)
+        vm[i] = fmaxf(max3(tm[S1][i] + rs.em[0][i], tm[S2][i] + rs.em[1][i], tm[S3][i] + rs.em[2][i]),
+                      fmaxf(tm[S4][i] + rs.em[3][i], tm[S5][i] + rs.em[4][i]));
+#pragma unroll
+    for (int i = 0; i < Q; ++i)
+        vi[i] = fmaxf(max3(ti[S1][i] + rs.eI[0], ti[S2][i] + rs.eI[1], ti[S3][i] + rs.eI[2]),
+                      fmaxf(ti[S4][i] + rs.eI[3], ti[S5][i] + rs.eI[4]));
+    float vx = fmaxf(max3(tx[S1] + rs.eN[0], tx[S2] + rs.eN[1], tx[S3] + rs.eN[2]),
+                     fmaxf(tx[S4] + rs.eN[3], tx[S5] + rs.eN[4]));
+
+    uint32_t code[5];
+    codes_of(rs.w1, code);
+    load_emis_part<Q, 3, 5, ROW>(rs.em, emis_lane, code);
+    load_row_insert(rec_next, rs.eI);
+    if (gw == 0 && lane < 3) load_row_special(rec_next, rs.eN);
+    rs.w1 = rs.w2;
+    rs.w2 = __ldg(w_next2);
+
+    float eloc = vm[0];
+#pragma unroll
+    for (int i = 1; i < Q; ++i) eloc = fmaxf(eloc, vm[i]);
+    const float ew = warp_max(eloc);
+    float vm_prev = __shfl_up_sync(FULL, vm[Q - 1], 1);
+    float vi_prev = __shfl_up_sync(FULL, vi[Q - 1], 1);
+    if (lane == 0) vm_prev = NEG_INF, vi_prev = NEG_INF; /* the left warp's values arrive with the rendezvous */
+    load_emis_part<Q, 0, 3, ROW>(rs.em, emis_lane, code);
+
+    /* D chain inside the warp (nothing from the warp to the left yet), first carry round straight-line */
+    float d[Q];
+    d[0] = vm_prev + p.MD[0];
+#pragma unroll
+    for (int i = 1; i < Q; ++i) d[i] = fmaxf(vm[i - 1] + p.MD[i], d[i - 1] + p.DD[i]);
+    float old = d[Q - 1];
+    float din = __shfl_up_sync(FULL, old, 1);
+    if (lane == 0) din = NEG_INF;
+    {
+        float x = din;
+#pragma unroll
+        for (int i = 0; i < Q; ++i)
+        {
+            x = x + p.DD[i];
+            d[i] = fmaxf(d[i], x);
+            x = d[i];
+        }
+    }
+    bool more = __any_sync(FULL, d[Q - 1] > old);
+    /* independent of the D chain: Tin_I, and the part of Tin_M that comes from this warp's own M and I (slot R's old
+     * content, row j-5, is dead) */
+#pragma unroll
+    for (int i = 0; i < Q; ++i)
+    {
+        const float pm = i == 0 ? vm_prev : vm[i - 1];
+        const float pi = i == 0 ? vi_prev : vi[i - 1];
+        tm[R][i] = fmaxf(pm + p.MM[i], pi + p.IM[i]);
+        ti[R][i] = fmaxf(vm[i] + p.MI[i], vi[i] + p.II[i]);
+    }
+    while (more)
+    {
+        old = d[Q - 1];
+        din = __shfl_up_sync(FULL, old, 1);
+        if (lane == 0) din = NEG_INF;
+        float x = din;
+#pragma unroll
+        for (int i = 0; i < Q; ++i)
+        {
+            x = x + p.DD[i];
+            d[i] = fmaxf(d[i], x);
+            x = d[i];
+        }
+        more = __any_sync(FULL, d[Q - 1] > old);
+    }
+
+    /* rendezvous A */
+    float E, vN, vJ, vC, din0;
+    int xs = 0;
+    bool final_d = TW == 2;
+    if constexpr (CL == 2)
+    {
+        const float xN = __shfl_sync(FULL, vx, 0), xJ = __shfl_sync(FULL, vx, 1), xC = __shfl_sync(FULL, vx, 2);
+        const float pay_a[8] = {vm[Q - 1], vi[Q - 1], ew, d[Q - 1], xN, xJ, xC, 0.0f};
+        xs = grp.exchange(gw, lane, pay_a);
+        const float(*x)[8] = sh.xch[xs];
+        if (lane == 0 && gw) vm_prev = x[gw - 1][0], vi_prev = x[gw - 1][1];
+        E = x[0][2];
+#pragma unroll
+        for (int w = 1; w < TW; ++w) E = fmaxf(E, x[w][2]);
+        vN = x[0][4], vJ = x[0][5], vC = x[0][6];
+        din0 = gw ? x[gw - 1][3] : NEG_INF;
+        if (DCP_CARRY_BOUND)
+        {
+            const int w = min(max(lane, 1), TW - 1);
+            final_d = carry_cannot_rise<TW>(cb, lane, x[w - 1][0], x[w - 1][3], x[w][3]);
+        }
+    }
+    else
+    {
+        if (lane == 31)
+        {
+            sh.vm_last[par][gw] = vm[Q - 1], sh.vi_last[par][gw] = vi[Q - 1];
+            sh.e_warp[par][gw] = ew, sh.d_loc[par][gw] = d[Q - 1];
+        }
+        if (gw == 0 && lane < 3) sh.v_spec[par][lane] = vx;
+        __syncthreads();
+        if (lane == 0 && gw) vm_prev = sh.vm_last[par][gw - 1], vi_prev = sh.vi_last[par][gw - 1];
+        E = sh.e_warp[par][0];
+#pragma unroll
+        for (int w = 1; w < TW; ++w) E = fmaxf(E, sh.e_warp[par][w]);
+        vN = sh.v_spec[par][0], vJ = sh.v_spec[par][1], vC = sh.v_spec[par][2];
+        din0 = gw ? sh.d_loc[par][gw - 1] : NEG_INF;
+        if (DCP_CARRY_BOUND_CL1 && TW > 2)
+        {
+            const int w = min(max(lane, 1), TW - 1);
+            final_d = carry_cannot_rise<TW>(cb, lane, sh.vm_last[par][w - 1], sh.d_loc[par][w - 1], sh.d_loc[par][w]);
+        }
+    }
+
+    /* the carry from the warp to the left enters at lane 0: first round straight-line */
+    const float before = __shfl_sync(FULL, d[Q - 1], 31);
+    old = d[Q - 1];
+    din = __shfl_up_sync(FULL, old, 1);
+    if (lane == 0) din = din0;
+    {
+        float x = lane == 0 ? fmaxf(vm_prev + p.MD[0], din0 + p.DD[0]) : din + p.DD[0];
+        d[0] = fmaxf(d[0], x);
+        x = d[0];
+#pragma unroll
+        for (int i = 1; i < Q; ++i)
+        {
+            x = x + p.DD[i];
+            d[i] = fmaxf(d[i], x);
+            x = d[i];
+        }
+    }
+    more = __any_sync(FULL, d[Q - 1] > old);
+    /* independent of the carry: B, the specials, the B->M part of Tin_M, lane 0's M->M / I->M from the left warp */
+    const float B = max3(vN + NB, vJ + JB, E + EB);
+    tx[R] = fmaxf(E + cE, vx + cX);
+    if (lane == 0) tm[R][0] = fmaxf(vm_prev + p.MM[0], vi_prev + p.IM[0]);
+#pragma unroll
+    for (int i = 0; i < Q; ++i) tm[R][i] = fmaxf(tm[R][i], B + p.ent[i]);
+    while (more)
+    {
+        old = d[Q - 1];
+        din = __shfl_up_sync(FULL, old, 1);
+        if (lane == 0) din = din0;
+        float x = lane == 0 ? fmaxf(vm_prev + p.MD[0], din0 + p.DD[0]) : din + p.DD[0];
+        d[0] = fmaxf(d[0], x);
+        x = d[0];
+#pragma unroll
+        for (int i = 1; i < Q; ++i)
+        {
+            x = x + p.DD[i];
+            d[i] = fmaxf(d[i], x);
+            x = d[i];
+        }
+        more = __any_sync(FULL, d[Q - 1] > old);
+    }
+    /* more than two warps: a warp whose last D rose has to be re-read by its right neighbour (rare; exact lazy rounds) */
+    if (!final_d)
+    {
+        float bef = before;
+        for (int round = 0;; ++round)
+        {
+            const float after = __shfl_sync(FULL, d[Q - 1], 31);
+            if constexpr (CL == 2)
+            {
+                const float pay_c[8] = {after > bef ? 1.0f : 0.0f, d[Q - 1], 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+                xs = grp.exchange(gw, lane, pay_c);
+                float rose = sh.xch[xs][0][0];
+#pragma unroll
+                for (int w = 1; w < TW; ++w) rose = fmaxf(rose, sh.xch[xs][w][0]);
+                if (rose == 0.0f) break;
+                din0 = gw ? sh.xch[xs][gw - 1][1] : NEG_INF;
+            }
+            else
+            {
+                const int b = round & 1;
+                /* publish the new end first: if any warp rose, everybody re-reads its left neighbour after the OR */
+                if (lane == 31) sh.d_last[b][gw] = d[Q - 1];
+                if (!__syncthreads_or(after > bef)) break;
+                din0 = gw ? sh.d_last[b][gw - 1] : NEG_INF;
+            }
+            bef = after;
+            for (;;)
+            {
+                old = d[Q - 1];
+                din = __shfl_up_sync(FULL, old, 1);
+                if (lane == 0) din = din0;
+                float x = lane == 0 ? fmaxf(vm_prev + p.MD[0], din0 + p.DD[0]) : din + p.DD[0];
+                d[0] = fmaxf(d[0], x);
+                x = d[0];
+#pragma unroll
+                for (int i = 1; i < Q; ++i)
+                {
+                    x = x + p.DD[i];
+                    d[i] = fmaxf(d[i], x);
+                    x = d[i];
+                }
+                if (!__any_sync(FULL, d[Q - 1] > old)) break;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < Q; ++i)
+    {
+        const float pd = i == 0 ? din : d[i - 1];
+        tm[R][i] = fmaxf(tm[R][i], pd + p.DM[i]);
     }
     E_out = E;
     vC_out = vC;
@@ -268,6 +553,12 @@ k_score_mw(const float *__restrict__ emis, const float *__restrict__ trans, cons
         const ProfMeta pm = metas[prof];
         NodeParams<Q> p;
         load_params<Q>(p, trans + pm.trans_off, 32 * Q * TW, gw * 32 * Q + lane * Q);
+        CarryBound cb = {NEG_INF, NEG_INF, NEG_INF};
+        if (TW > 2 && lane < TW)
+        {
+            const float *b = trans + pm.trans_off + 8 * (32 * Q * TW); /* [3][TW] after the eight parameter arrays */
+            cb.S = __ldg(b + lane), cb.md0 = __ldg(b + TW + lane), cb.dd0 = __ldg(b + 2 * TW + lane);
+        }
         const float *emis_lane = emis + pm.emis_off + gw * 256 + lane * 4;
         const SeqMeta sm = seqs[s];
         const RowRec *recs = rows + (size_t)pm.null_id * total_recs + sm.rec_off;
@@ -307,20 +598,26 @@ k_score_mw(const float *__restrict__ emis, const float *__restrict__ trans, cons
 
         float E = NEG_INF, vC = NEG_INF;
         uint32_t j = 1;
+#if DCP_MW_V2
+#define MW_ROW mw_row2
+#else
+#define MW_ROW mw_row
+#endif
 #define MW_ARGS(jj) recs + min((uint32_t)(jj) + 1u, L), wc + min((uint32_t)(jj) + 3u, L), gw, lane, (int)((jj)&1u), grp
         for (; j + 4 <= L; j += 5)
         {
-            mw_row<W, CL, 0, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j), NB, JB, EB, cE, cX, E, vC);
-            mw_row<W, CL, 1, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 1), NB, JB, EB, cE, cX, E, vC);
-            mw_row<W, CL, 2, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 2), NB, JB, EB, cE, cX, E, vC);
-            mw_row<W, CL, 3, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 3), NB, JB, EB, cE, cX, E, vC);
-            mw_row<W, CL, 4, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 4), NB, JB, EB, cE, cX, E, vC);
+            MW_ROW<W, CL, 0, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j), NB, JB, EB, cE, cX, cb, E, vC);
+            MW_ROW<W, CL, 1, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 1), NB, JB, EB, cE, cX, cb, E, vC);
+            MW_ROW<W, CL, 2, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 2), NB, JB, EB, cE, cX, cb, E, vC);
+            MW_ROW<W, CL, 3, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 3), NB, JB, EB, cE, cX, cb, E, vC);
+            MW_ROW<W, CL, 4, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 4), NB, JB, EB, cE, cX, cb, E, vC);
         }
-        if (j <= L) mw_row<W, CL, 0, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j), NB, JB, EB, cE, cX, E, vC);
-        if (j + 1 <= L) mw_row<W, CL, 1, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 1), NB, JB, EB, cE, cX, E, vC);
-        if (j + 2 <= L) mw_row<W, CL, 2, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 2), NB, JB, EB, cE, cX, E, vC);
-        if (j + 3 <= L) mw_row<W, CL, 3, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 3), NB, JB, EB, cE, cX, E, vC);
+        if (j <= L) MW_ROW<W, CL, 0, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j), NB, JB, EB, cE, cX, cb, E, vC);
+        if (j + 1 <= L) MW_ROW<W, CL, 1, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 1), NB, JB, EB, cE, cX, cb, E, vC);
+        if (j + 2 <= L) MW_ROW<W, CL, 2, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 2), NB, JB, EB, cE, cX, cb, E, vC);
+        if (j + 3 <= L) MW_ROW<W, CL, 3, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 3), NB, JB, EB, cE, cX, cb, E, vC);
 #undef MW_ARGS
+#undef MW_ROW
         if (gw == 0 && lane == 0) alt_out[(size_t)s * nprof + prof] = fmaxf(E + ET, vC + CT);
     }
 }

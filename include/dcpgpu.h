@@ -353,8 +353,8 @@ long dcpgpu_prod_row(struct dcpgpu_result const *, struct dcpgpu_db const *, uin
 
 /* Measured FP32 issue peaks of `device` (the roofline denominators of the score kernel):
  * out[0] FADD, out[1] FMNMX3, out[2] the DP cell's 2:1 FADD:FMNMX3 mix, in 1e9 lane-instructions/s;
- * out[3] = SM count. */
-enum rc dcpgpu_microbench_alu(int device, double out[4]);
+ * out[3] = SM count; out[4], out[5] = SM clock in MHz measured inside the mix / FADD kernel. */
+enum rc dcpgpu_microbench_alu(int device, double out[6]);
 
 char const *dcpgpu_last_error(void); /* thread-local message of the last failure */
 
