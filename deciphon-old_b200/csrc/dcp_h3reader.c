@@ -135,7 +135,12 @@ enum rc protein_h3reader_next(struct protein_h3reader *r)
             break;
     }
     if (r->leng == 0) return parse_error(r, "LENG missing or zero");
-    if (!r->acc[0]) strncpy(r->acc, r->name, sizeof r->acc - 1);
+    if (!r->acc[0])
+    {
+        /* no ACC line: the name stands in, cut to PROFILE_ACC_SIZE (limits.h:13) */
+        memcpy(r->acc, r->name, sizeof r->acc - 1);
+        r->acc[sizeof r->acc - 1] = '\0';
+    }
     if (!next_line(r)) return parse_error(r, "missing transition header"); /* m->m m->i ... */
 
     enum rc rc = protein_model_setup(r->model, r->leng);

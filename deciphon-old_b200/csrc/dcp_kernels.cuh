@@ -79,6 +79,7 @@ __device__ __forceinline__ void load_row_special(const RowRec *__restrict__ r, f
 #ifndef DCP_Q7_LOAD8
 #define DCP_Q7_LOAD8 0
 #endif
+
 /* L1 policy experiments for the emission lines, by window length l (0..4 = 1..5 nt):
  * 0 default everywhere; 1: 5-nt lines no_allocate; 2: 4- and 5-nt lines no_allocate;
  * 3: 1..3-nt lines evict_last, 5-nt no_allocate; 4: 1..3 evict_last, 4..5 no_allocate */

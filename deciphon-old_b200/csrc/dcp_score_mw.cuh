@@ -275,8 +275,11 @@ __device__ __forceinline__ void mw_row(float (&tm)[5][Q], float (&ti)[5][Q], flo
 #ifndef DCP_MW_V2
 #define DCP_MW_V2 1
 #endif
+/* One-block groups: skipping the second barrier gains 5 % where 12 warps are resident (168 registers: (3,6,4) 339 ->
+ * 357, (4,5,3) 343 -> 361 G padded cells/s) and loses 6..9 % in the 255-register classes ((4,8,2) 468 -> 427, (8,8,1)
+ * 417 -> 394: the three bound registers push the row into spills) -- so it is on for the former only. */
 #ifndef DCP_CARRY_BOUND_CL1
-#define DCP_CARRY_BOUND_CL1 0 /* one-block groups: skipping their second barrier measured no gain */
+#define DCP_CARRY_BOUND_CL1(W, BPS) ((W) * (BPS) > 8)
 #endif
 /*
  * mw_row2: the same row as mw_row, laid out for the instruction scheduler.  ptxas schedules inside basic blocks, and
@@ -286,7 +289,7 @@ __device__ __forceinline__ void mw_row(float (&tm)[5][Q], float (&ti)[5][Q], flo
  * rendezvous, the B->M part after it -- sits in the same block, so it fills the chain's latency.  Values are
  * bit-identical: only maxima are re-associated, every sum is still (V_src + t).
  */
-template <int W, int CL, int R, int Q>
+template <int W, int CL, int R, int Q, int BPS>
 __device__ __forceinline__ void mw_row2(float (&tm)[5][Q], float (&ti)[5][Q], float (&tx)[5],
                                         const NodeParams<Q> &p, RowState<Q> &rs,
                                         const float *__restrict__ emis_lane, const RowRec *__restrict__ rec_next,
@@ -410,7 +413,7 @@ __device__ __forceinline__ void mw_row2(float (&tm)[5][Q], float (&ti)[5][Q], fl
         for (int w = 1; w < TW; ++w) E = fmaxf(E, sh.e_warp[par][w]);
         vN = sh.v_spec[par][0], vJ = sh.v_spec[par][1], vC = sh.v_spec[par][2];
         din0 = gw ? sh.d_loc[par][gw - 1] : NEG_INF;
-        if (DCP_CARRY_BOUND_CL1 && TW > 2)
+        if (DCP_CARRY_BOUND_CL1(W, BPS) && TW > 2)
         {
             const int w = min(max(lane, 1), TW - 1);
             final_d = carry_cannot_rise<TW>(cb, lane, sh.vm_last[par][w - 1], sh.d_loc[par][w - 1], sh.d_loc[par][w]);
@@ -599,23 +602,23 @@ k_score_mw(const float *__restrict__ emis, const float *__restrict__ trans, cons
         float E = NEG_INF, vC = NEG_INF;
         uint32_t j = 1;
 #if DCP_MW_V2
-#define MW_ROW mw_row2
+#define MW_ROW(WW, CC, RR, QQ) mw_row2<WW, CC, RR, QQ, BPS>
 #else
-#define MW_ROW mw_row
+#define MW_ROW(WW, CC, RR, QQ) mw_row<WW, CC, RR, QQ>
 #endif
 #define MW_ARGS(jj) recs + min((uint32_t)(jj) + 1u, L), wc + min((uint32_t)(jj) + 3u, L), gw, lane, (int)((jj)&1u), grp
         for (; j + 4 <= L; j += 5)
         {
-            MW_ROW<W, CL, 0, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j), NB, JB, EB, cE, cX, cb, E, vC);
-            MW_ROW<W, CL, 1, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 1), NB, JB, EB, cE, cX, cb, E, vC);
-            MW_ROW<W, CL, 2, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 2), NB, JB, EB, cE, cX, cb, E, vC);
-            MW_ROW<W, CL, 3, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 3), NB, JB, EB, cE, cX, cb, E, vC);
-            MW_ROW<W, CL, 4, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 4), NB, JB, EB, cE, cX, cb, E, vC);
+            MW_ROW(W, CL, 0, Q)(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j), NB, JB, EB, cE, cX, cb, E, vC);
+            MW_ROW(W, CL, 1, Q)(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 1), NB, JB, EB, cE, cX, cb, E, vC);
+            MW_ROW(W, CL, 2, Q)(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 2), NB, JB, EB, cE, cX, cb, E, vC);
+            MW_ROW(W, CL, 3, Q)(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 3), NB, JB, EB, cE, cX, cb, E, vC);
+            MW_ROW(W, CL, 4, Q)(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 4), NB, JB, EB, cE, cX, cb, E, vC);
         }
-        if (j <= L) MW_ROW<W, CL, 0, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j), NB, JB, EB, cE, cX, cb, E, vC);
-        if (j + 1 <= L) MW_ROW<W, CL, 1, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 1), NB, JB, EB, cE, cX, cb, E, vC);
-        if (j + 2 <= L) MW_ROW<W, CL, 2, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 2), NB, JB, EB, cE, cX, cb, E, vC);
-        if (j + 3 <= L) MW_ROW<W, CL, 3, Q>(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 3), NB, JB, EB, cE, cX, cb, E, vC);
+        if (j <= L) MW_ROW(W, CL, 0, Q)(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j), NB, JB, EB, cE, cX, cb, E, vC);
+        if (j + 1 <= L) MW_ROW(W, CL, 1, Q)(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 1), NB, JB, EB, cE, cX, cb, E, vC);
+        if (j + 2 <= L) MW_ROW(W, CL, 2, Q)(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 2), NB, JB, EB, cE, cX, cb, E, vC);
+        if (j + 3 <= L) MW_ROW(W, CL, 3, Q)(tm, ti, tx, p, rs, emis_lane, MW_ARGS(j + 3), NB, JB, EB, cE, cX, cb, E, vC);
 #undef MW_ARGS
 #undef MW_ROW
         if (gw == 0 && lane == 0) alt_out[(size_t)s * nprof + prof] = fmaxf(E + ET, vC + CT);

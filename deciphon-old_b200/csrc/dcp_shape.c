@@ -23,7 +23,7 @@
 static const struct dcp_class kClasses[] = {DCP_CLASS_TABLE(ROW)};
 #undef ROW
 enum { kNumClasses = sizeof kClasses / sizeof kClasses[0] };
-_Static_assert(kNumClasses <= DCP_MAX_CLASSES, "raise DCP_MAX_CLASSES");
+_Static_assert((int)kNumClasses <= (int)DCP_MAX_CLASSES, "raise DCP_MAX_CLASSES");
 
 unsigned dcp_num_classes(void) { return kNumClasses; }
 struct dcp_class const *dcp_class_at(unsigned cls) { return cls < kNumClasses ? &kClasses[cls] : NULL; }
