@@ -22,23 +22,23 @@
 #define DCP_CLASS_TABLE(X)                                                                                      \
     /* one warp per pair: 16 / 12 / 8 resident warps per SM */                                                  \
     X(1, 2, 16, 406) X(1, 4, 12, 596) X(1, 5, 8, 573) X(1, 6, 8, 644) X(1, 8, 8, 726)                           \
-    /* two warps: 12 resident warps per SM with 5 nodes per lane (168 registers, no spills), else 8 */          \
-    X(2, 5, 6, 452) X(2, 6, 4, 485) X(2, 7, 4, 515) X(2, 8, 4, 560)                                             \
+    /* two warps: 12 resident warps per SM with 5 nodes per lane (168 registers), else 8 */                     \
+    X(2, 5, 6, 467) X(2, 6, 4, 485) X(2, 7, 4, 504) X(2, 8, 4, 560)                                             \
     /* three warps: 12 resident warps (6 at 255 registers leave the schedulers idle) */                         \
-    X(3, 6, 4, 357)                                                                                             \
+    X(3, 6, 4, 382)                                                                                             \
     /* four warps */                                                                                            \
-    X(4, 5, 3, 361) X(4, 6, 2, 399) X(4, 7, 2, 430) X(4, 8, 2, 468)                                             \
-    /* five to eight warps: a block of 8 warps fills the SM, fewer leave issue slots idle */                    \
-    X(6, 6, 2, 312) X(5, 8, 1, 285) X(8, 6, 1, 340) X(8, 7, 1, 385) X(8, 8, 1, 417)                             \
+    X(4, 5, 3, 393) X(4, 6, 2, 404) X(4, 7, 2, 436) X(4, 8, 2, 468)                                             \
+    /* six and eight warps: 12 or 8 resident warps per SM; five or seven leave issue slots idle */                       \
+    X(6, 6, 2, 359) X(8, 6, 1, 355) X(8, 7, 1, 391) X(8, 8, 1, 417)                             \
     /* two blocks of a cluster */                                                                               \
-    X(16, 6, 1, 257) X(14, 8, 1, 256) X(16, 8, 1, 272)
+    X(16, 6, 1, 265) X(16, 8, 1, 308)
 
 /* Measured and left out (rates before the straight-line row layout, which lifted every multi-warp class by 5..30 %;
  * each loses to a neighbour in padded width / rate):
  * (1,1,16: 193) (1,3,12: 437) (1,7,8: 618 -- see DESIGN.md 6.2: ptxas sinks the next row's emission loads to mid-row,
  * long-scoreboard stalls 0.46 per issue against 0.07 at 8 nodes per lane) (2,5,4: 332) (2,6,6: 408,
  * spills) (3,5,4: 311) (3,6,2: 294) (3,7,2: 315) (3,8,2: 342) (4,5,2: 269) (4,6,3: 311, spills) (5,5,2: 315)
- * (5,6,2: 286) (6,5,2: 286) (6,8,1: 320) (7,8,1: 352) (8,5,1: 259) (10,8: 197 with the new layout) (12,8: 195) (16,5: 171) (16,7: 211);
+ * (5,6,2: 286) (6,5,2: 286) (6,8,1: 320) (7,8,1: 352) (8,5,1: 259) (5,8,1: 285 and 14,8: 266 with the new layout, 10,8: 197) (12,8: 195) (16,5: 171) (16,7: 211);
  * profiles/r02_class_sweep_table.jsonl */
 
 #endif

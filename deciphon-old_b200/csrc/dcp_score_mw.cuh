@@ -55,10 +55,11 @@ __device__ __forceinline__ bool carry_cannot_rise(const CarryBound &cb, int lane
 
 struct MwShared
 {
+    alignas(16) float4 rec[2][kMaxGroupWarps]; /* mw_row2: per-warp record of the row, by row parity */
+    alignas(16) float v_spec[2][4];            /* V_N, V_J, V_C of the row */
     float d_loc[2][kMaxGroupWarps]; /* ends of the warps' own D chains, by row parity */
     float vm_last[2][kMaxGroupWarps], vi_last[2][kMaxGroupWarps], e_warp[2][kMaxGroupWarps];
     float d_last[2][kMaxGroupWarps];
-    float v_spec[2][4]; /* V_N, V_J, V_C of the row */
     int flag[2][2];
     unsigned long long item;
     alignas(16) float xch[2][kMaxGroupWarps][8]; /* 2-block groups: Group::exchange buffers ... */
@@ -385,38 +386,63 @@ __device__ __forceinline__ void mw_row2(float (&tm)[5][Q], float (&ti)[5][Q], fl
         const float xN = __shfl_sync(FULL, vx, 0), xJ = __shfl_sync(FULL, vx, 1), xC = __shfl_sync(FULL, vx, 2);
         const float pay_a[8] = {vm[Q - 1], vi[Q - 1], ew, d[Q - 1], xN, xJ, xC, 0.0f};
         xs = grp.exchange(gw, lane, pay_a);
-        const float(*x)[8] = sh.xch[xs];
-        if (lane == 0 && gw) vm_prev = x[gw - 1][0], vi_prev = x[gw - 1][1];
-        E = x[0][2];
-#pragma unroll
-        for (int w = 1; w < TW; ++w) E = fmaxf(E, x[w][2]);
-        vN = x[0][4], vJ = x[0][5], vC = x[0][6];
-        din0 = gw ? x[gw - 1][3] : NEG_INF;
+        const float4 *x = reinterpret_cast<const float4 *>(sh.xch[xs]); /* two float4 per warp */
+        /* lane w holds warp w's record; E is one redux over the per-warp maxima instead of TW loads and maxima */
+        const float4 mine = x[2 * min(lane, TW - 1)];
+        E = warp_max(lane < TW ? mine.z : NEG_INF);
+        const float4 left = x[2 * max(gw - 1, 0)], spec = x[1];
+        if (lane == 0 && gw) vm_prev = left.x, vi_prev = left.y;
+        vN = spec.x, vJ = spec.y, vC = spec.z;
+        din0 = gw ? left.w : NEG_INF;
         if (DCP_CARRY_BOUND)
         {
-            const int w = min(max(lane, 1), TW - 1);
-            final_d = carry_cannot_rise<TW>(cb, lane, x[w - 1][0], x[w - 1][3], x[w][3]);
+            const float4 lw = x[2 * (min(max(lane, 1), TW - 1) - 1)];
+            final_d = carry_cannot_rise<TW>(cb, lane, lw.x, lw.w, mine.w);
         }
     }
     else
     {
-        if (lane == 31)
+        if constexpr (Q < 8)
         {
-            sh.vm_last[par][gw] = vm[Q - 1], sh.vi_last[par][gw] = vi[Q - 1];
-            sh.e_warp[par][gw] = ew, sh.d_loc[par][gw] = d[Q - 1];
+            /* one 16-byte record per warp: {V_M, V_I of its last node, its maximum of V_M, the end of its own D chain};
+             * lane w reads warp w's record and E is one redux over the per-warp maxima.  +4..9 % below 8 nodes per lane;
+             * at 8 per lane (255 registers, no slack) it costs 4..8 %, so those classes keep the scalar form below */
+            if (lane == 31) sh.rec[par][gw] = make_float4(vm[Q - 1], vi[Q - 1], ew, d[Q - 1]);
+            if (gw == 0 && lane < 3) sh.v_spec[par][lane] = vx;
+            __syncthreads();
+            const float4 mine = sh.rec[par][min(lane, TW - 1)];
+            E = warp_max(lane < TW ? mine.z : NEG_INF);
+            const float4 left = sh.rec[par][max(gw - 1, 0)];
+            const float4 spec = *reinterpret_cast<const float4 *>(sh.v_spec[par]);
+            if (lane == 0 && gw) vm_prev = left.x, vi_prev = left.y;
+            vN = spec.x, vJ = spec.y, vC = spec.z;
+            din0 = gw ? left.w : NEG_INF;
+            if (DCP_CARRY_BOUND_CL1(W, BPS) && TW > 2)
+            {
+                const float4 lw = sh.rec[par][min(max(lane, 1), TW - 1) - 1];
+                final_d = carry_cannot_rise<TW>(cb, lane, lw.x, lw.w, mine.w);
+            }
         }
-        if (gw == 0 && lane < 3) sh.v_spec[par][lane] = vx;
-        __syncthreads();
-        if (lane == 0 && gw) vm_prev = sh.vm_last[par][gw - 1], vi_prev = sh.vi_last[par][gw - 1];
-        E = sh.e_warp[par][0];
-#pragma unroll
-        for (int w = 1; w < TW; ++w) E = fmaxf(E, sh.e_warp[par][w]);
-        vN = sh.v_spec[par][0], vJ = sh.v_spec[par][1], vC = sh.v_spec[par][2];
-        din0 = gw ? sh.d_loc[par][gw - 1] : NEG_INF;
-        if (DCP_CARRY_BOUND_CL1(W, BPS) && TW > 2)
+        else
         {
-            const int w = min(max(lane, 1), TW - 1);
-            final_d = carry_cannot_rise<TW>(cb, lane, sh.vm_last[par][w - 1], sh.d_loc[par][w - 1], sh.d_loc[par][w]);
+            if (lane == 31)
+            {
+                sh.vm_last[par][gw] = vm[Q - 1], sh.vi_last[par][gw] = vi[Q - 1];
+                sh.e_warp[par][gw] = ew, sh.d_loc[par][gw] = d[Q - 1];
+            }
+            if (gw == 0 && lane < 3) sh.v_spec[par][lane] = vx;
+            __syncthreads();
+            if (lane == 0 && gw) vm_prev = sh.vm_last[par][gw - 1], vi_prev = sh.vi_last[par][gw - 1];
+            E = sh.e_warp[par][0];
+#pragma unroll
+            for (int w = 1; w < TW; ++w) E = fmaxf(E, sh.e_warp[par][w]);
+            vN = sh.v_spec[par][0], vJ = sh.v_spec[par][1], vC = sh.v_spec[par][2];
+            din0 = gw ? sh.d_loc[par][gw - 1] : NEG_INF;
+            if (DCP_CARRY_BOUND_CL1(W, BPS) && TW > 2)
+            {
+                const int w = min(max(lane, 1), TW - 1);
+                final_d = carry_cannot_rise<TW>(cb, lane, sh.vm_last[par][w - 1], sh.d_loc[par][w - 1], sh.d_loc[par][w]);
+            }
         }
     }
 
