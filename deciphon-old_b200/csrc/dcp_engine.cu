@@ -208,11 +208,17 @@ extern "C" enum rc dcpgpu_db_new(struct dcpgpu_db **out, int device)
         e = cudaMemPoolSetAttribute(db->pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&db->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < dcpgpu_db::kSide && e == cudaSuccess; ++i)
+    {
+        e = cudaStreamCreateWithFlags(&db->side[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&db->join_ev[i], cudaEventDisableTiming);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&db->fork_ev, cudaEventDisableTiming);
     if (e != cudaSuccess)
     {
         dcp_set_error(cudaGetErrorString(e));
-        if (db->pool) cudaMemPoolDestroy(db->pool);
-        delete db;
+        db->owns_profs = false;
+        dcpgpu_db_del(db);
         return RC_EFAIL;
     }
     *out = db;
@@ -473,6 +479,12 @@ extern "C" void dcpgpu_db_del(struct dcpgpu_db *db)
         db_release_device(db);
         if (db->h_stage) cudaFreeHost(db->h_stage);
         if (db->stream) cudaStreamDestroy(db->stream);
+        for (int i = 0; i < dcpgpu_db::kSide; ++i)
+        {
+            if (db->side[i]) cudaStreamSynchronize(db->side[i]), cudaStreamDestroy(db->side[i]);
+            if (db->join_ev[i]) cudaEventDestroy(db->join_ev[i]);
+        }
+        if (db->fork_ev) cudaEventDestroy(db->fork_ev);
         if (db->pool) cudaMemPoolDestroy(db->pool);
     }
     delete db;
@@ -653,16 +665,24 @@ extern "C" enum rc dcpgpu_scan_resident(struct dcpgpu_db *db, struct dcpgpu_seqs
     uint64_t cells = 0;
     ScoreArgs sa = {db->d_emis, db->d_trans, db->d_metas, nullptr, 0, sq->d_metas, nseq, total_recs,
                     b_rows.as<RowRec>(), b_wcodes.as<uint16_t>(), b_spec.as<float>(), res->d_alt, nprof, nullptr, seq_tile};
+    /* one persistent launch per kernel class, spread over the main and the side streams: every launch sizes its grid
+     * to fill the GPU, so they still run one after the other, but a class's blocks start as the previous class's
+     * blocks run out of work (the tail of a launch is up to one work item long) */
+    StreamFan fan(db);
+    static const bool fan_out = !(getenv("DCPGPU_ONE_STREAM") && atoi(getenv("DCPGPU_ONE_STREAM")) != 0);
+    if (fan_out) CU_TRY(fan.fork());
     for (int q = 0; q < kMaxClasses; ++q)
     {
         if (db->class_list[q].empty()) continue;
         const dcp_class &kc = *dcp_class_at(q);
         sa.class_profs = db->d_class[q], sa.n_class = (uint32_t)db->class_list[q].size();
         sa.counter = b_counter.as<unsigned long long>() + q;
-        CU_TRY(kc.tw == 1 ? dcp_launch_score(kc, db->sm_count, st, sa) : dcp_launch_score_mw(kc, db->sm_count, st, sa));
+        cudaStream_t cs = fan_out ? fan.next() : st;
+        CU_TRY(kc.tw == 1 ? dcp_launch_score(kc, db->sm_count, cs, sa) : dcp_launch_score_mw(kc, db->sm_count, cs, sa));
         launches++;
         for (uint32_t id : db->class_list[q]) cells += (uint64_t)db->metas[id].M * sq->total;
     }
+    if (fan_out) CU_TRY(fan.join());
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaEventRecord(ev[2], st));
 

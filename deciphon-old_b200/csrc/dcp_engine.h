@@ -77,6 +77,11 @@ struct dcpgpu_db
     int device = 0; /* -1: host-only view (the global profile list of a multi-device database) */
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    /* side streams: the per-class launches of a scan are spread over them so that one class's tail (persistent
+     * blocks running out of work, or a handful of hits to trace) overlaps the next class's start */
+    static constexpr int kSide = 3;
+    cudaStream_t side[kSide] = {nullptr, nullptr, nullptr};
+    cudaEvent_t fork_ev = nullptr, join_ev[kSide] = {nullptr, nullptr, nullptr};
     cudaMemPool_t pool = nullptr; /* the engine's own stream-ordered pool (scratch of scans, results) */
     bool committed = false;
     bool owns_profs = true;        /* false: shard of a dcpgpu_mdb, profiles belong to its view */
@@ -176,6 +181,41 @@ struct ScoreArgs
 };
 cudaError_t dcp_launch_score(const dcp_class &c, int sm_count, cudaStream_t st, const ScoreArgs &a);    /* tw = 1 */
 cudaError_t dcp_launch_score_mw(const dcp_class &c, int sm_count, cudaStream_t st, const ScoreArgs &a); /* tw > 1 */
+
+/* Launches of a phase spread over the database's main stream and its side streams: fork() makes the side streams
+ * wait for what the main stream has queued so far, next() hands out the streams round-robin, join() makes the main
+ * stream wait for everything queued on the side streams. */
+struct StreamFan
+{
+    dcpgpu_db *db;
+    int n = 0;
+    bool used[dcpgpu_db::kSide] = {false, false, false};
+    explicit StreamFan(dcpgpu_db *d) : db(d) {}
+    cudaError_t fork()
+    {
+        cudaError_t e = cudaEventRecord(db->fork_ev, db->stream);
+        for (int i = 0; i < dcpgpu_db::kSide && e == cudaSuccess; ++i) e = cudaStreamWaitEvent(db->side[i], db->fork_ev, 0);
+        return e;
+    }
+    cudaStream_t next()
+    {
+        const int k = n++ % (dcpgpu_db::kSide + 1);
+        if (k == 0) return db->stream;
+        used[k - 1] = true;
+        return db->side[k - 1];
+    }
+    cudaError_t join()
+    {
+        cudaError_t e = cudaSuccess;
+        for (int i = 0; i < dcpgpu_db::kSide && e == cudaSuccess; ++i)
+            if (used[i])
+            {
+                e = cudaEventRecord(db->join_ev[i], db->side[i]);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(db->stream, db->join_ev[i], 0);
+            }
+        return e;
+    }
+};
 
 /* dcp_trace.cu */
 enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const RowRec *d_rows,

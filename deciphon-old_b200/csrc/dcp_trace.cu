@@ -872,8 +872,13 @@ enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const
         CU_TRY(b_err.alloc(sizeof(uint32_t), db));
         CU_TRY(cudaMemcpyAsync(b_jobs.p, sorted.data(), nj * sizeof(TraceJob), cudaMemcpyHostToDevice, st));
         CU_TRY(cudaMemsetAsync(b_err.p, 0, sizeof(uint32_t), st));
+        /* one launch per kernel class, side by side on the main and side streams: a class often holds a handful of
+         * hits, and a trace launch lasts as long as its longest sequence however few hits it has */
+        StreamFan fan(db);
+        CU_TRY(fan.fork());
         for (uint32_t a = 0; a < nj;)
         {
+            cudaStream_t st = fan.next();
             uint32_t cls = db->metas[sorted[a].prof].cls, b = a;
             while (b < nj && db->metas[sorted[b].prof].cls == cls) ++b;
             {
@@ -894,6 +899,7 @@ enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const
             (*launches)++;
             a = b;
         }
+        CU_TRY(fan.join());
         CU_TRY(cudaGetLastError());
         k_walk<<<(nj + 63) / 64, 64, 0, st>>>(db->d_metas, sq->d_metas, b_jobs.as<TraceJob>(), nj,
                                               b_cells.as<uint16_t>(), b_rows.as<uint32_t>(), 0, b_n.as<uint32_t>(),
