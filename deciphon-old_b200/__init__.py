@@ -37,7 +37,7 @@ EXPORTS = [
     "dcpgpu_result_nseqs", "dcpgpu_result_nprofiles", "dcpgpu_result_null_loglik", "dcpgpu_result_alt_loglik",
     "dcpgpu_result_hit", "dcpgpu_result_nhits", "dcpgpu_result_hit_at", "dcpgpu_result_hits", "dcpgpu_result_steps",
     "dcpgpu_result_timing",
-    "dcpgpu_result_del", "dcpgpu_shard_profiles", "dcpgpu_kernel_shape", "dcpgpu_profile_cost", "dcpgpu_shard_sequences",
+    "dcpgpu_result_del", "dcpgpu_shard_profiles", "dcpgpu_kernel_shape", "dcpgpu_kernel_padded_width", "dcpgpu_profile_cost", "dcpgpu_shard_sequences",
     "dcpgpu_mdb_new", "dcpgpu_mdb_add", "dcpgpu_mdb_commit", "dcpgpu_mdb_view", "dcpgpu_mdb_ndevices",
     "dcpgpu_mdb_nprofiles", "dcpgpu_mdb_axis", "dcpgpu_mdb_imbalance", "dcpgpu_mdb_device_of", "dcpgpu_mdb_device_bytes",
     "dcpgpu_mdb_scan", "dcpgpu_mdb_del", "dcpgpu_result_nparts", "dcpgpu_result_part_timing", "dcpgpu_prod_fwrite_header", "dcpgpu_prod_fwrite",
@@ -147,6 +147,8 @@ def lib():
     L.dcpgpu_shard_profiles.argtypes = [u, vp, u, vp]
     L.dcpgpu_kernel_shape.argtypes = [u, vp, vp, vp]
     L.dcpgpu_kernel_shape.restype = C.c_int
+    L.dcpgpu_kernel_padded_width.argtypes = [u]
+    L.dcpgpu_kernel_padded_width.restype = u
     L.dcpgpu_profile_cost.argtypes = [u]
     L.dcpgpu_profile_cost.restype = C.c_double
     L.dcpgpu_shard_sequences.argtypes = [u, vp, u, vp]
@@ -238,6 +240,11 @@ def kernel_shape(core_size):
     w, q, b = C.c_uint(), C.c_uint(), C.c_uint()
     _check(lib().dcpgpu_kernel_shape(core_size, C.byref(w), C.byref(q), C.byref(b)))
     return w.value, q.value, b.value
+
+
+def kernel_padded_width(core_size):
+    """Nodes the kernels compute for a profile of `core_size` nodes (its kernel class's capacity)."""
+    return int(lib().dcpgpu_kernel_padded_width(int(core_size)))
 
 
 def shard_profiles(core_sizes, nshards):

@@ -99,18 +99,19 @@ __global__ void k_null(const SeqMeta *__restrict__ seqs, uint32_t nseq, uint32_t
  * (node k-1 = warp * 32 Q + lane * Q + sub sits in half sub/4, float sub%4 of its lane; pads are -inf).
  */
 __global__ void k_layout(const float *__restrict__ raw, float *__restrict__ out, uint32_t M, uint32_t Q, uint32_t QP,
-                         uint32_t W)
+                         uint32_t W, uint32_t LN)
 {
-    const uint32_t ROW = 32 * QP * W;
+    /* LN lanes per pair (32, or 16 for the half-warp classes): a line is [warp][half][LN lanes][4] */
+    const uint32_t ROW = LN * QP * W;
     const size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= (size_t)kTab * ROW) return;
     const uint32_t code = (uint32_t)(x / ROW), pos = (uint32_t)(x % ROW);
-    const uint32_t warp = pos / (32 * QP), r = pos % (32 * QP);
-    const uint32_t half = r / 128, lane = (r % 128) / 4, sub = half * 4 + (r % 4);
+    const uint32_t warp = pos / (LN * QP), r = pos % (LN * QP);
+    const uint32_t half = r / (LN * 4), lane = (r % (LN * 4)) / 4, sub = half * 4 + (r % 4);
     float v = NEG_INF;
     if (sub < Q)
     {
-        const uint32_t k = warp * 32 * Q + lane * Q + sub;
+        const uint32_t k = warp * LN * Q + lane * Q + sub;
         if (k < M) v = raw[(size_t)k * kTab + code];
     }
     out[x] = v;
@@ -285,11 +286,11 @@ static enum rc db_take(struct dcpgpu_db *db, struct protein_profile *prof, take_
     return RC_OK;
 }
 
-static void kernel_shape(uint32_t M, uint32_t &Q, uint32_t &W, uint32_t &cls)
+static void kernel_shape(uint32_t M, uint32_t &Q, uint32_t &W, uint32_t &cls, uint32_t &LN)
 {
     cls = dcp_kernel_class(M);
     const dcp_class *c = dcp_class_at(cls);
-    Q = c->q, W = c->tw;
+    Q = c->q, W = c->tw ? c->tw : 1, LN = c->tw ? 32 : 16; /* tw = 0: two pairs per warp, 16 lanes each */
 }
 
 namespace
@@ -336,16 +337,16 @@ enum rc db_commit(dcpgpu_db *db)
     for (size_t i = 0; i < nprof; ++i)
     {
         uint32_t M = db->profs[i]->core_size;
-        uint32_t Q, W, cls;
-        kernel_shape(M, Q, W, cls);
+        uint32_t Q, W, cls, LN;
+        kernel_shape(M, Q, W, cls, LN);
         uint32_t QP = Q <= 4 ? 4 : 8;
         ProfMeta &m = db->metas[i];
         m.M = M, m.Q = Q, m.QP = QP, m.null_id = db->null_id[i];
-        m.W = W, m.cls = cls;
+        m.W = W, m.cls = cls, m.LN = LN, m.pad = 0;
         m.emis_off = emis_floats;
         m.trans_off = trans_floats;
-        emis_floats += (uint64_t)kTab * 32 * QP * W;
-        trans_floats += (uint64_t)8 * 32 * Q * W + 3 * W; /* + the carry bounds of the W warps (dcp_score_mw.cuh) */
+        emis_floats += (uint64_t)kTab * LN * QP * W;
+        trans_floats += (uint64_t)8 * LN * Q * W + 3 * W; /* + the carry bounds of the W warps (dcp_score_mw.cuh) */
         db->class_list[m.cls].push_back((uint32_t)i);
         max_M = std::max(max_M, M);
     }
@@ -378,11 +379,11 @@ enum rc db_commit(dcpgpu_db *db)
         memcpy(stg.host[b], p->match_emission, raw * sizeof(float));
         CU_TRY(cudaMemcpyAsync(stg.dev[b], stg.host[b], raw * sizeof(float), cudaMemcpyHostToDevice, db->stream));
         CU_TRY(cudaEventRecord(stg.freed[b], db->stream));
-        const uint32_t ROW = 32 * m.QP * m.W;
+        const uint32_t ROW = m.LN * m.QP * m.W;
         const size_t out = (size_t)kTab * ROW;
         k_layout<<<(unsigned)((out + 255) / 256), 256, 0, db->stream>>>(stg.dev[b], db->d_emis + m.emis_off, m.M, m.Q,
-                                                                         m.QP, m.W);
-        const uint32_t NP = 32 * m.Q * m.W;
+                                                                         m.QP, m.W, m.LN);
+        const uint32_t NP = m.LN * m.Q * m.W;
         float *tr = tr_all.data() + m.trans_off;
         for (uint32_t k = 1; k <= m.M; ++k) /* node k, slot k-1 */
         {
@@ -405,9 +406,9 @@ enum rc db_commit(dcpgpu_db *db)
         float *cbnd = tr + 8 * NP;
         for (uint32_t w = 0; w < m.W; ++w)
         {
-            const uint32_t n0 = w * 32 * m.Q;
+            const uint32_t n0 = w * m.LN * m.Q;
             double sum = 0.0;
-            for (uint32_t n = n0 + 1; n < n0 + 32 * m.Q; ++n) sum += (double)tr[4 * NP + n];
+            for (uint32_t n = n0 + 1; n < n0 + m.LN * m.Q; ++n) sum += (double)tr[4 * NP + n];
             cbnd[w] = std::isinf(sum) ? NEG_INF : std::nextafterf((float)sum, INFINITY);
             cbnd[m.W + w] = tr[3 * NP + n0], cbnd[2 * m.W + w] = tr[4 * NP + n0];
         }
@@ -678,7 +679,7 @@ extern "C" enum rc dcpgpu_scan_resident(struct dcpgpu_db *db, struct dcpgpu_seqs
         sa.class_profs = db->d_class[q], sa.n_class = (uint32_t)db->class_list[q].size();
         sa.counter = b_counter.as<unsigned long long>() + q;
         cudaStream_t cs = fan_out ? fan.next() : st;
-        CU_TRY(kc.tw == 1 ? dcp_launch_score(kc, db->sm_count, cs, sa) : dcp_launch_score_mw(kc, db->sm_count, cs, sa));
+        CU_TRY(kc.tw <= 1 ? dcp_launch_score(kc, db->sm_count, cs, sa) : dcp_launch_score_mw(kc, db->sm_count, cs, sa));
         launches++;
         for (uint32_t id : db->class_list[q]) cells += (uint64_t)db->metas[id].M * sq->total;
     }

@@ -59,6 +59,7 @@ struct ProfMeta
 {
     uint32_t M, Q, QP, null_id;
     uint32_t W, cls; /* warps per pair; kernel class (row of the class table) */
+    uint32_t LN, pad; /* lanes per pair: 32, or 16 when two pairs share a warp (W = 1) */
     uint64_t emis_off;  /* floats into d_emis */
     uint64_t trans_off; /* floats into d_trans */
 };
@@ -79,9 +80,9 @@ struct dcpgpu_db
     cudaStream_t stream = nullptr;
     /* side streams: the per-class launches of a scan are spread over them so that one class's tail (persistent
      * blocks running out of work, or a handful of hits to trace) overlaps the next class's start */
-    static constexpr int kSide = 3;
-    cudaStream_t side[kSide] = {nullptr, nullptr, nullptr};
-    cudaEvent_t fork_ev = nullptr, join_ev[kSide] = {nullptr, nullptr, nullptr};
+    static constexpr int kSide = 7;
+    cudaStream_t side[kSide] = {};
+    cudaEvent_t fork_ev = nullptr, join_ev[kSide] = {};
     cudaMemPool_t pool = nullptr; /* the engine's own stream-ordered pool (scratch of scans, results) */
     bool committed = false;
     bool owns_profs = true;        /* false: shard of a dcpgpu_mdb, profiles belong to its view */
@@ -179,7 +180,7 @@ struct ScoreArgs
     unsigned long long *counter; /* work queue cursor of this launch (zeroed) */
     uint32_t seq_tile;           /* sequences per L2 tile */
 };
-cudaError_t dcp_launch_score(const dcp_class &c, int sm_count, cudaStream_t st, const ScoreArgs &a);    /* tw = 1 */
+cudaError_t dcp_launch_score(const dcp_class &c, int sm_count, cudaStream_t st, const ScoreArgs &a);    /* tw = 1, 0 */
 cudaError_t dcp_launch_score_mw(const dcp_class &c, int sm_count, cudaStream_t st, const ScoreArgs &a); /* tw > 1 */
 
 /* Launches of a phase spread over the database's main stream and its side streams: fork() makes the side streams
@@ -189,7 +190,7 @@ struct StreamFan
 {
     dcpgpu_db *db;
     int n = 0;
-    bool used[dcpgpu_db::kSide] = {false, false, false};
+    bool used[dcpgpu_db::kSide] = {};
     explicit StreamFan(dcpgpu_db *d) : db(d) {}
     cudaError_t fork()
     {

@@ -100,7 +100,9 @@ __device__ __forceinline__ float4 ldg4(const float *p, int L)
     return v;
 }
 
-template <int Q, int L0, int L1, int ROW = 32 * (Q <= 4 ? 4 : 8)>
+/* ROW = floats per table line of the profile; HOFF = floats between a lane's first and second quad (lanes per
+ * pair x 4: 128 for a whole warp per pair, 64 for a half-warp per pair) */
+template <int Q, int L0, int L1, int ROW = 32 * (Q <= 4 ? 4 : 8), int HOFF = 128>
 __device__ __forceinline__ void load_emis_part(float (&em)[5][Q], const float *__restrict__ emis_lane,
                                                const uint32_t (&code)[5])
 {
@@ -124,7 +126,7 @@ __device__ __forceinline__ void load_emis_part(float (&em)[5][Q], const float *_
         /* second half (+128 floats) holds nodes 4..Q-1 of the lane: load exactly Q-4 floats */
         if (Q == 8)
         {
-            float4 b = ldg4(src + 128, l);
+            float4 b = ldg4(src + HOFF, l);
             em[l][4 % Q] = b.x, em[l][5 % Q] = b.y, em[l][6 % Q] = b.z, em[l][7 % Q] = b.w;
         }
         else if (Q == 7)
@@ -134,31 +136,31 @@ __device__ __forceinline__ void load_emis_part(float (&em)[5][Q], const float *_
              * with a dead component into three 4-byte loads (25 instead of 15 loads per row) */
             float4 b;
             asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];"
-                         : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(src + 128));
+                         : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(src + HOFF));
             em[l][4 % Q] = b.x, em[l][5 % Q] = b.y, em[l][6 % Q] = b.z;
 #else
-            float2 b = __ldg(reinterpret_cast<const float2 *>(src + 128));
-            float c = __ldg(src + 130);
+            float2 b = __ldg(reinterpret_cast<const float2 *>(src + HOFF));
+            float c = __ldg(src + HOFF + 2);
             em[l][4 % Q] = b.x, em[l][5 % Q] = b.y, em[l][6 % Q] = c;
 #endif
         }
         else if (Q == 6)
         {
-            float2 b = __ldg(reinterpret_cast<const float2 *>(src + 128));
+            float2 b = __ldg(reinterpret_cast<const float2 *>(src + HOFF));
             em[l][4 % Q] = b.x, em[l][5 % Q] = b.y;
         }
         else if (Q == 5)
         {
-            em[l][4 % Q] = __ldg(src + 128);
+            em[l][4 % Q] = __ldg(src + HOFF);
         }
     }
 }
 
-template <int Q, int ROW = 32 * (Q <= 4 ? 4 : 8)>
+template <int Q, int ROW = 32 * (Q <= 4 ? 4 : 8), int HOFF = 128>
 __device__ __forceinline__ void load_emis(float (&em)[5][Q], const float *__restrict__ emis_lane,
                                           const uint32_t (&code)[5])
 {
-    load_emis_part<Q, 0, 5, ROW>(em, emis_lane, code);
+    load_emis_part<Q, 0, 5, ROW, HOFF>(em, emis_lane, code);
 }
 
 /* ----------------------------------------------------------------------------------------- */

@@ -414,5 +414,242 @@ k_score(const float *__restrict__ emis, const float *__restrict__ trans, const P
     }
 }
 
+
+/* ----------------------------------------------------------------------------------------- */
+/* profiles of up to 128 nodes: TWO (sequence, profile) pairs per warp, 16 lanes each          */
+/* ----------------------------------------------------------------------------------------- */
+/*
+ * A warp's row costs ~78 instructions whatever it computes (window codes and addresses, row-record loads, shuffles,
+ * the E reduction, N/J/C/B) plus ~30 per node and lane; a 50-node profile in a whole warp pays the fixed part for 2
+ * nodes per lane.  Here the two halves of a warp run two sequences against the same profile in lock step: the same
+ * instruction stream as k_score<Q> -- shuffles and the E reduction confined to 16 lanes, row records, window codes,
+ * lengths and length-dependent specials per half -- so the fixed part is shared by two pairs and the padded width of a
+ * pair is 16 Q instead of 32 Q'.  Bit-identical arithmetic (the lane layout of a pair is the same consecutive-nodes
+ * layout, the D chain the same exact lazy propagation over 16 lanes).
+ */
+/* maximum over the 16 lanes of this lane's half.  redux.sync with a per-half member mask is compiled into a divergent
+ * loop over the distinct masks (REDUX + branches: the half-warp kernels ran 1.5x slower per row with it); two
+ * whole-warp reductions with the other half masked out by -inf are straight-line */
+__device__ __forceinline__ float half_max(float x, int half)
+{
+    const float lo = warp_max(half ? NEG_INF : x), hi = warp_max(half ? x : NEG_INF);
+    return half ? hi : lo;
+}
+
+template <int Q, int R>
+__device__ __forceinline__ void score_row_h(float (&tm)[5][Q], float (&ti)[5][Q], float (&tx)[5],
+                                            const NodeParams<Q> &p, RowState<Q> &rs,
+                                            const float *__restrict__ emis_lane,
+                                            const RowRec *__restrict__ rec_next,
+                                            const uint16_t *__restrict__ w_next2, int hl, int half, float NB,
+                                            float JB, float EB, float cE, float cX, float &E_out, float &vx_out)
+{
+    constexpr int S1 = (R + 4) % 5, S2 = (R + 3) % 5, S3 = (R + 2) % 5, S4 = (R + 1) % 5, S5 = R;
+    constexpr int QP = Q <= 4 ? 4 : 8, ROW = 16 * QP, HOFF = 64;
+
+    float vm[Q], vi[Q];
+#pragma unroll
+    for (int i = 0; i < Q; ++i)
+        vm[i] = fmaxf(max3(tm[S1][i] + rs.em[0][i], tm[S2][i] + rs.em[1][i], tm[S3][i] + rs.em[2][i]),
+                      fmaxf(tm[S4][i] + rs.em[3][i], tm[S5][i] + rs.em[4][i]));
+#pragma unroll
+    for (int i = 0; i < Q; ++i)
+        vi[i] = fmaxf(max3(ti[S1][i] + rs.eI[0], ti[S2][i] + rs.eI[1], ti[S3][i] + rs.eI[2]),
+                      fmaxf(ti[S4][i] + rs.eI[3], ti[S5][i] + rs.eI[4]));
+    float vx = fmaxf(max3(tx[S1] + rs.eN[0], tx[S2] + rs.eN[1], tx[S3] + rs.eN[2]),
+                     fmaxf(tx[S4] + rs.eN[3], tx[S5] + rs.eN[4]));
+
+    uint32_t code[5];
+    codes_of(rs.w1, code);
+    load_emis_part<Q, 3, 5, ROW, HOFF>(rs.em, emis_lane, code);
+    rs.w1 = rs.w2;
+    rs.w2 = __ldg(w_next2);
+    load_row_insert(rec_next, rs.eI);
+    if (hl < 3) load_row_special(rec_next, rs.eN);
+
+    float eloc = vm[0];
+#pragma unroll
+    for (int i = 1; i < Q; ++i) eloc = fmaxf(eloc, vm[i]);
+    const float E = half_max(eloc, half);
+
+    float vm_prev = __shfl_up_sync(FULL, vm[Q - 1], 1, 16);
+    if (hl == 0) vm_prev = NEG_INF;
+
+    float d[Q];
+    d[0] = vm_prev + p.MD[0];
+#pragma unroll
+    for (int i = 1; i < Q; ++i) d[i] = fmaxf(vm[i - 1] + p.MD[i], d[i - 1] + p.DD[i]);
+    float old = d[Q - 1];
+    float din = __shfl_up_sync(FULL, old, 1, 16);
+    if (hl == 0) din = NEG_INF;
+    {
+        float x = din;
+#pragma unroll
+        for (int i = 0; i < Q; ++i)
+        {
+            x = x + p.DD[i];
+            d[i] = fmaxf(d[i], x);
+            x = d[i];
+        }
+    }
+    bool more = __any_sync(FULL, d[Q - 1] > old);
+
+    float vi_prev = __shfl_up_sync(FULL, vi[Q - 1], 1, 16);
+    if (hl == 0) vi_prev = NEG_INF;
+
+    load_emis_part<Q, 0, 3, ROW, HOFF>(rs.em, emis_lane, code);
+
+    const float vN = __shfl_sync(FULL, vx, 0, 16);
+    const float vJ = __shfl_sync(FULL, vx, 1, 16);
+    const float B = max3(vN + NB, vJ + JB, E + EB);
+    tx[R] = fmaxf(E + cE, vx + cX);
+
+#pragma unroll
+    for (int i = 0; i < Q; ++i)
+    {
+        const float pm = i == 0 ? vm_prev : vm[i - 1];
+        const float pi = i == 0 ? vi_prev : vi[i - 1];
+        tm[R][i] = max3(B + p.ent[i], pm + p.MM[i], pi + p.IM[i]);
+        ti[R][i] = fmaxf(vm[i] + p.MI[i], vi[i] + p.II[i]);
+    }
+    while (more)
+    {
+        old = d[Q - 1];
+        din = __shfl_up_sync(FULL, old, 1, 16);
+        if (hl == 0) din = NEG_INF;
+        float x = din;
+#pragma unroll
+        for (int i = 0; i < Q; ++i)
+        {
+            x = x + p.DD[i];
+            d[i] = fmaxf(d[i], x);
+            x = d[i];
+        }
+        more = __any_sync(FULL, d[Q - 1] > old);
+    }
+#pragma unroll
+    for (int i = 0; i < Q; ++i)
+    {
+        const float pd = i == 0 ? din : d[i - 1];
+        tm[R][i] = fmaxf(tm[R][i], pd + p.DM[i]);
+    }
+    E_out = E;
+    vx_out = vx;
+}
+
+/* this lane's half: recs / wc / L / sp of its own sequence; Lmax = the longer of the warp's two sequences */
+template <int Q>
+__device__ __forceinline__ float score_pair_h(const NodeParams<Q> &p, const float *__restrict__ emis_lane,
+                                              const RowRec *__restrict__ recs, const uint16_t *__restrict__ wc,
+                                              uint32_t L, uint32_t Lmax, const float *__restrict__ sp, int hl,
+                                              int half)
+{
+    constexpr int QP = Q <= 4 ? 4 : 8;
+    const float NN = sp[0], CC = sp[1], JJ = sp[2], NB = sp[3], CT = sp[4], JB = sp[5];
+    const float ET = sp[9], ECC = sp[10], EB = sp[11], EJJ = sp[12];
+    const float cE = hl == 0 ? NEG_INF : (hl == 1 ? EJJ : ECC);
+    const float cX = hl == 0 ? NN : (hl == 1 ? JJ : CC);
+
+    float tm[5][Q], ti[5][Q], tx[5];
+#pragma unroll
+    for (int s = 0; s < 5; ++s)
+    {
+        tx[s] = NEG_INF;
+#pragma unroll
+        for (int i = 0; i < Q; ++i) tm[s][i] = NEG_INF, ti[s][i] = NEG_INF;
+    }
+#pragma unroll
+    for (int i = 0; i < Q; ++i) tm[4][i] = NB + p.ent[i];
+    tx[4] = hl == 0 ? NN : NEG_INF;
+
+    RowState<Q> rs;
+#pragma unroll
+    for (int l = 0; l < 5; ++l) rs.eN[l] = NEG_INF;
+    {
+        uint32_t code[5];
+        codes_of(__ldg(wc + 1), code);
+        load_emis<Q, 16 * QP, 64>(rs.em, emis_lane, code);
+    }
+    load_row_insert(recs + 1, rs.eI);
+    if (hl < 3) load_row_special(recs + 1, rs.eN);
+    rs.w1 = __ldg(wc + min(2u, L));
+    rs.w2 = __ldg(wc + min(3u, L));
+    rs.w3 = 0;
+
+    /* whole groups of five rows up to the longer sequence; rows past this half's own L recompute on clamped inputs
+     * and are ignored, E and V_X of row L are latched when they pass */
+    float E = NEG_INF, vx = NEG_INF, E_L = NEG_INF, vx_L = NEG_INF;
+#define ROW_ARGS_H(jj) recs + min((uint32_t)(jj) + 1u, L), wc + min((uint32_t)(jj) + 3u, L)
+#define LATCH_H(jj) /* selects, not a branch: L differs between the halves */                                   \
+    {                                                                                                          \
+        const bool at = (jj) == L;                                                                             \
+        E_L = at ? E : E_L, vx_L = at ? vx : vx_L;                                                             \
+    }
+    for (uint32_t j = 1; j <= Lmax; j += 5)
+    {
+        score_row_h<Q, 0>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS_H(j), hl, half, NB, JB, EB, cE, cX, E, vx);
+        LATCH_H(j)
+        score_row_h<Q, 1>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS_H(j + 1), hl, half, NB, JB, EB, cE, cX, E, vx);
+        LATCH_H(j + 1)
+        score_row_h<Q, 2>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS_H(j + 2), hl, half, NB, JB, EB, cE, cX, E, vx);
+        LATCH_H(j + 2)
+        score_row_h<Q, 3>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS_H(j + 3), hl, half, NB, JB, EB, cE, cX, E, vx);
+        LATCH_H(j + 3)
+        score_row_h<Q, 4>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS_H(j + 4), hl, half, NB, JB, EB, cE, cX, E, vx);
+        LATCH_H(j + 4)
+    }
+#undef ROW_ARGS_H
+#undef LATCH_H
+    const float vC = __shfl_sync(FULL, vx_L, 2, 16);
+    return fmaxf(E_L + ET, vC + CT);
+}
+
+template <int Q>
+__global__ void __launch_bounds__(score_warps(Q) * 32, 1)
+k_score_h(const float *__restrict__ emis, const float *__restrict__ trans, const ProfMeta *__restrict__ metas,
+          const uint32_t *__restrict__ class_profs, uint32_t n_class_profs, const SeqMeta *__restrict__ seqs,
+          uint32_t nseq, uint64_t total_recs, const RowRec *__restrict__ rows, const uint16_t *__restrict__ wcodes,
+          const float *__restrict__ spec, float *__restrict__ alt_out, uint32_t nprof,
+          unsigned long long *__restrict__ counter, uint32_t seq_tile)
+{
+    const int lane = threadIdx.x & 31, hl = lane & 15, half = lane >> 4;
+    /* work items as in k_score: (sequence tile, profile, chunk of kSeqChunk sequences); a chunk is taken two
+     * sequences at a time, one per half-warp */
+    const uint32_t nchunks = (nseq + kSeqChunk - 1) / kSeqChunk;
+    const uint32_t tile_chunks = seq_tile / kSeqChunk;
+    const unsigned long long n_items = (unsigned long long)n_class_profs * nchunks;
+    for (;;)
+    {
+        unsigned long long item = 0;
+        if (lane == 0) item = atomicAdd(counter, 1ULL);
+        item = __shfl_sync(FULL, item, 0);
+        if (item >= n_items) break;
+        const unsigned long long per_full_tile = (unsigned long long)tile_chunks * n_class_profs;
+        const uint32_t tile = (uint32_t)(item / per_full_tile);
+        const unsigned long long in_tile = item - (unsigned long long)tile * per_full_tile;
+        const uint32_t chunks_here = min(tile_chunks, nchunks - tile * tile_chunks);
+        const uint32_t pi = (uint32_t)(in_tile / chunks_here);
+        const uint32_t ci = tile * tile_chunks + (uint32_t)(in_tile % chunks_here);
+        const uint32_t prof = class_profs[pi];
+        const ProfMeta pm = metas[prof];
+        NodeParams<Q> p;
+        load_params<Q>(p, trans + pm.trans_off, 16 * Q, hl * Q);
+        const float *emis_lane = emis + pm.emis_off + hl * 4;
+        const RowRec *rows_t = rows + (size_t)pm.null_id * total_recs;
+        const uint32_t s_end = min(nseq, (ci + 1) * kSeqChunk);
+        for (uint32_t s0 = ci * kSeqChunk; s0 < s_end; s0 += 2)
+        {
+            const uint32_t s = min(s0 + (uint32_t)half, s_end - 1); /* odd tail: the upper half repeats the last one */
+            const SeqMeta sm = seqs[s];
+            /* the row loop's trip count, from warp-uniform loads (a shuffle would make the loop look divergent to the
+             * compiler, which then guards every shuffle in it with BRA.DIV) */
+            const uint32_t Lmax = max(seqs[s0].len, seqs[min(s0 + 1, s_end - 1)].len);
+            const float T = score_pair_h<Q>(p, emis_lane, rows_t + sm.rec_off, wcodes + sm.rec_off, sm.len, Lmax,
+                                            spec + (size_t)s * 16, hl, half);
+            if (hl == 0 && s0 + (uint32_t)half < s_end) alt_out[(size_t)s * nprof + prof] = T;
+        }
+    }
+}
+
 } // namespace
 #endif

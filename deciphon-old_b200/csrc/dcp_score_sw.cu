@@ -28,16 +28,27 @@ cudaError_t launch_score(int nblocks, cudaStream_t st, const ScoreArgs &a)
                                                                a.alt, a.nprof, a.counter, a.seq_tile);
     return cudaGetLastError();
 }
+/* two pairs per warp, 16 lanes each (class table rows with TW = 0) */
+template <int Q>
+cudaError_t launch_score_h(int nblocks, cudaStream_t st, const ScoreArgs &a)
+{
+    cudaFuncSetAttribute(k_score_h<Q>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    k_score_h<Q><<<nblocks, score_warps(Q) * 32, 0, st>>>(a.emis, a.trans, a.metas, a.class_profs, a.n_class, a.seqs, a.nseq,
+                                                         a.total_recs, a.rows, a.wcodes, a.spec, a.alt, a.nprof,
+                                                         a.counter, a.seq_tile);
+    return cudaGetLastError();
+}
 } // namespace
 
 cudaError_t dcp_launch_score(const dcp_class &c, int sm_count, cudaStream_t st, const ScoreArgs &a)
 {
     const int nblocks = sm_count; /* persistent: one block per SM (as many warps as the register file holds) */
 #define X(TW, Q, BPS, RATE)                                                                                 \
-    if (TW == 1 && c.q == Q)                                                                                \
+    if (TW <= 1 && c.tw == TW && c.q == Q)                                                                  \
     {                                                                                                       \
-        static_assert(TW != 1 || BPS == score_warps(Q), "class table: warps per block of k_score<Q>");      \
-        return launch_score<(TW == 1 ? Q : 1)>(nblocks, st, a);                                             \
+        static_assert(TW > 1 || BPS == score_warps(Q), "class table: warps per block of k_score<Q>");       \
+        if (TW == 1) return launch_score<(TW == 1 ? Q : 1)>(nblocks, st, a);                                \
+        return launch_score_h<(TW == 0 ? Q : 4)>(nblocks, st, a);                                           \
     }
     DCP_CLASS_TABLE(X)
 #undef X

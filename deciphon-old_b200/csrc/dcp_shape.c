@@ -25,6 +25,9 @@ static const struct dcp_class kClasses[] = {DCP_CLASS_TABLE(ROW)};
 enum { kNumClasses = sizeof kClasses / sizeof kClasses[0] };
 _Static_assert((int)kNumClasses <= (int)DCP_MAX_CLASSES, "raise DCP_MAX_CLASSES");
 
+/* nodes a class holds: tw warps of 32 lanes, or (tw = 0) the 16 lanes of a half-warp, q nodes per lane */
+static unsigned class_capacity(struct dcp_class const *c) { return (c->tw ? c->tw * 32 : 16) * c->q; }
+
 unsigned dcp_num_classes(void) { return kNumClasses; }
 struct dcp_class const *dcp_class_at(unsigned cls) { return cls < kNumClasses ? &kClasses[cls] : NULL; }
 
@@ -40,13 +43,13 @@ unsigned dcp_kernel_class(unsigned M)
         unsigned tw = 0, q = 0, bps = 0;
         if (sscanf(force, "%u,%u,%u", &tw, &q, &bps) == 3)
             for (unsigned c = 0; c < kNumClasses; ++c)
-                if (kClasses[c].tw == tw && kClasses[c].q == q && kClasses[c].bps == bps && tw * 32 * q >= M) return c;
+                if (kClasses[c].tw == tw && kClasses[c].q == q && kClasses[c].bps == bps && class_capacity(&kClasses[c]) >= M) return c;
     }
     unsigned best = kNumClasses;
     double best_cost = 0.0;
     for (unsigned c = 0; c < kNumClasses; ++c)
     {
-        const unsigned cap = kClasses[c].tw * 32 * kClasses[c].q;
+        const unsigned cap = class_capacity(&kClasses[c]);
         if (cap < M || kClasses[c].rate <= 0.0) continue;
         const double cost = (double)cap / kClasses[c].rate;
         if (best == kNumClasses || cost < best_cost) best = c, best_cost = cost;
@@ -59,7 +62,7 @@ enum rc dcpgpu_kernel_shape(unsigned core_size, unsigned *warps, unsigned *nodes
     if (core_size == 0 || core_size > DCP_PROTEIN_MODEL_CORE_SIZE_MAX)
         return dcp_error(RC_EINVAL, "core size out of range");
     struct dcp_class const *c = &kClasses[dcp_kernel_class(core_size)];
-    if (warps) *warps = c->tw;
+    if (warps) *warps = c->tw ? c->tw : 1; /* half-warp classes: one warp (shared by two pairs) */
     if (nodes_per_lane) *nodes_per_lane = c->q;
     if (blocks) *blocks = c->tw > (unsigned)DCP_MAX_W ? 2 : 1;
     return RC_OK;
@@ -70,7 +73,13 @@ double dcp_profile_cost(unsigned core_size)
     if (core_size == 0) return 0.0;
     if (core_size > DCP_PROTEIN_MODEL_CORE_SIZE_MAX) core_size = DCP_PROTEIN_MODEL_CORE_SIZE_MAX;
     struct dcp_class const *c = &kClasses[dcp_kernel_class(core_size)];
-    return (double)(c->tw * 32 * c->q) / (c->rate > 0.0 ? c->rate : 300.0);
+    return (double)class_capacity(c) / (c->rate > 0.0 ? c->rate : 300.0);
+}
+
+unsigned dcpgpu_kernel_padded_width(unsigned core_size)
+{
+    if (core_size == 0 || core_size > DCP_PROTEIN_MODEL_CORE_SIZE_MAX) return 0;
+    return class_capacity(&kClasses[dcp_kernel_class(core_size)]);
 }
 
 double dcpgpu_profile_cost(unsigned core_size) { return dcp_profile_cost(core_size); }

@@ -69,13 +69,16 @@ __device__ __forceinline__ void ring_rotate(float (&tm)[5][Q], float (&ti)[5][Q]
     tn[4] = a, tj[4] = b, tc[4] = c;
 }
 
-template <int Q, int R>
+/* LN = lanes per hit: 32, or 16 for the half-warp classes (the trace kernel then runs the hit twice, on both halves
+ * of the warp: identical values, identical stores -- traceback is not worth a second code path) */
+template <int Q, int R, int LN>
 __device__ __forceinline__ void trace_row(float (&tm)[5][Q], float (&ti)[5][Q], float (&tn)[5], float (&tj)[5],
                                           float (&tc)[5], const NodeParams<Q> &p,
                                           const float *__restrict__ emis_lane, const RowRec *__restrict__ rec,
                                           uint32_t wcode, int lane, const float *__restrict__ sp, uint16_t *__restrict__ cell_bp,
                                           uint32_t *__restrict__ row_bp, float &T_out)
 {
+    constexpr int QP = Q <= 4 ? 4 : 8;
     constexpr int S[5] = {(R + 4) % 5, (R + 3) % 5, (R + 2) % 5, (R + 1) % 5, R};
     const float NN = sp[0], CC = sp[1], JJ = sp[2], NB = sp[3], CT = sp[4], JB = sp[5];
     const float ET = sp[9], ECC = sp[10], EB = sp[11], EJJ = sp[12];
@@ -85,7 +88,7 @@ __device__ __forceinline__ void trace_row(float (&tm)[5][Q], float (&ti)[5][Q], 
     uint32_t code[5];
     codes_of(wcode, code);
     float em[5][Q];
-    load_emis<Q>(em, emis_lane, code);
+    load_emis<Q, LN * QP, LN * 4>(em, emis_lane, code);
 
     /* W[j-l][X][l] for every emitting state: the five candidate sums per state */
     float sM[Q][5], sI[Q][5], vm[Q], vi[Q];
@@ -114,8 +117,8 @@ __device__ __forceinline__ void trace_row(float (&tm)[5][Q], float (&ti)[5][Q], 
 #pragma unroll
     for (int l = 0; l < 5; ++l)
     {
-        pM0[l] = __shfl_up_sync(FULL, sM[Q - 1][l], 1);
-        pI0[l] = __shfl_up_sync(FULL, sI[Q - 1][l], 1);
+        pM0[l] = __shfl_up_sync(FULL, sM[Q - 1][l], 1, LN);
+        pI0[l] = __shfl_up_sync(FULL, sI[Q - 1][l], 1, LN);
         if (lane == 0) pM0[l] = NEG_INF, pI0[l] = NEG_INF;
     }
 
@@ -141,7 +144,7 @@ __device__ __forceinline__ void trace_row(float (&tm)[5][Q], float (&ti)[5][Q], 
     for (;;)
     {
         float old = d[Q - 1];
-        din = __shfl_up_sync(FULL, old, 1);
+        din = __shfl_up_sync(FULL, old, 1, LN);
         if (lane == 0) din = NEG_INF;
         float x = din;
 #pragma unroll
@@ -227,11 +230,11 @@ __device__ __forceinline__ void trace_row(float (&tm)[5][Q], float (&ti)[5][Q], 
         first_max5(sI[i], p.II[i], 5, ib, icode);
         tm[R][i] = mb;
         ti[R][i] = ib;
-        cell_bp[i * 32 + lane] = (uint16_t)(mcode | icode << 4 | dcode[i] << 8);
+        cell_bp[i * LN + lane] = (uint16_t)(mcode | icode << 4 | dcode[i] << 8);
     }
 }
 
-template <int Q>
+template <int Q, int LN>
 __global__ void __launch_bounds__(128) k_trace(const float *__restrict__ emis, const float *__restrict__ trans,
                                                const ProfMeta *__restrict__ metas,
                                                const SeqMeta *__restrict__ seqs, uint64_t total_rows,
@@ -240,14 +243,14 @@ __global__ void __launch_bounds__(128) k_trace(const float *__restrict__ emis, c
                                                uint16_t *__restrict__ cell_bp, uint32_t *__restrict__ row_bp,
                                                float *__restrict__ alt_out)
 {
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & (LN - 1); /* index inside the hit's lanes; with LN = 16 both halves run the same hit */
     uint32_t job = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (job >= njobs) return;
     TraceJob tj_ = jobs[job];
     ProfMeta pm = metas[tj_.prof];
     SeqMeta sm = seqs[tj_.seq];
     NodeParams<Q> p;
-    load_params<Q>(p, trans + pm.trans_off, 32 * Q, lane * Q);
+    load_params<Q>(p, trans + pm.trans_off, LN * Q, lane * Q);
     const float *emis_lane = emis + pm.emis_off + lane * 4;
     const RowRec *r = rows + (size_t)pm.null_id * total_rows + sm.rec_off + 1; /* record of row 1 */
     const uint16_t *wc = wcodes + sm.rec_off; /* wc[j] = window of row j */
@@ -270,18 +273,18 @@ __global__ void __launch_bounds__(128) k_trace(const float *__restrict__ emis, c
     for (int i = 0; i < Q; ++i)
     {
         tm[4][i] = NB + p.ent[i];
-        cb[i * 32 + lane] = 0;
+        cb[i * LN + lane] = 0;
     }
     tn[4] = NN;
     if (lane == 0) rb[0] = 0;
 
     float T = NEG_INF;
     uint32_t j = 1;
-    constexpr uint32_t CS = Q * 32; /* cell backpointers per row */
+    constexpr uint32_t CS = Q * LN; /* cell backpointers per row */
 #pragma unroll 1
     for (; j <= L; ++j)
     {
-        trace_row<Q, 0>(tm, ti, tn, tjr, tc, p, emis_lane, r + (j - 1), wc[j], lane, sp, cb + (size_t)j * CS, rb + j, T);
+        trace_row<Q, 0, LN>(tm, ti, tn, tjr, tc, p, emis_lane, r + (j - 1), wc[j], lane, sp, cb + (size_t)j * CS, rb + j, T);
         ring_rotate<Q>(tm, ti, tn, tjr, tc);
     }
     if (lane == 0) alt_out[job] = T;
@@ -675,8 +678,8 @@ __global__ void k_walk(const ProfMeta *__restrict__ metas, const SeqMeta *__rest
     uint32_t job = blockIdx.x * blockDim.x + threadIdx.x;
     if (job >= njobs) return;
     TraceJob tj = jobs[job];
-    const uint32_t Q = metas[tj.prof].Q, W = metas[tj.prof].W;
-    const uint32_t CS = Q * 32 * W;
+    const uint32_t Q = metas[tj.prof].Q, W = metas[tj.prof].W, LN = metas[tj.prof].LN;
+    const uint32_t CS = Q * LN * W;
     const uint16_t *cb = cell_bp + tj.cell_off;
     const uint32_t *rb = row_bp + tj.row_off;
     const uint32_t L = seqs[tj.seq].len;
@@ -717,7 +720,7 @@ __global__ void k_walk(const ProfMeta *__restrict__ metas, const SeqMeta *__rest
         if (st == W_M || st == W_I || st == W_D)
         {
             uint32_t node = k - 1;
-            uint16_t c = cb[(size_t)r * CS + (node % Q) * (32 * W) + node / Q]; /* [sub][warp][lane] */
+            uint16_t c = cb[(size_t)r * CS + (node % Q) * (LN * W) + node / Q]; /* [sub][warp][lane] */
             if (st == W_M)
             {
                 uint32_t m = c & 15;
@@ -796,11 +799,11 @@ __global__ void k_walk(const ProfMeta *__restrict__ metas, const SeqMeta *__rest
         }
 }
 
-template <int Q>
+template <int Q, int LN>
 void launch_trace(cudaStream_t st, uint32_t njobs, const dcpgpu_db *db, const dcpgpu_seqs *sq, const RowRec *rows,
                   const uint16_t *wcodes, const float *spec, const TraceJob *jobs, uint16_t *cell_bp, uint32_t *row_bp, float *alt)
 {
-    k_trace<Q><<<(njobs + 3) / 4, 128, 0, st>>>(db->d_emis, db->d_trans, db->d_metas, sq->d_metas, sq->total + sq->nseq, rows,
+    k_trace<Q, LN><<<(njobs + 3) / 4, 128, 0, st>>>(db->d_emis, db->d_trans, db->d_metas, sq->d_metas, sq->total + sq->nseq, rows,
                                                 wcodes, spec, jobs, njobs, cell_bp, row_bp, alt);
 }
 
@@ -810,8 +813,8 @@ void launch_trace_class(cudaStream_t st, uint32_t njobs, const dcpgpu_db *db, co
                         const uint16_t *wcodes, const float *spec, const TraceJob *jobs, uint16_t *cell_bp,
                         uint32_t *row_bp, float *alt)
 {
-    if constexpr (TW == 1)
-        launch_trace<Q>(st, njobs, db, sq, rows, wcodes, spec, jobs, cell_bp, row_bp, alt);
+    if constexpr (TW <= 1)
+        launch_trace<Q, TW == 1 ? 32 : 16>(st, njobs, db, sq, rows, wcodes, spec, jobs, cell_bp, row_bp, alt);
     else
     {
         constexpr int CL = TW > kMaxW ? 2 : 1, W = TW / CL;
@@ -843,12 +846,12 @@ enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const
         while (end < nhits)
         {
             const HitRec &h = res->hits[end];
-            uint32_t QW = db->metas[h.prof].Q * db->metas[h.prof].W;
+            uint32_t QW = db->metas[h.prof].Q * db->metas[h.prof].W * db->metas[h.prof].LN; /* padded nodes */
             size_t L1 = (size_t)sq->metas[h.seq].len + 1;
-            size_t need = L1 * QW * 32 * sizeof(uint16_t) + L1 * sizeof(uint32_t);
+            size_t need = L1 * QW * sizeof(uint16_t) + L1 * sizeof(uint32_t);
             if (!jobs.empty() && (cells * 2 + rowsz * 4 + need > budget)) break;
             jobs.push_back({h.seq, h.prof, cells, rowsz});
-            cells += L1 * QW * 32;
+            cells += L1 * QW;
             rowsz += L1;
             ++end;
         }

@@ -336,6 +336,9 @@ unsigned dcpgpu_result_nparts(struct dcpgpu_result const *);
  * (sequence, profile) pair, `nodes_per_lane`, and 1 or 2 thread blocks (a cluster) per pair; warps * 32 *
  * nodes_per_lane >= core_size is the padded width the kernels compute.  Pure function (no device needed). */
 enum rc dcpgpu_kernel_shape(unsigned core_size, unsigned *warps, unsigned *nodes_per_lane, unsigned *blocks);
+/* the padded width itself: warps * 32 * nodes_per_lane, or 16 * nodes_per_lane for profiles short enough that two
+ * (sequence, profile) pairs share a warp, 16 lanes each (0 for an invalid core size) */
+unsigned dcpgpu_kernel_padded_width(unsigned core_size);
 
 /* ------------------------------------------------------------------------- */
 /* Part 3 -- products.  src/server/prod.c:13-41,106-181, protein_match.c:21-56 */

@@ -144,24 +144,26 @@ def test_shard_profiles(pkg):
 
 
 def test_kernel_shape_covers_every_core_size(pkg):
-    """Profile length -> (warps, nodes per lane, blocks): the padded width always holds the profile, one warp up
-    to 256 nodes, one block up to 2048, a 2-block cluster up to 4096 (limits.h:11), never more than 50 % padding
-    above 96 nodes."""
+    """Profile length -> (warps, nodes per lane, blocks) and padded width: the padded width always holds the profile,
+    one warp (or half of one) up to 256 nodes, one block up to 2048, a 2-block cluster up to 4096 (limits.h:11), never
+    more than 50 % padding above 48 nodes."""
     for M in range(1, 4097):
         w, q, b = pkg.kernel_shape(M)
+        pad = pkg.kernel_padded_width(M)
         assert 1 <= q <= 8 and 1 <= w <= 16 and b in (1, 2)
-        assert w * 32 * q >= M, (M, w, q)
+        assert pad >= M and pad in (w * 32 * q, 16 * q), (M, w, q, pad)
         assert (w == 1) == (M <= 256)
         assert (b == 2) == (M > 2048)
         if b == 2:
             assert w % 2 == 0 and w // 2 <= 8
-        if M > 96:
-            assert w * 32 * q <= 1.5 * M, (M, w, q)
+        if M > 48:
+            assert pad <= 1.5 * M + 16, (M, w, q, pad)
     # the chooser minimises padded width / measured rate over the class table (dcp_classes.h): the cost never
     # decreases with the profile length, and a profile never lands in a class it does not fit
     costs = [pkg.profile_cost(M) for M in range(1, 4097)]
     assert all(b >= a for a, b in zip(costs, costs[1:]))
     assert pkg.kernel_shape(256) == (1, 8, 1) and pkg.kernel_shape(512)[0] == 2 and pkg.kernel_shape(4096) == (16, 8, 2)
+    assert pkg.kernel_padded_width(60) == 64 and pkg.kernel_padded_width(200) == 256  # two pairs per warp below 129 nodes
     for bad in (0, 4097):
         with pytest.raises(pkg.DcpError):
             pkg.kernel_shape(bad)

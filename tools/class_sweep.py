@@ -40,7 +40,7 @@ def main():
     forced = []
     if sys.argv[1:2] == ["--table"]:
         forced = table_rows()
-        sizes = [tw * 32 * q for tw, q, bps in forced]
+        sizes = [(tw * 32 if tw else 16) * q for tw, q, bps in forced]
     else:
         sizes = [int(x) for x in sys.argv[1:]] or DEFAULT
     L = int(os.environ.get("L", 1500))
@@ -73,8 +73,8 @@ def main():
                 best = t.score_ms
             cells = t.alt_cells
             del r
-        padded = w * 32 * q
-        print(json.dumps({"M": M, "warps": w, "q": q, "blocks": b, "bps": forced[idx][2] if forced else None, "padded": padded, "nprof": nprof, "nreads": nreads,
+        padded = pkg.kernel_padded_width(M)
+        print(json.dumps({"M": M, "warps": forced[idx][0] if forced else w, "q": q, "blocks": b, "bps": forced[idx][2] if forced else None, "padded": padded, "nprof": nprof, "nreads": nreads,
                           "L": L, "score_ms": round(best, 3), "gcups": round(cells / best / 1e6, 1),
                           "padded_gnodes_per_s": round(cells / M * padded / best / 1e6, 1)}), flush=True)
         del st, db
