@@ -1,5 +1,13 @@
 mkdir -p gpurun_out/r2
-python -m pytest tests -m gpu -q 2>&1 | tail -3
-python bench.py --workload fixeddb --db-profiles 2500 --db-reads 1000 --steps 3 --warmup 2 --no-cpu 2>/dev/null | python -c "
+DCPGPU_FORCE_SHAPE=1,7,8 python tools/sanitize_probe.py 193 200 210 224 2>&1 | tail -1
+DCPGPU_PIPE=1 python tools/sanitize_probe.py 129 150 161 190 193 256 2>&1 | tail -1
+for cfg in "1,7,8 200 224" ; do set -- $cfg; DCPGPU_FORCE_SHAPE=$1 python tools/class_sweep.py $2 $3 2>&1 | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); print('pfam shard', d['phases_ms_rank0'], 'value', round(d['value'],1), 'e2e', round(d['e2e']['value'],1), d['merged_hits'])"
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('p7', d['M'], d['padded'], d['score_ms'], d['gcups'], d['padded_gnodes_per_s'])"; done
+DCPGPU_PIPE=1 python tools/class_sweep.py 160 192 200 256 2>&1 | python -c "
+import json,sys
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('pipe', d['M'], d['q'], d['padded'], d['score_ms'], d['gcups'], d['padded_gnodes_per_s'])"
