@@ -12,17 +12,17 @@ namespace
 /* alt Viterbi, score pass, profiles of 257..4096 nodes: a group of warps per pair            */
 /* ----------------------------------------------------------------------------------------- */
 /*
- * Same recurrence, same fp32 operation order and the same lane layout as k_score<8>; node
- * k-1 = gwarp * 256 + lane * 8 + sub.  257..2048 nodes: W warps of one block (CL = 1);
+ * Same recurrence, same fp32 operation order and the same lane layout as k_score<Q>; node
+ * k-1 = gwarp * 32 Q + lane * Q + sub.  257..2048 nodes: W warps of one block (CL = 1);
  * 2049..4096 nodes: W warps in each block of a 2-block cluster (CL = 2, 255 registers x 16 warps do
  * not fit one SM), exchanging through distributed shared memory.  What a single warp exchanges with
- * shuffles is exchanged between warps through shared memory, two group barriers per row:
+ * shuffles is exchanged between warps through shared memory, at most two rendezvous per row:
  *   A   V_M / V_I / D of each warp's last node (D from the warp-local chain), per-warp max of V_M (-> E),
  *       V_N / V_J / V_C of warp 0
  *   C   group-wide OR: did any warp's last D rise when the left neighbour's values came in?
- *       (if so publish the new D, barrier B, and repeat -- exact lazy propagation, as inside a warp)
- * Measured alternatives that were not faster: keeping 8 warps per SM with 5 or 6 nodes per lane
- * (M = 600: 252 vs 267 GCUPS) -- the barriers, not the occupancy, bound these kernels.
+ *       (if so every warp re-reads its left neighbour's new D and repeats -- exact lazy propagation, as inside a
+ *       warp).  Not needed with two warps, and skipped when the carry bound below shows that no D can rise.
+ * Which (warps, nodes per lane, resident blocks) shapes exist and what they achieve: dcp_classes.h.
  */
 /*
  * Carry bound of one warp of a group (lane w holds warp w's): S = an upper bound of the sum of the D->D scores of
@@ -55,7 +55,7 @@ __device__ __forceinline__ bool carry_cannot_rise(const CarryBound &cb, int lane
 
 struct MwShared
 {
-    alignas(16) float4 rec[2][kMaxGroupWarps]; /* mw_row2: per-warp record of the row, by row parity */
+    alignas(16) float4 rec[2][kMaxGroupWarps]; /* mw_row: per-warp record of the row, by row parity */
     alignas(16) float v_spec[2][4];            /* V_N, V_J, V_C of the row */
     float d_loc[2][kMaxGroupWarps]; /* ends of the warps' own D chains, by row parity */
     float vm_last[2][kMaxGroupWarps], vi_last[2][kMaxGroupWarps], e_warp[2][kMaxGroupWarps];
@@ -66,216 +66,6 @@ struct MwShared
     unsigned long long xbar[2];                  /* ... and their mbarriers */
 };
 
-template <int W, int CL, int R, int Q>
-__device__ __forceinline__ void mw_row(float (&tm)[5][Q], float (&ti)[5][Q], float (&tx)[5],
-                                       const NodeParams<Q> &p, RowState<Q> &rs,
-                                       const float *__restrict__ emis_lane, const RowRec *__restrict__ rec_next,
-                                       const uint16_t *__restrict__ w_next2, int gw, int lane, int par,
-                                       Group<CL, MwShared> &grp, float NB, float JB, float EB, float cE, float cX,
-                                       const CarryBound &cb, float &E_out, float &vC_out)
-{
-    constexpr int TW = W * CL;
-    constexpr int ROW = 256 * TW;
-    constexpr int S1 = (R + 4) % 5, S2 = (R + 3) % 5, S3 = (R + 2) % 5, S4 = (R + 1) % 5, S5 = R;
-    MwShared &sh = *grp.me;
-
-    float vm[Q], vi[Q];
-#pragma unroll
-    for (int i = 0; i < Q; ++i)
-        vm[i] = fmaxf(max3(tm[S1][i] + rs.em[0][i], tm[S2][i] + rs.em[1][i], tm[S3][i] + rs.em[2][i]),
-                      fmaxf(tm[S4][i] + rs.em[3][i], tm[S5][i] + rs.em[4][i]));
-#pragma unroll
-    for (int i = 0; i < Q; ++i)
-        vi[i] = fmaxf(max3(ti[S1][i] + rs.eI[0], ti[S2][i] + rs.eI[1], ti[S3][i] + rs.eI[2]),
-                      fmaxf(ti[S4][i] + rs.eI[3], ti[S5][i] + rs.eI[4]));
-    /* N, J, C live in lanes 0..2 of the group's first warp */
-    float vx = fmaxf(max3(tx[S1] + rs.eN[0], tx[S2] + rs.eN[1], tx[S3] + rs.eN[2]),
-                     fmaxf(tx[S4] + rs.eN[3], tx[S5] + rs.eN[4]));
-
-    /* next row's loads (same software pipeline as the single-warp kernel) */
-    uint32_t code[5];
-    codes_of(rs.w1, code);
-    load_emis_part<Q, 3, 5, ROW>(rs.em, emis_lane, code);
-    load_row_insert(rec_next, rs.eI);
-    if (gw == 0 && lane < 3) load_row_special(rec_next, rs.eN);
-    rs.w1 = rs.w2;
-    rs.w2 = __ldg(w_next2);
-
-    float eloc = vm[0];
-#pragma unroll
-    for (int i = 1; i < Q; ++i) eloc = fmaxf(eloc, vm[i]);
-    float ew = warp_max(eloc);
-    float vm_prev = __shfl_up_sync(FULL, vm[Q - 1], 1);
-    float vi_prev = __shfl_up_sync(FULL, vi[Q - 1], 1);
-    load_emis_part<Q, 0, 3, ROW>(rs.em, emis_lane, code);
-
-    /* D chain inside the warp, nothing from the warp to the left yet: the warp's first node starts at -inf
-     * (its M->D and D->D sources both live in the left warp and arrive together after barrier A) */
-    float d[Q];
-    d[0] = lane == 0 ? NEG_INF : vm_prev + p.MD[0];
-#pragma unroll
-    for (int i = 1; i < Q; ++i) d[i] = fmaxf(vm[i - 1] + p.MD[i], d[i - 1] + p.DD[i]);
-    float din;
-    for (;;)
-    {
-        float old = d[Q - 1];
-        din = __shfl_up_sync(FULL, old, 1);
-        float x = lane == 0 ? NEG_INF : din + p.DD[0];
-        d[0] = fmaxf(d[0], x);
-        x = d[0];
-#pragma unroll
-        for (int i = 1; i < Q; ++i)
-        {
-            x = x + p.DD[i];
-            d[i] = fmaxf(d[i], x);
-            x = d[i];
-        }
-        if (!__any_sync(FULL, d[Q - 1] > old)) break;
-    }
-#ifndef DCP_CLUSTER_XCH
-#define DCP_CLUSTER_XCH 1
-#endif
-    float E, vN, vJ, vC;
-    if constexpr (CL == 2 && DCP_CLUSTER_XCH)
-    {
-        /* A: boundary values, per-warp maxima, the local D chains' ends and the specials, one exchange */
-        const float xN = __shfl_sync(FULL, vx, 0), xJ = __shfl_sync(FULL, vx, 1), xC = __shfl_sync(FULL, vx, 2);
-        const float pay_a[8] = {vm[Q - 1], vi[Q - 1], ew, d[Q - 1], xN, xJ, xC, 0.0f};
-        int s = grp.exchange(gw, lane, pay_a);
-        {
-            const float(*x)[8] = sh.xch[s];
-            if (lane == 0)
-            {
-                vm_prev = gw ? x[gw - 1][0] : NEG_INF;
-                vi_prev = gw ? x[gw - 1][1] : NEG_INF;
-            }
-            E = x[0][2];
-#pragma unroll
-            for (int w = 1; w < TW; ++w) E = fmaxf(E, x[w][2]);
-            vN = x[0][4], vJ = x[0][5], vC = x[0][6];
-        }
-        float din0 = gw ? sh.xch[s][gw - 1][3] : NEG_INF;
-        bool final_d = false;
-        if (DCP_CARRY_BOUND)
-        {
-            const int w = min(max(lane, 1), TW - 1);
-            final_d = carry_cannot_rise<TW>(cb, lane, sh.xch[s][w - 1][0], sh.xch[s][w - 1][3], sh.xch[s][w][3]);
-        }
-        /* carries between warps, lazily: every round ends with an exchange of (did my last D rise, my last D) */
-        for (;;)
-        {
-            const float before = __shfl_sync(FULL, d[Q - 1], 31);
-            for (;;)
-            {
-                float old = d[Q - 1];
-                din = __shfl_up_sync(FULL, old, 1);
-                if (lane == 0) din = din0;
-                float x = lane == 0 ? fmaxf(vm_prev + p.MD[0], din0 + p.DD[0]) : din + p.DD[0];
-                d[0] = fmaxf(d[0], x);
-                x = d[0];
-#pragma unroll
-                for (int i = 1; i < Q; ++i)
-                {
-                    x = x + p.DD[i];
-                    d[i] = fmaxf(d[i], x);
-                    x = d[i];
-                }
-                if (!__any_sync(FULL, d[Q - 1] > old)) break;
-            }
-            if (final_d) break; /* no warp's last D can have risen: the values exchanged at A were final */
-            const float pay_c[8] = {d[Q - 1] > before ? 1.0f : 0.0f, d[Q - 1], 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-            s = grp.exchange(gw, lane, pay_c);
-            float rose = sh.xch[s][0][0];
-#pragma unroll
-            for (int w = 1; w < TW; ++w) rose = fmaxf(rose, sh.xch[s][w][0]);
-            if (rose == 0.0f) break; /* C */
-            din0 = gw ? sh.xch[s][gw - 1][1] : NEG_INF;
-        }
-    }
-    else
-    {
-        if (lane == 31)
-        {
-            GRP_PUT(grp, vm_last[par][gw], vm[Q - 1]);
-            GRP_PUT(grp, vi_last[par][gw], vi[Q - 1]);
-            GRP_PUT(grp, e_warp[par][gw], ew);
-            GRP_PUT(grp, d_loc[par][gw], d[Q - 1]);
-        }
-        if (gw == 0 && lane < 3) GRP_PUT(grp, v_spec[par][lane], vx);
-        grp.sync(); /* A: boundary values, per-warp maxima, specials and the local D chains' ends */
-
-        if (lane == 0)
-        {
-            vm_prev = gw ? sh.vm_last[par][gw - 1] : NEG_INF;
-            vi_prev = gw ? sh.vi_last[par][gw - 1] : NEG_INF;
-        }
-        E = sh.e_warp[par][0];
-#pragma unroll
-        for (int w = 1; w < TW; ++w) E = fmaxf(E, sh.e_warp[par][w]);
-        vN = sh.v_spec[par][0], vJ = sh.v_spec[par][1], vC = sh.v_spec[par][2];
-
-        bool final_d = TW == 2;
-        if (DCP_CARRY_BOUND && TW > 2)
-        {
-            const int w = min(max(lane, 1), TW - 1);
-            final_d = carry_cannot_rise<TW>(cb, lane, sh.vm_last[par][w - 1], sh.d_loc[par][w - 1], sh.d_loc[par][w]);
-        }
-        /* carries between warps: D of the warp's first node = max(V_M(left) + MD, D(left) + DD), then lazily on */
-        float din0 = NEG_INF; /* D of the last node of the warp to the left */
-        for (int round = 0;; ++round)
-        {
-            const int b = round & 1;
-            if (round > 0)
-            {
-                if (lane == 31) GRP_PUT(grp, d_last[b][gw], d[Q - 1]);
-                grp.sync(); /* B */
-            }
-            din0 = gw ? (round == 0 ? sh.d_loc[par][gw - 1] : sh.d_last[b][gw - 1]) : NEG_INF;
-            const float before = __shfl_sync(FULL, d[Q - 1], 31);
-            for (;;)
-            {
-                float old = d[Q - 1];
-                din = __shfl_up_sync(FULL, old, 1);
-                if (lane == 0) din = din0;
-                float x = lane == 0 ? fmaxf(vm_prev + p.MD[0], din0 + p.DD[0]) : din + p.DD[0];
-                d[0] = fmaxf(d[0], x);
-                x = d[0];
-#pragma unroll
-                for (int i = 1; i < Q; ++i)
-                {
-                    x = x + p.DD[i];
-                    d[i] = fmaxf(d[i], x);
-                    x = d[i];
-                }
-                if (!__any_sync(FULL, d[Q - 1] > old)) break;
-            }
-            /* two warps: the left warp has no carry-in, so the D it published at A was final, and nobody reads
-             * the right warp's -- no second round can happen and barrier C is not needed (M = 512: 457 -> 520 GCUPS).
-             * More warps: the same holds whenever the carry bound shows that no warp's last D can rise. */
-            if (final_d) break;
-            const float after = __shfl_sync(FULL, d[Q - 1], 31);
-            if (!grp.any(after > before, sh.flag, CL == 2 ? grp.peer->flag : sh.flag, b)) break; /* C */
-        }
-    }
-
-    float B = max3(vN + NB, vJ + JB, E + EB);
-    tx[R] = fmaxf(E + cE, vx + cX);
-#pragma unroll
-    for (int i = 0; i < Q; ++i)
-    {
-        float pm = i == 0 ? vm_prev : vm[i - 1];
-        float pi = i == 0 ? vi_prev : vi[i - 1];
-        float pd = i == 0 ? din : d[i - 1];
-        tm[R][i] = fmaxf(fmaxf(B + p.ent[i], pm + p.MM[i]), fmaxf(pi + p.IM[i], pd + p.DM[i]));
-        ti[R][i] = fmaxf(vm[i] + p.MI[i], vi[i] + p.II[i]);
-    }
-    E_out = E;
-    vC_out = vC;
-}
-
-#ifndef DCP_MW_V2
-#define DCP_MW_V2 1
-#endif
 /* One-block groups: skipping the second barrier gains 5 % where 12 warps are resident (168 registers: (3,6,4) 339 ->
  * 357, (4,5,3) 343 -> 361 G padded cells/s) and loses 6..9 % in the 255-register classes ((4,8,2) 468 -> 427, (8,8,1)
  * 417 -> 394: the three bound registers push the row into spills) -- so it is on for the former only. */
@@ -283,15 +73,15 @@ __device__ __forceinline__ void mw_row(float (&tm)[5][Q], float (&ti)[5][Q], flo
 #define DCP_CARRY_BOUND_CL1(W, BPS) ((W) * (BPS) > 8)
 #endif
 /*
- * mw_row2: the same row as mw_row, laid out for the instruction scheduler.  ptxas schedules inside basic blocks, and
- * the lazy carry loops of mw_row are blocks of their own that hold nothing but one dependent add/max chain.  Here the
- * first carry round on either side of the rendezvous is straight-line code (a further round is a rare loop after
- * it), and the work that does not depend on the D chain -- Tin_I, the M->M / I->M part of Tin_M before the
- * rendezvous, the B->M part after it -- sits in the same block, so it fills the chain's latency.  Values are
- * bit-identical: only maxima are re-associated, every sum is still (V_src + t).
+ * One DP row of a warp group, laid out for the instruction scheduler.  ptxas schedules inside basic blocks, and lazy
+ * carry loops are blocks of their own that hold nothing but one dependent add/max chain (round 1's layout: issue slots
+ * 43 % busy, `wait` the top stall).  Here the first carry round on either side of the rendezvous is straight-line code
+ * (a further round is a rare loop after it), and the work that does not depend on the D chain -- Tin_I, the M->M /
+ * I->M part of Tin_M before the rendezvous, the B->M part after it -- sits in the same block, so it fills the chain's
+ * latency.  Only maxima are re-associated, every sum is still (V_src + t): bit-identical to the sequential order.
  */
 template <int W, int CL, int R, int Q, int BPS>
-__device__ __forceinline__ void mw_row2(float (&tm)[5][Q], float (&ti)[5][Q], float (&tx)[5],
+__device__ __forceinline__ void mw_row(float (&tm)[5][Q], float (&ti)[5][Q], float (&tx)[5],
                                         const NodeParams<Q> &p, RowState<Q> &rs,
                                         const float *__restrict__ emis_lane, const RowRec *__restrict__ rec_next,
                                         const uint16_t *__restrict__ w_next2, int gw, int lane, int par,
@@ -627,11 +417,7 @@ k_score_mw(const float *__restrict__ emis, const float *__restrict__ trans, cons
 
         float E = NEG_INF, vC = NEG_INF;
         uint32_t j = 1;
-#if DCP_MW_V2
-#define MW_ROW(WW, CC, RR, QQ) mw_row2<WW, CC, RR, QQ, BPS>
-#else
-#define MW_ROW(WW, CC, RR, QQ) mw_row<WW, CC, RR, QQ>
-#endif
+#define MW_ROW(WW, CC, RR, QQ) mw_row<WW, CC, RR, QQ, BPS>
 #define MW_ARGS(jj) recs + min((uint32_t)(jj) + 1u, L), wc + min((uint32_t)(jj) + 3u, L), gw, lane, (int)((jj)&1u), grp
         for (; j + 4 <= L; j += 5)
         {

@@ -337,6 +337,34 @@ def test_scan_from_a_pressed_dcp_database(pkg, o32, tmp_path):
     assert out.returncode == 1 and "imm" in out.stderr
 
 
+def test_every_kernel_class_on_short_ragged_sequences(pkg, o32):
+    """One profile per row of the kernel class table (two pairs per warp, one warp, groups of 2 / 3 / 4 / 6 / 8 warps,
+    two-block groups) against sequences of 1..97 nt, every pair traced: scores, paths and the (sequence, profile)
+    order.  Ragged lengths put a long and a short sequence into the two halves of one warp."""
+    rng = np.random.default_rng(17)
+    sizes = [20, 60, 75, 90, 120, 150, 180, 250, 300, 380, 440, 500, 560, 620, 700, 800, 1000, 1100, 1300, 1700, 2000,
+             2500, 3500]
+    shapes = {(pkg.kernel_shape(m), pkg.kernel_padded_width(m)) for m in sizes}
+    assert len(shapes) >= 20  # every row of the table is exercised
+    cfg = pkg.protein_cfg(pkg.ENTRY_DIST_OCCUPANCY, 0.01)
+    db = pkg.Db(0)
+    twins = []
+    for i, M in enumerate(sizes):
+        p = pkg.ProteinProfile.build(*plan7_profile_inputs(rng, M), cfg, "CLS%02d" % i)
+        db.add(p)
+        twins.append(oracle_twin(o32, p, 0.01))
+    db.commit()
+    seqs = [random_seq(rng, n) for n in (1, 97, 7, 64, 41, 2, 33)]
+    res = db.scan(seqs, lrt_threshold=-1e30)
+    ref = o32.scan(twins, seqs, thr=-1e30, flavour=1)
+    assert np.array_equal(res.alt_loglik, ref["alt"]) and np.array_equal(res.null_loglik, ref["null"])
+    want = ref_paths(ref, len(sizes))
+    assert res.nhits == len(want)
+    for i in range(res.nhits):
+        s, p, path = res.hit_at(i)
+        assert path == want[(s, p)], (s, sizes[p])
+
+
 def test_fp32_path_within_reference_tolerance_of_double_oracle(pkg, o32, o64):
     """The reference's CI runs float and double builds against the same goldens with rel. tolerance 5e-5 for float
     (test/hope_support.h:26).  The fp32 GPU scores must sit within that tolerance of the DOUBLE oracle fed the
