@@ -9,6 +9,8 @@
 #endif
 #include "dcp_kernels.cuh"
 
+#include <type_traits>
+
 namespace
 {
 /* ----------------------------------------------------------------------------------------- */
@@ -45,6 +47,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
     }
 }
 
+/* What the traceback pass (dcp_trace.cu) needs from a row besides the ring: the row's final D values of this lane's
+ * nodes and B.  The score kernels pass no tap (NoTap: nothing is generated). */
+struct NoTap
+{
+};
+template <int Q>
+struct RowTap
+{
+    float d[Q], B;
+};
+template <class Tap, int Q>
+__device__ __forceinline__ void tap_row(Tap *tap, const float (&d)[Q], float B)
+{
+    if constexpr (!std::is_same<Tap, NoTap>::value)
+    {
+#pragma unroll
+        for (int i = 0; i < Q; ++i) tap->d[i] = d[i];
+        tap->B = B;
+    }
+}
+
 /* loads in flight for the next row(s) */
 template <int Q>
 struct RowState
@@ -76,13 +99,14 @@ struct TmaCtx
     uint32_t g; /* rows issued so far by this warp: stage = g & 1, phase parity = (g >> 1) & 1 */
 };
 
-template <int Q, int R, bool TMA>
+template <int Q, int R, bool TMA, class Tap = NoTap>
 __device__ __forceinline__ void score_row(float (&tm)[5][Q], float (&ti)[5][Q], float (&tx)[5],
                                           const NodeParams<Q> &p, RowState<Q> &rs,
                                           const float *__restrict__ emis_lane,
                                           const RowRec *__restrict__ rec_next,
                                           const uint16_t *__restrict__ w_next2, int lane, float NB, float JB,
-                                          float EB, float cE, float cX, float &E_out, float &vx_out, TmaCtx &tc)
+                                          float EB, float cE, float cX, float &E_out, float &vx_out, TmaCtx &tc,
+                                          Tap *tap = nullptr)
 {
     constexpr int S1 = (R + 4) % 5, S2 = (R + 3) % 5, S3 = (R + 2) % 5, S4 = (R + 1) % 5, S5 = R;
     constexpr int QP = Q <= 4 ? 4 : 8, LINE = 32 * QP;
@@ -227,6 +251,7 @@ __device__ __forceinline__ void score_row(float (&tm)[5][Q], float (&ti)[5][Q], 
         float pd = i == 0 ? din : d[i - 1];
         tm[R][i] = fmaxf(tm[R][i], pd + p.DM[i]);
     }
+    tap_row(tap, d, B);
     E_out = E;
     vx_out = vx;
 }
@@ -436,13 +461,14 @@ __device__ __forceinline__ float half_max(float x, int half)
     return half ? hi : lo;
 }
 
-template <int Q, int R>
+template <int Q, int R, class Tap = NoTap>
 __device__ __forceinline__ void score_row_h(float (&tm)[5][Q], float (&ti)[5][Q], float (&tx)[5],
                                             const NodeParams<Q> &p, RowState<Q> &rs,
                                             const float *__restrict__ emis_lane,
                                             const RowRec *__restrict__ rec_next,
                                             const uint16_t *__restrict__ w_next2, int hl, int half, float NB,
-                                            float JB, float EB, float cE, float cX, float &E_out, float &vx_out)
+                                            float JB, float EB, float cE, float cX, float &E_out, float &vx_out,
+                                            Tap *tap = nullptr)
 {
     constexpr int S1 = (R + 4) % 5, S2 = (R + 3) % 5, S3 = (R + 2) % 5, S4 = (R + 1) % 5, S5 = R;
     constexpr int QP = Q <= 4 ? 4 : 8, ROW = 16 * QP, HOFF = 64;
@@ -533,6 +559,7 @@ __device__ __forceinline__ void score_row_h(float (&tm)[5][Q], float (&ti)[5][Q]
         const float pd = i == 0 ? din : d[i - 1];
         tm[R][i] = fmaxf(tm[R][i], pd + p.DM[i]);
     }
+    tap_row(tap, d, B);
     E_out = E;
     vx_out = vx;
 }

@@ -80,13 +80,13 @@ struct MwShared
  * I->M part of Tin_M before the rendezvous, the B->M part after it -- sits in the same block, so it fills the chain's
  * latency.  Only maxima are re-associated, every sum is still (V_src + t): bit-identical to the sequential order.
  */
-template <int W, int CL, int R, int Q, int BPS>
+template <int W, int CL, int R, int Q, int BPS, class Tap = NoTap>
 __device__ __forceinline__ void mw_row(float (&tm)[5][Q], float (&ti)[5][Q], float (&tx)[5],
                                         const NodeParams<Q> &p, RowState<Q> &rs,
                                         const float *__restrict__ emis_lane, const RowRec *__restrict__ rec_next,
                                         const uint16_t *__restrict__ w_next2, int gw, int lane, int par,
                                         Group<CL, MwShared> &grp, float NB, float JB, float EB, float cE, float cX,
-                                        const CarryBound &cb, float &E_out, float &vC_out)
+                                        const CarryBound &cb, float &E_out, float &vC_out, Tap *tap = nullptr)
 {
     constexpr int TW = W * CL;
     constexpr int ROW = 256 * TW;
@@ -328,6 +328,7 @@ __device__ __forceinline__ void mw_row(float (&tm)[5][Q], float (&ti)[5][Q], flo
         const float pd = i == 0 ? din : d[i - 1];
         tm[R][i] = fmaxf(tm[R][i], pd + p.DM[i]);
     }
+    tap_row(tap, d, B);
     E_out = E;
     vC_out = vC;
 }

@@ -2,23 +2,32 @@
  * dcp_trace.cu -- traceback pass for hits only (imm_prod.path of imm_dp_viterbi on the alt dp,
  * consumed by prod_fwrite, src/server/prod.c:153-181).
  *
- * k_trace<Q> re-runs the alt recurrence of one (sequence, profile) hit with the same warp /
- * lane / register layout and the same fp32 operation order as k_score<Q> (so T[L] is bit-equal),
- * and records for every state and row which incoming (transition, source length) won.  The
- * winner is imm's: first maximum, strict '>', over incoming transitions in canonical order and,
- * inside one transition, over the source's emission length ascending -- evaluated on the rounded
- * sums fl(fl(Tin + e) + t), exactly like a start-position interpreter would.
+ * The reference keeps one backpointer per (row, state) of the whole DP matrix of a task (imm_task, reused per
+ * thread: src/server/scan_thread.c:40-55).  Here a hit is traced by row checkpointing, with the score kernels' own
+ * row code (score_row / score_row_h / mw_row: same lane layout, same fp32 operation order, so T[L] is bit-equal
+ * and is cross-checked against the score pass):
+ *
+ *   forward   rows 1..L; before every segment of C rows the five-row ring of Tin_M / Tin_I / Tin_N,J,C -- all the
+ *             state the recurrence carries -- is stored: 40 B per node and C rows instead of a backpointer per cell
+ *   backward  segment by segment from the last: reload the ring, recompute the segment's rows, this time storing
+ *             Tin_M, Tin_I and D of every cell and E, B, Tin_N/J/C of every row into a per-group scratch
+ *             ((C + 5) rows, reused by every segment and every hit: it lives in L2), then walk the path through the
+ *             segment.  No backpointer is ever computed for a cell the path does not visit.
+ *   walk      one warp per hit, one lane per candidate: at state s and row r the lanes evaluate the incoming
+ *             (transition, source length) candidates of Tin_s[r] from the stored values -- fl(fl(Tin_src[r-l] +
+ *             e_src(seq[r-l:r])) + t), the sums a start-position interpreter forms -- and the first lane that
+ *             attains the maximum wins.  That is imm's rule: first maximum, strict '>', over incoming transitions in
+ *             canonical order and, inside one transition, over the source's emission length ascending.
  *
  * Canonical incoming order (imm's own order is not recoverable from the reference tree):
  *   M_k: B, M_{k-1}, I_{k-1}, D_{k-1}    I_k: M_k, I_k    D_k: M_{k-1}, D_{k-1}
  *   E: M_1, M_2, D_2, M_3, D_3, ...      N: S, N    B: S, N, J, E    J: E, J   C: E, C   T: E, C
- *
- * Backpointers: one uint16 per (row, node) [mcode:4 | icode:4 | dcode:3] stored as
- * [row][sub-node][lane] (64-byte coalesced stores) and one uint32 per row for the specials
- * [ecode:15 | n:3 | b:4 | j:3 | c:3 | t:3].
+ * (D_k <= max_{k' < k} V_M(k') because M->D and D->D scores are <= 0 -- checked at commit -- and fp32 addition of a
+ * non-positive number never rounds upwards, so under strict '>' a D state never wins E: E's source is the first
+ * M_k, and inside it the first length, whose sum equals E.)
  */
 #include "dcp_classes.h"
-#include "dcp_kernels.cuh"
+#include "dcp_score_mw.cuh"
 
 #include <algorithm>
 #include <cstring>
@@ -30,797 +39,645 @@ namespace
 struct TraceJob
 {
     uint32_t seq, prof;
-    uint64_t cell_off; /* uint16 units */
-    uint64_t row_off;  /* uint32 units */
+    uint64_t ck_off;   /* floats into the checkpoint buffer */
+    uint64_t step_off; /* first of `cap` steps of this hit in the raw step buffer (filled from the end) */
+    uint32_t cap, pad;
 };
 
-__device__ __forceinline__ void first_max5(const float (&s)[5], float t, int base, float &best, int &code)
+struct TraceArgs
 {
-#pragma unroll
-    for (int l = 0; l < 5; ++l)
-    {
-        float v = s[l] + t;
-        if (v > best) best = v, code = base + l;
-    }
-}
-
-
-/*
- * The trace kernels run one copy of the row code and rotate the five-row rings with register moves (95 moves against
- * ~1700 instructions of a row).  The score kernels' five-fold unrolling (static ring slots, no moves) made the trace
- * kernels 9 x 1700 instructions long, and the instruction cache misses were their top stall (ncu: no_instruction
- * 3.0 of 7.3 cycles per issue, profiles/r01_k_trace_mw_long_ncu.txt).
- */
-template <int Q>
-__device__ __forceinline__ void ring_rotate(float (&tm)[5][Q], float (&ti)[5][Q], float (&tn)[5], float (&tj)[5],
-                                            float (&tc)[5])
-{
-#pragma unroll
-    for (int i = 0; i < Q; ++i)
-    {
-        float a = tm[0][i], b = ti[0][i];
-#pragma unroll
-        for (int s = 0; s < 4; ++s) tm[s][i] = tm[s + 1][i], ti[s][i] = ti[s + 1][i];
-        tm[4][i] = a, ti[4][i] = b;
-    }
-    float a = tn[0], b = tj[0], c = tc[0];
-#pragma unroll
-    for (int s = 0; s < 4; ++s) tn[s] = tn[s + 1], tj[s] = tj[s + 1], tc[s] = tc[s + 1];
-    tn[4] = a, tj[4] = b, tc[4] = c;
-}
-
-/* LN = lanes per hit: 32, or 16 for the half-warp classes (the trace kernel then runs the hit twice, on both halves
- * of the warp: identical values, identical stores -- traceback is not worth a second code path) */
-template <int Q, int R, int LN>
-__device__ __forceinline__ void trace_row(float (&tm)[5][Q], float (&ti)[5][Q], float (&tn)[5], float (&tj)[5],
-                                          float (&tc)[5], const NodeParams<Q> &p,
-                                          const float *__restrict__ emis_lane, const RowRec *__restrict__ rec,
-                                          uint32_t wcode, int lane, const float *__restrict__ sp, uint16_t *__restrict__ cell_bp,
-                                          uint32_t *__restrict__ row_bp, float &T_out)
-{
-    constexpr int QP = Q <= 4 ? 4 : 8;
-    constexpr int S[5] = {(R + 4) % 5, (R + 3) % 5, (R + 2) % 5, (R + 1) % 5, R};
-    const float NN = sp[0], CC = sp[1], JJ = sp[2], NB = sp[3], CT = sp[4], JB = sp[5];
-    const float ET = sp[9], ECC = sp[10], EB = sp[11], EJJ = sp[12];
-    struct { float eI[5], eN[5]; } in;
-    load_row_insert(rec, in.eI);
-    load_row_special(rec, in.eN);
-    uint32_t code[5];
-    codes_of(wcode, code);
-    float em[5][Q];
-    load_emis<Q, LN * QP, LN * 4>(em, emis_lane, code);
-
-    /* W[j-l][X][l] for every emitting state: the five candidate sums per state */
-    float sM[Q][5], sI[Q][5], vm[Q], vi[Q];
-#pragma unroll
-    for (int i = 0; i < Q; ++i)
-    {
-#pragma unroll
-        for (int l = 0; l < 5; ++l)
-        {
-            sM[i][l] = tm[S[l]][i] + em[l][i];
-            sI[i][l] = ti[S[l]][i] + in.eI[l];
-        }
-        vm[i] = fmaxf(max3(sM[i][0], sM[i][1], sM[i][2]), fmaxf(sM[i][3], sM[i][4]));
-        vi[i] = fmaxf(max3(sI[i][0], sI[i][1], sI[i][2]), fmaxf(sI[i][3], sI[i][4]));
-    }
-    float sN[5], sJ[5], sC[5];
-#pragma unroll
-    for (int l = 0; l < 5; ++l)
-    {
-        sN[l] = tn[S[l]] + in.eN[l];
-        sJ[l] = tj[S[l]] + in.eN[l];
-        sC[l] = tc[S[l]] + in.eN[l];
-    }
-    /* sums of the node to the left of this lane's first node */
-    float pM0[5], pI0[5];
-#pragma unroll
-    for (int l = 0; l < 5; ++l)
-    {
-        pM0[l] = __shfl_up_sync(FULL, sM[Q - 1][l], 1, LN);
-        pI0[l] = __shfl_up_sync(FULL, sI[Q - 1][l], 1, LN);
-        if (lane == 0) pM0[l] = NEG_INF, pI0[l] = NEG_INF;
-    }
-
-    /* D chain (order: M_{k-1} by length, then D_{k-1}) */
-    float d[Q];
-    int dcode[Q];
-#pragma unroll
-    for (int i = 0; i < Q; ++i)
-    {
-        float best = NEG_INF;
-        int code = 0;
-        if (i == 0)
-            first_max5(pM0, p.MD[0], 0, best, code);
-        else
-        {
-            first_max5(sM[i - 1], p.MD[i], 0, best, code);
-            float x = d[i - 1] + p.DD[i];
-            if (x > best) best = x, code = 5;
-        }
-        d[i] = best, dcode[i] = code;
-    }
-    float din;
-    for (;;)
-    {
-        float old = d[Q - 1];
-        din = __shfl_up_sync(FULL, old, 1, LN);
-        if (lane == 0) din = NEG_INF;
-        float x = din;
-#pragma unroll
-        for (int i = 0; i < Q; ++i)
-        {
-            x = x + p.DD[i];
-            if (x > d[i]) d[i] = x, dcode[i] = 5;
-            x = d[i];
-        }
-        if (!__any_sync(FULL, d[Q - 1] > old)) break;
-    }
-
-    /* E: first max over M_1, M_2, D_2, ... ; lanes hold increasing k */
-    float ebest = NEG_INF;
-    int ecode = 0;
-#pragma unroll
-    for (int i = 0; i < Q; ++i)
-    {
-        int k0 = lane * Q + i; /* k - 1 */
-        float zero = 0.0f;
-        first_max5(sM[i], zero, k0 * 6, ebest, ecode);
-        if (k0 >= 1)
-        {
-            float v = d[i] + zero;
-            if (v > ebest) ebest = v, ecode = k0 * 6 + 5;
-        }
-    }
-    float E = warp_max(ebest);
-    unsigned who = __ballot_sync(FULL, ebest == E);
-    ecode = __shfl_sync(FULL, ecode, who ? __ffs(who) - 1 : 0);
-
-    /* specials */
-    float best;
-    int ncode = 0, bcode = 0, jcode = 0, ccode = 0, tcode = 0;
-    best = NEG_INF;
-    first_max5(sN, NN, 1, best, ncode);
-    float tinN = best;
-    best = NEG_INF;
-    first_max5(sN, NB, 1, best, bcode);
-    first_max5(sJ, JB, 6, best, bcode);
-    {
-        float v = E + EB;
-        if (v > best) best = v, bcode = 11;
-    }
-    float B = best;
-    best = E + EJJ, jcode = 0;
-    first_max5(sJ, JJ, 1, best, jcode);
-    float tinJ = best;
-    best = E + ECC, ccode = 0;
-    first_max5(sC, CC, 1, best, ccode);
-    float tinC = best;
-    best = E + ET, tcode = 0;
-    first_max5(sC, CT, 1, best, tcode);
-    T_out = best;
-    tn[R] = tinN, tj[R] = tinJ, tc[R] = tinC;
-    if (lane == 0)
-        *row_bp = (uint32_t)ecode | (uint32_t)ncode << 15 | (uint32_t)bcode << 18 | (uint32_t)jcode << 22 |
-                  (uint32_t)ccode << 25 | (uint32_t)tcode << 28;
-
-    /* core Tin + backpointers */
-#pragma unroll
-    for (int i = 0; i < Q; ++i)
-    {
-        float mb = B + p.ent[i];
-        int mcode = 0;
-        if (i == 0)
-        {
-            first_max5(pM0, p.MM[0], 1, mb, mcode);
-            first_max5(pI0, p.IM[0], 6, mb, mcode);
-            float v = din + p.DM[0];
-            if (v > mb) mb = v, mcode = 11;
-        }
-        else
-        {
-            first_max5(sM[i - 1], p.MM[i], 1, mb, mcode);
-            first_max5(sI[i - 1], p.IM[i], 6, mb, mcode);
-            float v = d[i - 1] + p.DM[i];
-            if (v > mb) mb = v, mcode = 11;
-        }
-        float ib = NEG_INF;
-        int icode = 0;
-        first_max5(sM[i], p.MI[i], 0, ib, icode);
-        first_max5(sI[i], p.II[i], 5, ib, icode);
-        tm[R][i] = mb;
-        ti[R][i] = ib;
-        cell_bp[i * LN + lane] = (uint16_t)(mcode | icode << 4 | dcode[i] << 8);
-    }
-}
-
-template <int Q, int LN>
-__global__ void __launch_bounds__(128) k_trace(const float *__restrict__ emis, const float *__restrict__ trans,
-                                               const ProfMeta *__restrict__ metas,
-                                               const SeqMeta *__restrict__ seqs, uint64_t total_rows,
-                                               const RowRec *__restrict__ rows, const uint16_t *__restrict__ wcodes,
-                                               const float *__restrict__ spec, const TraceJob *__restrict__ jobs, uint32_t njobs,
-                                               uint16_t *__restrict__ cell_bp, uint32_t *__restrict__ row_bp,
-                                               float *__restrict__ alt_out)
-{
-    const int lane = threadIdx.x & (LN - 1); /* index inside the hit's lanes; with LN = 16 both halves run the same hit */
-    uint32_t job = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (job >= njobs) return;
-    TraceJob tj_ = jobs[job];
-    ProfMeta pm = metas[tj_.prof];
-    SeqMeta sm = seqs[tj_.seq];
-    NodeParams<Q> p;
-    load_params<Q>(p, trans + pm.trans_off, LN * Q, lane * Q);
-    const float *emis_lane = emis + pm.emis_off + lane * 4;
-    const RowRec *r = rows + (size_t)pm.null_id * total_rows + sm.rec_off + 1; /* record of row 1 */
-    const uint16_t *wc = wcodes + sm.rec_off; /* wc[j] = window of row j */
-    const float *sp = spec + (size_t)tj_.seq * 16;
-    uint16_t *cb = cell_bp + tj_.cell_off;
-    uint32_t *rb = row_bp + tj_.row_off;
-    const uint32_t L = sm.len;
-
-    float tm[5][Q], ti[5][Q], tn[5], tjr[5], tc[5];
-#pragma unroll
-    for (int s = 0; s < 5; ++s)
-    {
-        tn[s] = tjr[s] = tc[s] = NEG_INF;
-#pragma unroll
-        for (int i = 0; i < Q; ++i) tm[s][i] = NEG_INF, ti[s][i] = NEG_INF;
-    }
-    /* row 0: S starts; N <- S, B <- S, M_k <- B; codes are all 0 */
-    const float NN = sp[0], NB = sp[3];
-#pragma unroll
-    for (int i = 0; i < Q; ++i)
-    {
-        tm[4][i] = NB + p.ent[i];
-        cb[i * LN + lane] = 0;
-    }
-    tn[4] = NN;
-    if (lane == 0) rb[0] = 0;
-
-    float T = NEG_INF;
-    uint32_t j = 1;
-    constexpr uint32_t CS = Q * LN; /* cell backpointers per row */
-#pragma unroll 1
-    for (; j <= L; ++j)
-    {
-        trace_row<Q, 0, LN>(tm, ti, tn, tjr, tc, p, emis_lane, r + (j - 1), wc[j], lane, sp, cb + (size_t)j * CS, rb + j, T);
-        ring_rotate<Q>(tm, ti, tn, tjr, tc);
-    }
-    if (lane == 0) alt_out[job] = T;
-}
-
-/* ----------------------------------------------------------------------------------------- */
-/* traceback pass for hits on profiles of 257..2048 nodes: W warps (one block) per hit        */
-/* ----------------------------------------------------------------------------------------- */
-struct MwTraceShared
-{
-    alignas(16) float xch[2][kMaxGroupWarps][12]; /* 2-block groups: Group::exchange buffers ... */
-    unsigned long long xbar[2];                   /* ... and their mbarriers */
-    float pM[2][kMaxGroupWarps][5], pI[2][kMaxGroupWarps][5]; /* the five sums of each warp's last node */
-    float d_last[2][kMaxGroupWarps];
-    float e_best[2][kMaxGroupWarps];
-    int e_code[2][kMaxGroupWarps];
-    int flag[2][2];
+    const float *emis, *trans;
+    const ProfMeta *metas;
+    const SeqMeta *seqs;
+    uint64_t total_recs;
+    const RowRec *rows;
+    const uint16_t *wcodes;
+    const float *spec;
+    const TraceJob *jobs;
+    uint32_t njobs, C;             /* rows per segment (a multiple of 5) */
+    unsigned long long *counter;   /* job queue cursor of this launch (zeroed) */
+    float *ckpt;                   /* ring checkpoints of all jobs */
+    float *scratch;                /* per resident group: (C + 5) rows of cells and row records */
+    dcp_step *steps_raw;
+    uint32_t *nsteps;              /* per job; 0 on failure */
+    float *alt_out;                /* per job: T[L] of the forward pass */
+    uint32_t *errors;              /* [0] walks that left the DP matrix, [1] step buffers that were too small */
 };
 
-/* cell backpointers of a row: [sub-node][warp][lane] */
-template <int W, int CL, int R, int Q>
-__device__ __forceinline__ void trace_row_mw(float (&tm)[5][Q], float (&ti)[5][Q], float (&tn)[5], float (&tj)[5],
-                                             float (&tc)[5], const NodeParams<Q> &p,
-                                             const float *__restrict__ emis_lane, const RowRec *__restrict__ rec,
-                                             uint32_t wcode, int warp, int lane, int par,
-                                             Group<CL, MwTraceShared> &grp,
-                                             const float *__restrict__ sp, uint16_t *__restrict__ cell_bp,
-                                             uint32_t *__restrict__ row_bp, float &T_out)
+/* shape of a kernel class as the trace kernels see it: TW = 0 two hits^W halves per warp (16 lanes per hit; the trace
+ * kernel runs the same hit on both halves: identical values, identical stores), 1 one warp, >= 2 a group of warps */
+template <int TW, int Q>
+struct Shape
 {
-    constexpr int TW = W * CL; /* `warp` is the warp's index in the whole group, 0..TW-1 */
-    constexpr int ROW = 256 * TW;
-    constexpr int S[5] = {(R + 4) % 5, (R + 3) % 5, (R + 2) % 5, (R + 1) % 5, R};
-    MwTraceShared &sh = *grp.me;
-    const float NN = sp[0], CC = sp[1], JJ = sp[2], NB = sp[3], CT = sp[4], JB = sp[5];
-    const float ET = sp[9], ECC = sp[10], EB = sp[11], EJJ = sp[12];
-    struct { float eI[5], eN[5]; } in;
-    load_row_insert(rec, in.eI);
-    load_row_special(rec, in.eN);
-    uint32_t code[5];
-    codes_of(wcode, code);
-    float em[5][Q];
-    load_emis<Q, ROW>(em, emis_lane, code);
+    static constexpr int LN = TW == 0 ? 16 : 32;         /* lanes per warp-unit of a hit */
+    static constexpr int NW = TW == 0 ? 1 : TW;          /* warps per hit */
+    static constexpr int CL = NW > kMaxW ? 2 : 1;        /* blocks per hit */
+    static constexpr int W = NW / CL;                    /* warps per block and hit */
+    static constexpr int QP = Q <= 4 ? 4 : 8;
+    static constexpr int NT = LN * NW;                   /* threads that hold distinct nodes */
+    static constexpr int MP = NT * QP;                   /* padded node slots = floats per emission line */
+    static constexpr int NP = NT * Q;                    /* stride of the transition arrays */
+    static constexpr int BLOCK = TW <= 1 ? 128 : W * 32; /* TW <= 1: four independent warps per block */
+    static constexpr int MINB = TW <= 1 ? 2 : (CL == 2 ? 1 : (8 / W > 0 ? 8 / W : 1));
+    static constexpr int CK = 10 * MP + 32;              /* floats per ring checkpoint: [slot 5][M, I][MP] + [slot 5][4] */
+    static constexpr int RR = 8;                         /* floats per row record of the scratch: E, B, Tin_N, Tin_J, Tin_C */
+    static_assert(TW <= 1 || Q > 4, "warp groups use eight-float lanes");
+    __host__ __device__ static size_t scratch_floats(uint32_t C) { return (size_t)(C + 5) * (3 * MP + RR); }
+};
 
-    float sM[Q][5], sI[Q][5];
-#pragma unroll
-    for (int i = 0; i < Q; ++i)
-#pragma unroll
-        for (int l = 0; l < 5; ++l)
-        {
-            sM[i][l] = tm[S[l]][i] + em[l][i];
-            sI[i][l] = ti[S[l]][i] + in.eI[l];
-        }
-    float sN[5], sJ[5], sC[5];
-#pragma unroll
-    for (int l = 0; l < 5; ++l)
+/* a lane's Q values as one or two 16-byte stores: [quad][thread][4], so a warp's store is contiguous */
+template <int Q, int NT>
+__device__ __forceinline__ void store_q(float *dst, const float (&v)[Q])
+{
+    float4 a = make_float4(v[0], Q > 1 ? v[1 % Q] : 0.f, Q > 2 ? v[2 % Q] : 0.f, Q > 3 ? v[3 % Q] : 0.f);
+    *reinterpret_cast<float4 *>(dst) = a;
+    if (Q > 4)
     {
-        sN[l] = tn[S[l]] + in.eN[l];
-        sJ[l] = tj[S[l]] + in.eN[l];
-        sC[l] = tc[S[l]] + in.eN[l];
+        float4 b = make_float4(v[4 % Q], Q > 5 ? v[5 % Q] : 0.f, Q > 6 ? v[6 % Q] : 0.f, Q > 7 ? v[7 % Q] : 0.f);
+        *reinterpret_cast<float4 *>(dst + NT * 4) = b;
     }
-    float pM0[5], pI0[5];
+}
+template <int Q, int NT>
+__device__ __forceinline__ void load_q(const float *src, float (&v)[Q])
+{
+    const float4 a = __ldcg(reinterpret_cast<const float4 *>(src));
+    const float t[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-    for (int l = 0; l < 5; ++l)
+    for (int i = 0; i < (Q < 4 ? Q : 4); ++i) v[i] = t[i];
+    if (Q > 4)
     {
-        pM0[l] = __shfl_up_sync(FULL, sM[Q - 1][l], 1);
-        pI0[l] = __shfl_up_sync(FULL, sI[Q - 1][l], 1);
-        if (lane == 0) pM0[l] = NEG_INF, pI0[l] = NEG_INF; /* the left warp's values arrive with barrier A */
+        const float4 b = __ldcg(reinterpret_cast<const float4 *>(src + NT * 4));
+        const float u[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 4; i < Q; ++i) v[i % Q] = u[i - 4];
     }
+}
+/* slot of node n (0-based) in a cell array laid out by store_q */
+template <int Q, int NT>
+__device__ __forceinline__ uint32_t cell_slot(uint32_t n)
+{
+    const uint32_t t = n / Q, sub = n % Q;
+    return (sub >> 2) * (NT * 4) + t * 4 + (sub & 3);
+}
 
-    /* D chain (order: M_{k-1} by length, then D_{k-1}), first inside the warp: its first node has no source yet */
-    float d[Q];
-    int dcode[Q];
-#pragma unroll
-    for (int i = 0; i < Q; ++i)
+/* who this thread is inside its hit */
+struct Who
+{
+    int lane;  /* lane of the warp-unit: 0..LN-1 */
+    int half;  /* TW = 0: which half of the warp */
+    int gw;    /* warp of the group */
+    int t;     /* gw * LN + lane: owner of nodes t * Q .. t * Q + Q - 1 */
+    int xs;    /* 0..2: this thread carries N / J / C; 3: it writes E and B of the row; else -1 */
+};
+
+struct Specials
+{
+    float NN, CC, JJ, NB, CT, JB, ET, ECC, EB, EJJ, cE, cX;
+};
+
+/* ----------------------------------------------------------------------------------------- */
+/* rows j0 + 1 .. min(L, j0 + C) from the ring as it stands after row j0                       */
+/* ----------------------------------------------------------------------------------------- */
+template <int TW, int Q, int R>
+__device__ __forceinline__ void one_row(float (&tm)[5][Q], float (&ti)[5][Q], float (&tx)[5], const NodeParams<Q> &p,
+                                        RowState<Q> &rs, const float *__restrict__ emis_lane,
+                                        const RowRec *__restrict__ recs, const uint16_t *__restrict__ wc, uint32_t L,
+                                        uint32_t jj, uint32_t j0, const Specials &k, const Who &me,
+                                        Group<Shape<TW, Q>::CL, MwShared> &grp, const CarryBound &cb, bool store,
+                                        float *__restrict__ cells, float *__restrict__ rowrec, float &E_L, float &vC_L)
+{
+    using S = Shape<TW, Q>;
+    const RowRec *rn = recs + min(jj + 1u, L);
+    const uint16_t *wn = wc + min(jj + 3u, L);
+    RowTap<Q> tap;
+    float E, vC;
+    if constexpr (TW == 0)
+        score_row_h<Q, R>(tm, ti, tx, p, rs, emis_lane, rn, wn, me.lane, me.half, k.NB, k.JB, k.EB, k.cE, k.cX, E, vC, &tap);
+    else if constexpr (TW == 1)
     {
-        float best = NEG_INF;
-        int c = 0;
-        if (i == 0)
-            first_max5(pM0, p.MD[0], 0, best, c);
-        else
-        {
-            first_max5(sM[i - 1], p.MD[i], 0, best, c);
-            float x = d[i - 1] + p.DD[i];
-            if (x > best) best = x, c = 5;
-        }
-        d[i] = best, dcode[i] = c;
-    }
-    float din = NEG_INF;
-    for (;;)
-    {
-        float old = d[Q - 1];
-        din = __shfl_up_sync(FULL, old, 1);
-        if (lane == 0) din = NEG_INF;
-        float x = din;
-#pragma unroll
-        for (int i = 0; i < Q; ++i)
-        {
-            x = x + p.DD[i];
-            if (x > d[i]) d[i] = x, dcode[i] = 5;
-            x = d[i];
-        }
-        if (!__any_sync(FULL, d[Q - 1] > old)) break;
-    }
-#ifndef DCP_CLUSTER_XCH
-#define DCP_CLUSTER_XCH 1
-#endif
-    float E, ew;
-    int ecode;
-    if constexpr (CL == 2 && DCP_CLUSTER_XCH)
-    {
-        /* A: the five sums of each warp's last node and the end of its local D chain, one exchange (no cluster barrier) */
-        const float pay_a[12] = {sM[Q - 1][0], sM[Q - 1][1], sM[Q - 1][2], sM[Q - 1][3], sM[Q - 1][4], sI[Q - 1][0],
-                                 sI[Q - 1][1], sI[Q - 1][2], sI[Q - 1][3], sI[Q - 1][4], d[Q - 1],     0.0f};
-        int s = grp.exchange(warp, lane, pay_a);
-        if (lane == 0 && warp)
-        {
-#pragma unroll
-            for (int l = 0; l < 5; ++l) pM0[l] = sh.xch[s][warp - 1][l], pI0[l] = sh.xch[s][warp - 1][5 + l];
-            first_max5(pM0, p.MD[0], 0, d[0], dcode[0]);
-        }
-        float din0 = warp ? sh.xch[s][warp - 1][10] : NEG_INF;
-        for (;;)
-        {
-            const float before = __shfl_sync(FULL, d[Q - 1], 31);
-            for (;;)
-            {
-                float old = d[Q - 1];
-                din = __shfl_up_sync(FULL, old, 1);
-                if (lane == 0) din = din0;
-                float x = din;
-#pragma unroll
-                for (int i = 0; i < Q; ++i)
-                {
-                    x = x + p.DD[i];
-                    if (x > d[i]) d[i] = x, dcode[i] = 5;
-                    x = d[i];
-                }
-                if (!__any_sync(FULL, d[Q - 1] > old)) break;
-            }
-            /* E candidates of this warp with the D values of this round (final when no warp's last D rose) */
-            float ebest = NEG_INF;
-            ecode = 0;
-#pragma unroll
-            for (int i = 0; i < Q; ++i)
-            {
-                int k0 = warp * 32 * Q + lane * Q + i; /* k - 1 */
-                float zero = 0.0f;
-                first_max5(sM[i], zero, k0 * 6, ebest, ecode);
-                if (k0 >= 1)
-                {
-                    float v = d[i] + zero;
-                    if (v > ebest) ebest = v, ecode = k0 * 6 + 5;
-                }
-            }
-            ew = warp_max(ebest);
-            unsigned who = __ballot_sync(FULL, ebest == ew);
-            ecode = __shfl_sync(FULL, ecode, who ? __ffs(who) - 1 : 0);
-            const float pay_c[12] = {d[Q - 1] > before ? 1.0f : 0.0f, d[Q - 1], ew, __int_as_float(ecode), 0.0f, 0.0f, 0.0f,
-                                     0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-            s = grp.exchange(warp, lane, pay_c); /* C */
-            float rose = sh.xch[s][0][0];
-#pragma unroll
-            for (int w = 1; w < TW; ++w) rose = fmaxf(rose, sh.xch[s][w][0]);
-            if (rose == 0.0f) break;
-            din0 = warp ? sh.xch[s][warp - 1][1] : NEG_INF;
-        }
-        E = sh.xch[s][0][2];
-        ecode = __float_as_int(sh.xch[s][0][3]);
-#pragma unroll
-        for (int w = 1; w < TW; ++w)
-            if (sh.xch[s][w][2] > E) E = sh.xch[s][w][2], ecode = __float_as_int(sh.xch[s][w][3]);
+        TmaCtx tc = {nullptr, nullptr, 0};
+        score_row<Q, R, false>(tm, ti, tx, p, rs, emis_lane, rn, wn, me.lane, k.NB, k.JB, k.EB, k.cE, k.cX, E, vC, tc, &tap);
     }
     else
+        mw_row<S::W, S::CL, R, Q, 1>(tm, ti, tx, p, rs, emis_lane, rn, wn, me.gw, me.lane, (int)(jj & 1u), grp, k.NB, k.JB,
+                                     k.EB, k.cE, k.cX, cb, E, vC, &tap);
+    /* TW <= 1: vC is this lane's special state (V_C in lane 2); warp groups: V_C itself */
+    if (jj == L) E_L = E, vC_L = vC;
+    if (store)
     {
-        if (lane == 31)
+        const uint32_t slot = jj - j0 + 4u;
+        float *c = cells + (size_t)slot * (3 * S::MP);
+        store_q<Q, S::NT>(c, tm[R]);
+        store_q<Q, S::NT>(c + S::MP, ti[R]);
+        store_q<Q, S::NT>(c + 2 * S::MP, tap.d);
+        if (me.xs >= 0)
         {
-#pragma unroll
-            for (int l = 0; l < 5; ++l)
-            {
-                GRP_PUT(grp, pM[par][warp][l], sM[Q - 1][l]);
-                GRP_PUT(grp, pI[par][warp][l], sI[Q - 1][l]);
-            }
-            GRP_PUT(grp, d_last[0][warp], d[Q - 1]);
+            float *rr = rowrec + (size_t)slot * S::RR;
+            if (me.xs < 3)
+                rr[2 + me.xs] = tx[R];
+            else
+                rr[0] = E, rr[1] = tap.B;
         }
-        grp.sync(); /* A: the five sums of each warp's last node and the end of its local D chain */
-        if (lane == 0 && warp)
-        {
-#pragma unroll
-            for (int l = 0; l < 5; ++l) pM0[l] = sh.pM[par][warp - 1][l], pI0[l] = sh.pI[par][warp - 1][l];
-            /* M_{k-1} -> D_k candidates of the warp's first node come first in the order; its D_{k-1} follows below */
-            first_max5(pM0, p.MD[0], 0, d[0], dcode[0]);
-        }
-
-        /* carries between warps, lazily; the per-warp E candidates ride on the same barrier (C): when no warp's last D
-         * rose, every D was final and so are the candidates published in that round */
-        for (int round = 0;; ++round)
-        {
-            const int b = round & 1;
-            if (round > 0)
-            {
-                if (lane == 31) GRP_PUT(grp, d_last[b][warp], d[Q - 1]);
-                grp.sync(); /* B */
-            }
-            const float din0 = warp ? sh.d_last[b][warp - 1] : NEG_INF;
-            const float before = __shfl_sync(FULL, d[Q - 1], 31);
-            for (;;)
-            {
-                float old = d[Q - 1];
-                din = __shfl_up_sync(FULL, old, 1);
-                if (lane == 0) din = din0;
-                float x = din;
-#pragma unroll
-                for (int i = 0; i < Q; ++i)
-                {
-                    x = x + p.DD[i];
-                    if (x > d[i]) d[i] = x, dcode[i] = 5;
-                    x = d[i];
-                }
-                if (!__any_sync(FULL, d[Q - 1] > old)) break;
-            }
-            const float after = __shfl_sync(FULL, d[Q - 1], 31);
-
-            /* E: first max over M_1, M_2, D_2, ... ; warps and lanes hold increasing k */
-            float ebest = NEG_INF;
-            ecode = 0;
-#pragma unroll
-            for (int i = 0; i < Q; ++i)
-            {
-                int k0 = warp * 32 * Q + lane * Q + i; /* k - 1 */
-                float zero = 0.0f;
-                first_max5(sM[i], zero, k0 * 6, ebest, ecode);
-                if (k0 >= 1)
-                {
-                    float v = d[i] + zero;
-                    if (v > ebest) ebest = v, ecode = k0 * 6 + 5;
-                }
-            }
-            ew = warp_max(ebest);
-            unsigned who = __ballot_sync(FULL, ebest == ew);
-            ecode = __shfl_sync(FULL, ecode, who ? __ffs(who) - 1 : 0);
-            if (lane == 0)
-            {
-                GRP_PUT(grp, e_best[par][warp], ew);
-                GRP_PUT(grp, e_code[par][warp], ecode);
-            }
-            /* round 0 already used the left warp's local chain end; a warp whose last D rose has to be re-read */
-            if (!grp.any(after > before, sh.flag, CL == 2 ? grp.peer->flag : sh.flag, b)) break; /* C */
-        }
-        E = sh.e_best[par][0];
-        ecode = sh.e_code[par][0];
-#pragma unroll
-        for (int w = 1; w < TW; ++w)
-            if (sh.e_best[par][w] > E) E = sh.e_best[par][w], ecode = sh.e_code[par][w];
-    }
-
-    /* specials: every warp keeps its own copy of the N/J/C rings (identical values) */
-    float best;
-    int ncode = 0, bcode = 0, jcode = 0, ccode = 0, tcode = 0;
-    best = NEG_INF;
-    first_max5(sN, NN, 1, best, ncode);
-    float tinN = best;
-    best = NEG_INF;
-    first_max5(sN, NB, 1, best, bcode);
-    first_max5(sJ, JB, 6, best, bcode);
-    {
-        float v = E + EB;
-        if (v > best) best = v, bcode = 11;
-    }
-    float B = best;
-    best = E + EJJ, jcode = 0;
-    first_max5(sJ, JJ, 1, best, jcode);
-    float tinJ = best;
-    best = E + ECC, ccode = 0;
-    first_max5(sC, CC, 1, best, ccode);
-    float tinC = best;
-    best = E + ET, tcode = 0;
-    first_max5(sC, CT, 1, best, tcode);
-    T_out = best;
-    tn[R] = tinN, tj[R] = tinJ, tc[R] = tinC;
-    if (warp == 0 && lane == 0)
-        *row_bp = (uint32_t)ecode | (uint32_t)ncode << 15 | (uint32_t)bcode << 18 | (uint32_t)jcode << 22 |
-                  (uint32_t)ccode << 25 | (uint32_t)tcode << 28;
-
-#pragma unroll
-    for (int i = 0; i < Q; ++i)
-    {
-        float mb = B + p.ent[i];
-        int mcode = 0;
-        if (i == 0)
-        {
-            first_max5(pM0, p.MM[0], 1, mb, mcode);
-            first_max5(pI0, p.IM[0], 6, mb, mcode);
-            float v = din + p.DM[0];
-            if (v > mb) mb = v, mcode = 11;
-        }
-        else
-        {
-            first_max5(sM[i - 1], p.MM[i], 1, mb, mcode);
-            first_max5(sI[i - 1], p.IM[i], 6, mb, mcode);
-            float v = d[i - 1] + p.DM[i];
-            if (v > mb) mb = v, mcode = 11;
-        }
-        float ib = NEG_INF;
-        int icode = 0;
-        first_max5(sM[i], p.MI[i], 0, ib, icode);
-        first_max5(sI[i], p.II[i], 5, ib, icode);
-        tm[R][i] = mb;
-        ti[R][i] = ib;
-        cell_bp[i * (32 * TW) + warp * 32 + lane] = (uint16_t)(mcode | icode << 4 | dcode[i] << 8);
     }
 }
 
-template <int W, int CL, int Q>
-__global__ void __launch_bounds__(W * 32) k_trace_mw(const float *__restrict__ emis, const float *__restrict__ trans,
-                                                     const ProfMeta *__restrict__ metas,
-                                                     const SeqMeta *__restrict__ seqs, uint64_t total_rows,
-                                                     const RowRec *__restrict__ rows,
-                                                     const uint16_t *__restrict__ wcodes,
-                                                     const float *__restrict__ spec,
-                                                     const TraceJob *__restrict__ jobs, uint32_t njobs,
-                                                     uint16_t *__restrict__ cell_bp, uint32_t *__restrict__ row_bp,
-                                                     float *__restrict__ alt_out)
+template <int TW, int Q>
+__device__ __forceinline__ void run_rows(float (&tm)[5][Q], float (&ti)[5][Q], float (&tx)[5], const NodeParams<Q> &p,
+                                         const float *__restrict__ emis_lane, const RowRec *__restrict__ recs,
+                                         const uint16_t *__restrict__ wc, uint32_t L, uint32_t j0, uint32_t C,
+                                         const Specials &k, const Who &me, Group<Shape<TW, Q>::CL, MwShared> &grp,
+                                         const CarryBound &cb, bool store, float *__restrict__ cells,
+                                         float *__restrict__ rowrec, float &E_L, float &vC_L)
 {
-    constexpr int TW = W * CL;
-    __shared__ MwTraceShared sh;
-    Group<CL, MwTraceShared> grp;
-    grp.init(&sh);
-    if constexpr (CL == 2) grp.exchange_init(W);
-    const int lane = threadIdx.x & 31, warp = grp.rank * W + (threadIdx.x >> 5);
-    const uint32_t job = blockIdx.x / CL;
-    if (job >= njobs) return;
-    TraceJob tj_ = jobs[job];
-    ProfMeta pm = metas[tj_.prof];
-    SeqMeta sm = seqs[tj_.seq];
-    NodeParams<Q> p;
-    load_params<Q>(p, trans + pm.trans_off, 32 * Q * TW, warp * 32 * Q + lane * Q);
-    const float *emis_lane = emis + pm.emis_off + warp * 256 + lane * 4;
-    const RowRec *r = rows + (size_t)pm.null_id * total_rows + sm.rec_off; /* r[j] = record of row j */
-    const uint16_t *wc = wcodes + sm.rec_off;
-    const float *sp = spec + (size_t)tj_.seq * 16;
-    uint16_t *cb = cell_bp + tj_.cell_off;
-    uint32_t *rb = row_bp + tj_.row_off;
-    const uint32_t L = sm.len;
-    constexpr uint32_t CS = Q * 32 * TW;
-
-    float tm[5][Q], ti[5][Q], tn[5], tjr[5], tc[5];
+    using S = Shape<TW, Q>;
+    /* pipeline prologue of the score kernels, at row j0 + 1 */
+    RowState<Q> rs;
 #pragma unroll
-    for (int s = 0; s < 5; ++s)
+    for (int l = 0; l < 5; ++l) rs.eN[l] = NEG_INF;
     {
-        tn[s] = tjr[s] = tc[s] = NEG_INF;
-#pragma unroll
-        for (int i = 0; i < Q; ++i) tm[s][i] = NEG_INF, ti[s][i] = NEG_INF;
+        uint32_t code[5];
+        codes_of(__ldg(wc + j0 + 1), code);
+        load_emis<Q, S::MP, S::LN * 4>(rs.em, emis_lane, code);
     }
-    const float NN = sp[0], NB = sp[3];
-#pragma unroll
-    for (int i = 0; i < Q; ++i)
-    {
-        tm[4][i] = NB + p.ent[i];
-        cb[i * (32 * TW) + warp * 32 + lane] = 0;
-    }
-    tn[4] = NN;
-    if (warp == 0 && lane == 0) rb[0] = 0;
-    if (CL == 2) grp.sync(); /* both blocks' shared memory exists before the first remote store */
-
-    float T = NEG_INF;
-    uint32_t j = 1;
-#define TR_ARGS(jj) r + (jj), wc[(jj)], warp, lane, (int)((jj)&1u), grp, sp, cb + (size_t)(jj) * CS, rb + (jj), T
+    load_row_insert(recs + j0 + 1, rs.eI);
+    if (me.xs >= 0 && me.xs < 3) load_row_special(recs + j0 + 1, rs.eN);
+    rs.w1 = __ldg(wc + min(j0 + 2u, L));
+    rs.w2 = __ldg(wc + min(j0 + 3u, L));
+    rs.w3 = 0;
+    /* whole groups of five rows (static ring slots); rows past L recompute on clamped inputs and are ignored */
+    const uint32_t j1 = min(L, j0 + C);
+#define ONE(RR, jj) one_row<TW, Q, RR>(tm, ti, tx, p, rs, emis_lane, recs, wc, L, (jj), j0, k, me, grp, cb, store, cells, rowrec, E_L, vC_L)
 #pragma unroll 1
-    for (; j <= L; ++j)
+    for (uint32_t j = j0 + 1; j <= j1; j += 5)
     {
-        trace_row_mw<W, CL, 0, Q>(tm, ti, tn, tjr, tc, p, emis_lane, TR_ARGS(j));
-        ring_rotate<Q>(tm, ti, tn, tjr, tc);
+        ONE(0, j);
+        ONE(1, j + 1);
+        ONE(2, j + 2);
+        ONE(3, j + 3);
+        ONE(4, j + 4);
     }
-#undef TR_ARGS
-    if (warp == 0 && lane == 0) alt_out[job] = T;
-    if (CL == 2) grp.sync(); /* no block may exit while its peer can still store into its shared memory */
+#undef ONE
+}
+
+/* ----------------------------------------------------------------------------------------- */
+/* the walk                                                                                   */
+/* ----------------------------------------------------------------------------------------- */
+enum { W_S, W_N, W_B, W_E, W_J, W_C, W_T, W_M, W_I, W_D };
+
+struct Walker
+{
+    int st;
+    uint32_t k, r, len, n;
+    bool bad, over, done;
+};
+
+__device__ __forceinline__ uint16_t state_id_of(int st, uint32_t k)
+{
+    switch (st)
+    {
+    case W_M: return (uint16_t)(PROTEIN_MATCH_STATE | k);
+    case W_I: return (uint16_t)(PROTEIN_INSERT_STATE | k);
+    case W_D: return (uint16_t)(PROTEIN_DELETE_STATE | k);
+    case W_S: return PROTEIN_S_STATE;
+    case W_N: return PROTEIN_N_STATE;
+    case W_B: return PROTEIN_B_STATE;
+    case W_E: return PROTEIN_E_STATE;
+    case W_J: return PROTEIN_J_STATE;
+    case W_C: return PROTEIN_C_STATE;
+    default: return PROTEIN_T_STATE;
+    }
+}
+
+/* frame-table code of seq[r-l:r] from the packed window of row r */
+__device__ __forceinline__ uint32_t code_of_len(uint32_t w, uint32_t l)
+{
+    const uint32_t off = l == 1 ? 0u : l == 2 ? 4u : l == 3 ? 20u : l == 4 ? 84u : 340u;
+    return off + (w & ((1u << (2u * l)) - 1u));
 }
 
 /*
- * Follow the backpointers from (T, row L) to S.  mode 0: count steps; mode 1: write them
- * (reversed, then flipped in place) at steps + step_off[job].
+ * Walk while the current row lies in the segment above row j0 (rows j0 + 1 .. ; scratch slot of row x = x - j0 + 4,
+ * slots 0..4 = the ring rows j0 - 4 .. j0).  All 32 lanes of the warp run this with identical walker state; lane c
+ * evaluates candidate c.
  */
-enum { W_S, W_N, W_B, W_E, W_J, W_C, W_T, W_M, W_I, W_D };
-
-__global__ void k_walk(const ProfMeta *__restrict__ metas, const SeqMeta *__restrict__ seqs,
-                       const TraceJob *__restrict__ jobs, uint32_t njobs, const uint16_t *__restrict__ cell_bp,
-                       const uint32_t *__restrict__ row_bp, int mode, uint32_t *__restrict__ nsteps,
-                       const uint64_t *__restrict__ step_off, dcp_step *__restrict__ steps,
-                       uint32_t *__restrict__ errors)
+template <int TW, int Q>
+__device__ __forceinline__ void walk_segment(Walker &w, uint32_t j0, uint32_t M, const float *__restrict__ cells,
+                                             const float *__restrict__ rowrec, const float *__restrict__ emis,
+                                             const float *__restrict__ tr, const RowRec *__restrict__ recs,
+                                             const uint16_t *__restrict__ wc, const Specials &sp,
+                                             dcp_step *__restrict__ out, uint32_t cap, int c)
 {
-    uint32_t job = blockIdx.x * blockDim.x + threadIdx.x;
-    if (job >= njobs) return;
-    TraceJob tj = jobs[job];
-    const uint32_t Q = metas[tj.prof].Q, W = metas[tj.prof].W, LN = metas[tj.prof].LN;
-    const uint32_t CS = Q * LN * W;
-    const uint16_t *cb = cell_bp + tj.cell_off;
-    const uint32_t *rb = row_bp + tj.row_off;
-    const uint32_t L = seqs[tj.seq].len;
-    dcp_step *out = mode ? steps + step_off[job] : nullptr;
-    const uint32_t limit = mode ? nsteps[job] : 0xffffffffu;
+    using S = Shape<TW, Q>;
+    auto cell = [&](int which, uint32_t n, uint32_t row) -> float {
+        return __ldcg(cells + ((size_t)(row - j0 + 4u) * 3 + which) * S::MP + cell_slot<Q, S::NT>(n));
+    };
+    auto rowv = [&](int idx, uint32_t row) -> float { return __ldcg(rowrec + (size_t)(row - j0 + 4u) * S::RR + idx); };
+    auto emis_m = [&](uint32_t n, uint32_t code) -> float {
+        const uint32_t t = n / Q, sub = n % Q, wp = t / S::LN, ln = t % S::LN;
+        return __ldg(emis + (size_t)code * S::MP + wp * (S::LN * S::QP) + (sub >> 2) * (S::LN * 4) + ln * 4 + (sub & 3));
+    };
+    auto par = [&](int which, uint32_t n) -> float { return __ldg(tr + which * S::NP + n); };
 
-    int st = W_T;
-    uint32_t k = 0, r = L, len = 0, n = 0;
-    bool bad = false;
-    for (;;)
+    while (!w.done && !w.bad && !w.over && (w.r > j0 || j0 == 0))
     {
-        uint16_t id;
-        switch (st)
+        /* arrive: emit this state's step (the path is produced backwards: the buffer fills from its end) */
+        if (w.n >= cap)
         {
-        case W_M: id = (uint16_t)(PROTEIN_MATCH_STATE | k); break;
-        case W_I: id = (uint16_t)(PROTEIN_INSERT_STATE | k); break;
-        case W_D: id = (uint16_t)(PROTEIN_DELETE_STATE | k); break;
-        case W_S: id = PROTEIN_S_STATE; break;
-        case W_N: id = PROTEIN_N_STATE; break;
-        case W_B: id = PROTEIN_B_STATE; break;
-        case W_E: id = PROTEIN_E_STATE; break;
-        case W_J: id = PROTEIN_J_STATE; break;
-        case W_C: id = PROTEIN_C_STATE; break;
-        default: id = PROTEIN_T_STATE; break;
+            w.over = true;
+            break;
         }
-        if (mode)
+        if (c == 0)
         {
-            if (n >= limit) { bad = true; break; }
-            out[n].state_id = id, out[n].seqlen = (uint8_t)len;
+            dcp_step s;
+            s.state_id = state_id_of(w.st, w.k), s.seqlen = (uint8_t)w.len;
+            out[cap - 1u - w.n] = s;
         }
-        n++;
-        if (st == W_S) break;
-        if (n > 0x7ffffff0u) { bad = true; break; }
-        uint32_t rw = rb[r];
-        uint32_t src_len = 0;
-        int nst = st;
-        uint32_t nk = k;
-        if (st == W_M || st == W_I || st == W_D)
+        w.n++;
+        if (w.st == W_S)
         {
-            uint32_t node = k - 1;
-            uint16_t c = cb[(size_t)r * CS + (node % Q) * (LN * W) + node / Q]; /* [sub][warp][lane] */
-            if (st == W_M)
+            w.done = true;
+            break;
+        }
+        const uint32_t r = w.r;
+        int nst = w.st;
+        uint32_t nk = w.k, src_len = 0;
+        if (r == 0)
+        {
+            /* row 0: S -> N, S -> B, B -> M_k are the only finite entries */
+            if (w.st == W_M) nst = W_B;
+            else if (w.st == W_N || w.st == W_B) nst = W_S;
+            else w.bad = true;
+        }
+        else if (w.st == W_E)
+        {
+            /* first M_k in node order, then the first length, whose sum equals E[r] */
+            const float E = rowv(0, r);
+            const uint32_t win = __ldg(wc + r);
+            bool found = false;
+            for (uint32_t nb = 0; nb < M && !found; nb += 32)
             {
-                uint32_t m = c & 15;
-                if (m == 0) nst = W_B;
-                else if (m <= 5) nst = W_M, nk = k - 1, src_len = m;
-                else if (m <= 10) nst = W_I, nk = k - 1, src_len = m - 5;
-                else nst = W_D, nk = k - 1;
+                const uint32_t n = nb + (uint32_t)c;
+                int lhit = 0;
+                if (n < M)
+                {
+#pragma unroll
+                    for (int l = 5; l >= 1; --l)
+                    {
+                        const float s = cell(0, n, r - l) + emis_m(n, code_of_len(win, l));
+                        if (s == E) lhit = l;
+                    }
+                }
+                const unsigned who = __ballot_sync(FULL, lhit != 0);
+                if (who)
+                {
+                    const int src = __ffs(who) - 1;
+                    nk = nb + (uint32_t)src + 1u;
+                    src_len = (uint32_t)__shfl_sync(FULL, lhit, src);
+                    nst = W_M;
+                    found = true;
+                }
             }
-            else if (st == W_I)
+            if (!found) w.bad = true;
+        }
+        else
+        {
+            const uint32_t win = __ldg(wc + r);
+            const RowRec *rec = recs + r;
+            float v = NEG_INF;
+            if (w.st == W_M)
             {
-                uint32_t m = (c >> 4) & 15;
-                if (m <= 4) nst = W_M, src_len = m + 1;
-                else nst = W_I, src_len = m - 4;
+                const uint32_t n = w.k - 1u;
+                if (c == 0)
+                    v = rowv(1, r) + par(7, n);
+                else if (c <= 10)
+                {
+                    if (n >= 1)
+                    {
+                        const int which = c <= 5 ? 0 : 1;
+                        const uint32_t l = (uint32_t)(c - 1) % 5u + 1u;
+                        const float e = which == 0 ? emis_m(n - 1, code_of_len(win, l)) : __ldg(&rec->eI[l - 1]);
+                        v = (cell(which, n - 1, r - l) + e) + par(which, n);
+                    }
+                }
+                else if (c == 11)
+                {
+                    if (n >= 1) v = cell(2, n - 1, r) + par(2, n);
+                }
+            }
+            else if (w.st == W_I)
+            {
+                const uint32_t n = w.k - 1u;
+                if (c < 10)
+                {
+                    const int which = c < 5 ? 0 : 1;
+                    const uint32_t l = (uint32_t)c % 5u + 1u;
+                    const float e = which == 0 ? emis_m(n, code_of_len(win, l)) : __ldg(&rec->eI[l - 1]);
+                    v = (cell(which, n, r - l) + e) + par(5 + which, n);
+                }
+            }
+            else if (w.st == W_D)
+            {
+                const uint32_t n = w.k - 1u;
+                if (n >= 1)
+                {
+                    if (c < 5)
+                    {
+                        const uint32_t l = (uint32_t)c + 1u;
+                        v = (cell(0, n - 1, r - l) + emis_m(n - 1, code_of_len(win, l))) + par(3, n);
+                    }
+                    else if (c == 5)
+                        v = cell(2, n - 1, r) + par(4, n);
+                }
             }
             else
             {
-                uint32_t m = (c >> 8) & 7;
-                if (m <= 4) nst = W_M, nk = k - 1, src_len = m + 1;
-                else nst = W_D, nk = k - 1;
+                /* specials: candidate 0 = E (T, C, J) or S (N, B: row 0 only); 1..5 and 6..10 = an emitting source by
+                 * length; 11 = E -> B */
+                const uint32_t l = (uint32_t)(c - 1) % 5u + 1u;
+                const float eN = (c >= 1 && c <= 10) ? __ldg(&rec->eN[l - 1]) : 0.0f;
+                if (w.st == W_T)
+                {
+                    if (c == 0) v = rowv(0, r) + sp.ET;
+                    else if (c <= 5) v = (rowv(4, r - l) + eN) + sp.CT;
+                }
+                else if (w.st == W_C)
+                {
+                    if (c == 0) v = rowv(0, r) + sp.ECC;
+                    else if (c <= 5) v = (rowv(4, r - l) + eN) + sp.CC;
+                }
+                else if (w.st == W_J)
+                {
+                    if (c == 0) v = rowv(0, r) + sp.EJJ;
+                    else if (c <= 5) v = (rowv(3, r - l) + eN) + sp.JJ;
+                }
+                else if (w.st == W_N)
+                {
+                    if (c >= 1 && c <= 5) v = (rowv(2, r - l) + eN) + sp.NN;
+                }
+                else /* W_B */
+                {
+                    if (c >= 1 && c <= 5) v = (rowv(2, r - l) + eN) + sp.NB;
+                    else if (c >= 6 && c <= 10) v = (rowv(3, r - l) + eN) + sp.JB;
+                    else if (c == 11) v = rowv(0, r) + sp.EB;
+                }
             }
-            if (nk == 0 && nst != W_B) { bad = true; break; }
+            const float best = warp_max(v);
+            const unsigned who = __ballot_sync(FULL, v == best);
+            const uint32_t code = who ? (uint32_t)(__ffs(who) - 1) : 0u;
+            switch (w.st)
+            {
+            case W_M:
+                if (code == 0) nst = W_B;
+                else if (code <= 5) nst = W_M, nk = w.k - 1, src_len = code;
+                else if (code <= 10) nst = W_I, nk = w.k - 1, src_len = code - 5;
+                else nst = W_D, nk = w.k - 1;
+                if (nk == 0 && nst != W_B) w.bad = true;
+                break;
+            case W_I:
+                if (code <= 4) nst = W_M, src_len = code + 1;
+                else nst = W_I, src_len = code - 4;
+                break;
+            case W_D:
+                if (code <= 4) nst = W_M, nk = w.k - 1, src_len = code + 1;
+                else nst = W_D, nk = w.k - 1;
+                if (nk == 0) w.bad = true;
+                break;
+            case W_T:
+            case W_C:
+                if (code == 0) nst = W_E; else nst = W_C, src_len = code;
+                break;
+            case W_J:
+                if (code == 0) nst = W_E; else nst = W_J, src_len = code;
+                break;
+            case W_N:
+                if (code == 0) nst = W_S; else nst = W_N, src_len = code;
+                break;
+            default: /* W_B */
+                if (code == 0) nst = W_S;
+                else if (code <= 5) nst = W_N, src_len = code;
+                else if (code <= 10) nst = W_J, src_len = code - 5;
+                else nst = W_E;
+                break;
+            }
         }
-        else if (st == W_T)
-        {
-            uint32_t m = (rw >> 28) & 7;
-            if (m == 0) nst = W_E; else nst = W_C, src_len = m;
-        }
-        else if (st == W_C)
-        {
-            uint32_t m = (rw >> 25) & 7;
-            if (m == 0) nst = W_E; else nst = W_C, src_len = m;
-        }
-        else if (st == W_J)
-        {
-            uint32_t m = (rw >> 22) & 7;
-            if (m == 0) nst = W_E; else nst = W_J, src_len = m;
-        }
-        else if (st == W_B)
-        {
-            uint32_t m = (rw >> 18) & 15;
-            if (m == 0) nst = W_S;
-            else if (m <= 5) nst = W_N, src_len = m;
-            else if (m <= 10) nst = W_J, src_len = m - 5;
-            else nst = W_E;
-        }
-        else if (st == W_N)
-        {
-            uint32_t m = (rw >> 15) & 7;
-            if (m == 0) nst = W_S; else nst = W_N, src_len = m;
-        }
-        else /* W_E */
-        {
-            uint32_t m = rw & 0x7fff;
-            nk = m / 6 + 1;
-            uint32_t sub = m % 6;
-            if (sub <= 4) nst = W_M, src_len = sub + 1; else nst = W_D;
-        }
-        if (src_len > r) { bad = true; break; }
-        if (nst == W_S && r != 0) { bad = true; break; }
-        r -= src_len;
-        st = nst, k = nk, len = src_len;
+        if (src_len > r) w.bad = true;
+        if (nst == W_S && r != 0) w.bad = true;
+        if (w.bad) break;
+        w.r = r - src_len;
+        w.st = nst, w.k = nk, w.len = src_len;
     }
-    if (bad)
-    {
-        atomicAdd(errors, 1u);
-        if (!mode) nsteps[job] = 0;
-        return;
-    }
-    if (!mode)
-        nsteps[job] = n;
-    else
-        for (uint32_t a = 0, b = n - 1; a < b; ++a, --b)
-        {
-            dcp_step t = out[a];
-            out[a] = out[b], out[b] = t;
-        }
 }
 
-template <int Q, int LN>
-void launch_trace(cudaStream_t st, uint32_t njobs, const dcpgpu_db *db, const dcpgpu_seqs *sq, const RowRec *rows,
-                  const uint16_t *wcodes, const float *spec, const TraceJob *jobs, uint16_t *cell_bp, uint32_t *row_bp, float *alt)
-{
-    k_trace<Q, LN><<<(njobs + 3) / 4, 128, 0, st>>>(db->d_emis, db->d_trans, db->d_metas, sq->d_metas, sq->total + sq->nseq, rows,
-                                                wcodes, spec, jobs, njobs, cell_bp, row_bp, alt);
-}
-
-/* one warp per hit (TW = 1) or a group of TW warps, one block or the two blocks of a cluster */
+/* ----------------------------------------------------------------------------------------- */
+/* one hit after the other: forward pass with ring checkpoints, then segments backwards        */
+/* ----------------------------------------------------------------------------------------- */
 template <int TW, int Q>
-void launch_trace_class(cudaStream_t st, uint32_t njobs, const dcpgpu_db *db, const dcpgpu_seqs *sq, const RowRec *rows,
-                        const uint16_t *wcodes, const float *spec, const TraceJob *jobs, uint16_t *cell_bp,
-                        uint32_t *row_bp, float *alt)
+__global__ void __launch_bounds__(Shape<TW, Q>::BLOCK, Shape<TW, Q>::MINB) k_trace(const TraceArgs a)
 {
+    using S = Shape<TW, Q>;
+    constexpr int CL = S::CL;
+    __shared__ MwShared sh;
+    Group<CL, MwShared> grp;
+    grp.init(&sh);
+    Who me;
+    const int wlane = threadIdx.x & 31;
+    uint32_t group; /* index of this hit-at-a-time unit on the device: owner of one scratch area */
     if constexpr (TW <= 1)
-        launch_trace<Q, TW == 1 ? 32 : 16>(st, njobs, db, sq, rows, wcodes, spec, jobs, cell_bp, row_bp, alt);
+    {
+        me.lane = wlane & (S::LN - 1), me.half = TW == 0 ? wlane >> 4 : 0, me.gw = 0;
+        group = blockIdx.x * (S::BLOCK / 32) + (threadIdx.x >> 5);
+    }
     else
     {
-        constexpr int CL = TW > kMaxW ? 2 : 1, W = TW / CL;
-        launch_group(k_trace_mw<W, CL, Q>, CL, njobs * CL, W * 32, st, db->d_emis, db->d_trans, db->d_metas, sq->d_metas,
-                     sq->total + sq->nseq, rows, wcodes, spec, jobs, njobs, cell_bp, row_bp, alt);
+        me.lane = wlane, me.half = 0, me.gw = grp.rank * S::W + (int)(threadIdx.x >> 5);
+        group = blockIdx.x / CL;
+        if (CL == 2) grp.sync(); /* both blocks' shared memory exists before the first remote store */
+        if constexpr (CL == 2) grp.exchange_init(S::W);
     }
+    me.t = me.gw * S::LN + me.lane;
+    me.xs = (me.gw == 0 && me.lane < 4) ? me.lane : -1;
+    const bool walker = me.gw == 0; /* the warp that walks (TW = 0: both halves, as one warp of 32 candidates) */
+    float *const scr = a.scratch + (size_t)group * S::scratch_floats(a.C);
+    float *const cells = scr + (size_t)me.t * 4;                  /* this thread's first quad of row slot 0 */
+    float *const rowrec = scr + (size_t)(a.C + 5) * (3 * S::MP);  /* row records after the cell rows */
+    const uint32_t C = a.C;
+
+    for (;;)
+    {
+        uint32_t job;
+        if constexpr (TW <= 1)
+        {
+            unsigned long long it = 0;
+            if (wlane == 0) it = atomicAdd(a.counter, 1ULL);
+            job = (uint32_t)min(__shfl_sync(FULL, it, 0), (unsigned long long)a.njobs);
+        }
+        else
+        {
+            if (grp.rank == 0 && threadIdx.x == 0)
+            {
+                unsigned long long it = atomicAdd(a.counter, 1ULL);
+                GRP_PUT(grp, item, it);
+            }
+            grp.sync();
+            job = (uint32_t)min(sh.item, (unsigned long long)a.njobs);
+            grp.sync();
+        }
+        if (job >= a.njobs) break;
+        const TraceJob tj = a.jobs[job];
+        const ProfMeta pm = a.metas[tj.prof];
+        const SeqMeta sm = a.seqs[tj.seq];
+        const uint32_t L = sm.len;
+        NodeParams<Q> p;
+        load_params<Q>(p, a.trans + pm.trans_off, S::NP, me.t * Q);
+        CarryBound cb = {NEG_INF, NEG_INF, NEG_INF};
+        if (S::NW > 2 && me.lane < S::NW)
+        {
+            const float *b = a.trans + pm.trans_off + 8 * S::NP; /* [3][NW] after the eight parameter arrays */
+            cb.S = __ldg(b + me.lane), cb.md0 = __ldg(b + S::NW + me.lane), cb.dd0 = __ldg(b + 2 * S::NW + me.lane);
+        }
+        const float *emis_prof = a.emis + pm.emis_off;
+        const float *emis_lane = emis_prof + me.gw * (S::LN * S::QP) + me.lane * 4;
+        const RowRec *recs = a.rows + (size_t)pm.null_id * a.total_recs + sm.rec_off;
+        const uint16_t *wc = a.wcodes + sm.rec_off;
+        const float *spv = a.spec + (size_t)tj.seq * 16;
+        Specials k;
+        k.NN = spv[0], k.CC = spv[1], k.JJ = spv[2], k.NB = spv[3], k.CT = spv[4], k.JB = spv[5];
+        k.ET = spv[9], k.ECC = spv[10], k.EB = spv[11], k.EJJ = spv[12];
+        k.cE = me.xs == 0 ? NEG_INF : (me.xs == 1 ? k.EJJ : k.ECC);
+        k.cX = me.xs == 0 ? k.NN : (me.xs == 1 ? k.JJ : k.CC);
+        const uint32_t nseg = (L + C - 1) / C;
+        float *const ck = a.ckpt + tj.ck_off + (size_t)me.t * 4;
+
+        float tm[5][Q], ti[5][Q], tx[5];
+#pragma unroll
+        for (int s = 0; s < 5; ++s)
+        {
+            tx[s] = NEG_INF;
+#pragma unroll
+            for (int i = 0; i < Q; ++i) tm[s][i] = NEG_INF, ti[s][i] = NEG_INF;
+        }
+        /* row 0: S = 0, B[0] = NB, Tin_N[0] = NN, Tin_Mk[0] = B[0] + entry_k */
+#pragma unroll
+        for (int i = 0; i < Q; ++i) tm[4][i] = k.NB + p.ent[i];
+        tx[4] = me.xs == 0 ? k.NN : NEG_INF;
+
+        /* ---- forward: checkpoint the ring before every segment ---- */
+        float E_L = NEG_INF, vC_L = NEG_INF;
+#pragma unroll 1
+        for (uint32_t s = 0; s < nseg; ++s)
+        {
+            float *c = ck + (size_t)s * S::CK;
+#pragma unroll
+            for (int q = 0; q < 5; ++q)
+            {
+                store_q<Q, S::NT>(c + (q * 2 + 0) * S::MP, tm[q]);
+                store_q<Q, S::NT>(c + (q * 2 + 1) * S::MP, ti[q]);
+            }
+            if (me.xs >= 0 && me.xs < 3)
+            {
+                float *cx = a.ckpt + tj.ck_off + (size_t)s * S::CK + 10 * S::MP;
+#pragma unroll
+                for (int q = 0; q < 5; ++q) cx[q * 4 + me.xs] = tx[q];
+            }
+            run_rows<TW, Q>(tm, ti, tx, p, emis_lane, recs, wc, L, s * C, C, k, me, grp, cb, false, cells, rowrec, E_L, vC_L);
+        }
+        if constexpr (TW == 0) vC_L = __shfl_sync(FULL, vC_L, 2, 16);
+        if constexpr (TW == 1) vC_L = __shfl_sync(FULL, vC_L, 2);
+        const float T = fmaxf(E_L + k.ET, vC_L + k.CT);
+        /* warp groups: the shared row buffers alternate by row parity, and the backward pass restarts at other rows */
+        if constexpr (TW > 1) grp.sync();
+
+        /* ---- backward: recompute a segment with its cells stored, walk through it ---- */
+        Walker w;
+        w.st = W_T, w.k = 0, w.r = L, w.len = 0, w.n = 0, w.bad = false, w.over = false, w.done = false;
+        dcp_step *out = a.steps_raw + tj.step_off;
+#pragma unroll 1
+        for (uint32_t s = nseg; s-- > 0;)
+        {
+            const uint32_t j0 = s * C;
+            const float *c = ck + (size_t)s * S::CK;
+#pragma unroll
+            for (int q = 0; q < 5; ++q)
+            {
+                load_q<Q, S::NT>(c + (q * 2 + 0) * S::MP, tm[q]);
+                load_q<Q, S::NT>(c + (q * 2 + 1) * S::MP, ti[q]);
+                tx[q] = NEG_INF;
+            }
+            if (me.xs >= 0 && me.xs < 3)
+            {
+                const float *cx = a.ckpt + tj.ck_off + (size_t)s * S::CK + 10 * S::MP;
+#pragma unroll
+                for (int q = 0; q < 5; ++q) tx[q] = __ldcg(cx + q * 4 + me.xs);
+            }
+            /* the ring rows j0 - 4 .. j0 are slots 0 .. 4 of the scratch: the walk reads up to five rows back */
+#pragma unroll
+            for (int q = 0; q < 5; ++q)
+            {
+                float *d = cells + (size_t)q * (3 * S::MP);
+                store_q<Q, S::NT>(d, tm[q]);
+                store_q<Q, S::NT>(d + S::MP, ti[q]);
+                if (me.xs >= 0 && me.xs < 3) rowrec[q * S::RR + 2 + me.xs] = tx[q];
+            }
+            float e_dummy = NEG_INF, v_dummy = NEG_INF;
+            run_rows<TW, Q>(tm, ti, tx, p, emis_lane, recs, wc, L, j0, C, k, me, grp, cb, true, cells, rowrec, e_dummy, v_dummy);
+            if constexpr (TW <= 1) __syncwarp();
+            else grp.sync();
+            if (walker) walk_segment<TW, Q>(w, j0, pm.M, scr, rowrec, emis_prof, a.trans + pm.trans_off, recs, wc, k, out, tj.cap, wlane);
+            if constexpr (TW <= 1) __syncwarp();
+            else grp.sync();
+        }
+        if (walker && wlane == 0)
+        {
+            const bool ok = w.done && !w.bad && !w.over;
+            a.nsteps[job] = ok ? w.n : 0u;
+            a.alt_out[job] = T;
+            if (!ok) atomicAdd(a.errors + (w.over ? 1 : 0), 1u);
+        }
+    }
+    if constexpr (CL == 2) grp.sync(); /* no block may exit while its peer can still store into its shared memory */
+}
+
+/* dense copy of the paths: hit i owns nsteps[i] steps at the end of its raw buffer */
+__global__ void k_pack(const TraceJob *__restrict__ jobs, uint32_t njobs, const uint32_t *__restrict__ nsteps,
+                       const uint64_t *__restrict__ off, const dcp_step *__restrict__ raw, dcp_step *__restrict__ out)
+{
+    const uint32_t job = blockIdx.x;
+    if (job >= njobs) return;
+    const uint32_t n = nsteps[job];
+    const dcp_step *src = raw + jobs[job].step_off + (jobs[job].cap - n);
+    dcp_step *dst = out + off[job];
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+
+template <int TW, int Q>
+cudaError_t launch_trace(cudaStream_t st, int sm_count, TraceArgs a, float *scratch_pool, size_t *scratch_used,
+                         bool dry)
+{
+    using S = Shape<TW, Q>;
+    /* resident groups: as many as the device holds at once, no more than there are hits */
+    const uint32_t per_sm = TW <= 1 ? (uint32_t)(S::MINB * S::BLOCK / 32) : (uint32_t)S::MINB;
+    uint32_t groups = S::CL == 2 ? (uint32_t)(sm_count / 2) : (uint32_t)sm_count * per_sm;
+    groups = std::min(groups, a.njobs);
+    if (TW <= 1) groups = (groups + (S::BLOCK / 32) - 1) / (S::BLOCK / 32) * (S::BLOCK / 32); /* whole blocks of warps */
+    const size_t need = (size_t)groups * S::scratch_floats(a.C);
+    if (dry)
+    {
+        *scratch_used += need;
+        return cudaSuccess;
+    }
+    a.scratch = scratch_pool + *scratch_used;
+    *scratch_used += need;
+    unsigned blocks;
+    if (TW <= 1) blocks = groups / (S::BLOCK / 32);
+    else blocks = groups * S::CL;
+    return launch_group(k_trace<TW, Q>, S::CL, blocks, S::BLOCK, st, a);
+}
+
+uint32_t segment_rows(uint32_t Lmax)
+{
+    /* about sqrt(L) rows, a multiple of five: checkpoints and scratch both shrink with it */
+    uint32_t c = (uint32_t)std::ceil(std::sqrt((double)Lmax) / 5.0) * 5u;
+    return std::min(250u, std::max(20u, c));
 }
 
 } // namespace
@@ -830,92 +687,144 @@ enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const
 {
     cudaStream_t st = db->stream;
     const size_t nhits = res->hits.size();
-    /* backpointer budget per batch */
     size_t free_b = 0, total_b = 0;
     CU_TRY(cudaMemGetInfo(&free_b, &total_b));
     const size_t budget = std::min<size_t>(std::max<size_t>(free_b / 2, (size_t)64 << 20), (size_t)16 << 30);
-
     const std::vector<float> &score_alt = res->hit_alt; /* score pass result of each hit */
 
+    /* checkpoint floats of a hit, given its class's segment length */
+    auto ck_floats = [&](const HitRec &h, uint32_t C) -> size_t {
+        const ProfMeta &m = db->metas[h.prof];
+        const size_t MP = (size_t)m.LN * m.W * m.QP, L = sq->metas[h.seq].len;
+        return ((L + C - 1) / C) * (10 * MP + 32);
+    };
+    auto step_cap = [&](const HitRec &h, uint32_t mul) -> uint64_t {
+        const uint64_t L = sq->metas[h.seq].len, M = db->metas[h.prof].M;
+        return std::min<uint64_t>((2 * (L + M) + 64) * mul, (L + 2) * (M + 3) + 8);
+    };
+
     size_t done = 0;
+    uint32_t cap_mul = 1;
     while (done < nhits)
     {
-        /* take hits while their backpointers fit the budget; group the batch by class */
+        /* segment length per class from the longest sequence among ALL remaining hits of the class would need a
+         * pass of its own; the longest sequence of the batch is close enough and keeps this a single loop */
+        uint32_t Lmax = 1;
+        for (size_t i = done; i < nhits; ++i) Lmax = std::max(Lmax, sq->metas[res->hits[i].seq].len);
+        const uint32_t C = segment_rows(Lmax);
+
+        /* take hits while their checkpoints and step buffers fit the budget; group the batch by class */
         std::vector<TraceJob> jobs;
-        size_t cells = 0, rowsz = 0, end = done;
+        size_t ckf = 0, rawsteps = 0, end = done;
         while (end < nhits)
         {
             const HitRec &h = res->hits[end];
-            uint32_t QW = db->metas[h.prof].Q * db->metas[h.prof].W * db->metas[h.prof].LN; /* padded nodes */
-            size_t L1 = (size_t)sq->metas[h.seq].len + 1;
-            size_t need = L1 * QW * sizeof(uint16_t) + L1 * sizeof(uint32_t);
-            if (!jobs.empty() && (cells * 2 + rowsz * 4 + need > budget)) break;
-            jobs.push_back({h.seq, h.prof, cells, rowsz});
-            cells += L1 * QW;
-            rowsz += L1;
+            const size_t need_ck = ck_floats(h, C);
+            const uint64_t cap = step_cap(h, cap_mul);
+            if (cap > 0xfffffff0ull) return dcp_error(RC_EFAIL, "path buffer of a hit exceeds 2^32 steps");
+            if (!jobs.empty() && ((ckf + need_ck) * 4 + (rawsteps + cap) * sizeof(dcp_step) > budget)) break;
+            jobs.push_back({h.seq, h.prof, ckf, rawsteps, (uint32_t)cap, 0});
+            ckf += need_ck, rawsteps += cap;
             ++end;
         }
         const uint32_t nj = (uint32_t)jobs.size();
-        /* order jobs by class so each launch sees a contiguous range */
+        /* order jobs by class so each launch sees a contiguous range; inside a class the longest sequences first */
         std::vector<uint32_t> order(nj);
         for (uint32_t i = 0; i < nj; ++i) order[i] = i;
-        std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
-            return db->metas[jobs[a].prof].cls < db->metas[jobs[b].prof].cls;
+        std::stable_sort(order.begin(), order.end(), [&](uint32_t x, uint32_t y) {
+            const uint32_t cx = db->metas[jobs[x].prof].cls, cy = db->metas[jobs[y].prof].cls;
+            if (cx != cy) return cx < cy;
+            return sq->metas[jobs[x].seq].len > sq->metas[jobs[y].seq].len;
         });
         std::vector<TraceJob> sorted(nj);
         for (uint32_t i = 0; i < nj; ++i) sorted[i] = jobs[order[i]];
 
-        DevBuf b_jobs, b_cells, b_rows, b_alt, b_n, b_off, b_err, b_steps;
+        /* class ranges */
+        struct Range { uint32_t a, b, cls; };
+        std::vector<Range> ranges;
+        for (uint32_t x = 0; x < nj;)
+        {
+            uint32_t cls = db->metas[sorted[x].prof].cls, y = x;
+            while (y < nj && db->metas[sorted[y].prof].cls == cls) ++y;
+            ranges.push_back({x, y, cls});
+            x = y;
+        }
+
+        TraceArgs base = {};
+        base.emis = db->d_emis, base.trans = db->d_trans, base.metas = db->d_metas, base.seqs = sq->d_metas;
+        base.total_recs = sq->total + sq->nseq, base.rows = d_rows, base.wcodes = d_wcodes, base.spec = d_spec;
+        base.C = C;
+        /* the trace kernels depend on (warps per pair, nodes per lane) only, not on the occupancy variant */
+        auto launch_range = [&](const Range &r, cudaStream_t s, TraceArgs a, float *pool, size_t *used, bool dry) -> int {
+            const dcp_class &kc = *dcp_class_at(r.cls);
+            a.njobs = r.b - r.a;
+            bool launched = false;
+            cudaError_t e = cudaSuccess;
+#define X(TW, Q, BPS, RATE)                                                                                       \
+    if (!launched && kc.tw == TW && kc.q == Q)                                                                    \
+    {                                                                                                             \
+        e = launch_trace<TW, Q>(s, db->sm_count, a, pool, used, dry);                                             \
+        launched = true;                                                                                          \
+    }
+            DCP_CLASS_TABLE(X)
+#undef X
+            if (!launched) return -1;
+            return e == cudaSuccess ? 0 : 1;
+        };
+        size_t scratch_floats = 0;
+        for (const Range &r : ranges)
+            if (launch_range(r, nullptr, base, nullptr, &scratch_floats, true) < 0)
+                return dcp_error(RC_EFAIL, "no trace kernel for this kernel class");
+
+        DevBuf b_jobs, b_ck, b_scr, b_raw, b_alt, b_n, b_off, b_err, b_cnt, b_steps;
         CU_TRY(b_jobs.alloc(nj * sizeof(TraceJob), db));
-        CU_TRY(b_cells.alloc(cells * sizeof(uint16_t), db));
-        CU_TRY(b_rows.alloc(rowsz * sizeof(uint32_t), db));
+        CU_TRY(b_ck.alloc(ckf * sizeof(float), db));
+        CU_TRY(b_scr.alloc(scratch_floats * sizeof(float), db));
+        CU_TRY(b_raw.alloc(rawsteps * sizeof(dcp_step), db));
         CU_TRY(b_alt.alloc(nj * sizeof(float), db));
         CU_TRY(b_n.alloc(nj * sizeof(uint32_t), db));
         CU_TRY(b_off.alloc(nj * sizeof(uint64_t), db));
-        CU_TRY(b_err.alloc(sizeof(uint32_t), db));
+        CU_TRY(b_err.alloc(2 * sizeof(uint32_t), db));
+        CU_TRY(b_cnt.alloc(ranges.size() * sizeof(unsigned long long), db));
         CU_TRY(cudaMemcpyAsync(b_jobs.p, sorted.data(), nj * sizeof(TraceJob), cudaMemcpyHostToDevice, st));
-        CU_TRY(cudaMemsetAsync(b_err.p, 0, sizeof(uint32_t), st));
+        CU_TRY(cudaMemsetAsync(b_err.p, 0, 2 * sizeof(uint32_t), st));
+        CU_TRY(cudaMemsetAsync(b_cnt.p, 0, ranges.size() * sizeof(unsigned long long), st));
+        base.ckpt = b_ck.as<float>(), base.steps_raw = b_raw.as<dcp_step>(), base.errors = b_err.as<uint32_t>();
         /* one launch per kernel class, side by side on the main and side streams: a class often holds a handful of
          * hits, and a trace launch lasts as long as its longest sequence however few hits it has */
         StreamFan fan(db);
         CU_TRY(fan.fork());
-        for (uint32_t a = 0; a < nj;)
+        size_t used = 0;
+        for (size_t ri = 0; ri < ranges.size(); ++ri)
         {
-            cudaStream_t st = fan.next();
-            uint32_t cls = db->metas[sorted[a].prof].cls, b = a;
-            while (b < nj && db->metas[sorted[b].prof].cls == cls) ++b;
+            const Range &r = ranges[ri];
+            TraceArgs a = base;
+            a.jobs = b_jobs.as<TraceJob>() + r.a, a.nsteps = b_n.as<uint32_t>() + r.a, a.alt_out = b_alt.as<float>() + r.a;
+            a.counter = b_cnt.as<unsigned long long>() + ri;
+            if (launch_range(r, fan.next(), a, b_scr.as<float>(), &used, false) != 0)
             {
-                const dcp_class &kc = *dcp_class_at(cls);
-                bool launched = false;
-                /* the trace kernels depend on (warps per pair, nodes per lane) only, not on the occupancy variant */
-#define X(TW, Q, BPS, RATE)                                                                                       \
-    if (!launched && kc.tw == TW && kc.q == Q)                                                                    \
-    {                                                                                                             \
-        launch_trace_class<TW, Q>(st, b - a, db, sq, d_rows, d_wcodes, d_spec, b_jobs.as<TraceJob>() + a,         \
-                                  b_cells.as<uint16_t>(), b_rows.as<uint32_t>(), b_alt.as<float>() + a);          \
-        launched = true;                                                                                          \
-    }
-                DCP_CLASS_TABLE(X)
-#undef X
-                if (!launched) return dcp_error(RC_EFAIL, "no trace kernel for this kernel class");
+                CU_TRY(cudaGetLastError());
+                return dcp_error(RC_EFAIL, "trace kernel launch failed");
             }
             (*launches)++;
-            a = b;
         }
         CU_TRY(fan.join());
         CU_TRY(cudaGetLastError());
-        k_walk<<<(nj + 63) / 64, 64, 0, st>>>(db->d_metas, sq->d_metas, b_jobs.as<TraceJob>(), nj,
-                                              b_cells.as<uint16_t>(), b_rows.as<uint32_t>(), 0, b_n.as<uint32_t>(),
-                                              nullptr, nullptr, b_err.as<uint32_t>());
-        (*launches)++;
         std::vector<uint32_t> ns(nj);
         std::vector<float> talt(nj);
-        uint32_t nerr = 0;
+        uint32_t nerr[2] = {0, 0};
         CU_TRY(cudaMemcpyAsync(ns.data(), b_n.p, nj * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaMemcpyAsync(talt.data(), b_alt.p, nj * sizeof(float), cudaMemcpyDeviceToHost, st));
-        CU_TRY(cudaMemcpyAsync(&nerr, b_err.p, sizeof nerr, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(nerr, b_err.p, sizeof nerr, cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaStreamSynchronize(st));
-        if (nerr) return dcp_error(RC_EFAIL, "traceback walked off the DP matrix");
+        if (nerr[0]) return dcp_error(RC_EFAIL, "traceback walked off the DP matrix");
+        if (nerr[1])
+        {
+            /* a path longer than 2 (L + M) + 64 steps (many passes through the core): retry the batch with room */
+            if (cap_mul >= 4096) return dcp_error(RC_EFAIL, "traceback path does not fit its buffer");
+            cap_mul *= 8;
+            continue;
+        }
         std::vector<uint64_t> off(nj);
         uint64_t tot = 0;
         for (uint32_t i = 0; i < nj; ++i) off[i] = tot, tot += ns[i];
@@ -927,15 +836,13 @@ enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const
         }
         CU_TRY(b_steps.alloc(std::max<uint64_t>(tot, 1) * sizeof(dcp_step), db));
         CU_TRY(cudaMemcpyAsync(b_off.p, off.data(), nj * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-        k_walk<<<(nj + 63) / 64, 64, 0, st>>>(db->d_metas, sq->d_metas, b_jobs.as<TraceJob>(), nj,
-                                              b_cells.as<uint16_t>(), b_rows.as<uint32_t>(), 1, b_n.as<uint32_t>(),
-                                              b_off.as<uint64_t>(), b_steps.as<dcp_step>(), b_err.as<uint32_t>());
+        k_pack<<<nj, 128, 0, st>>>(b_jobs.as<TraceJob>(), nj, b_n.as<uint32_t>(), b_off.as<uint64_t>(),
+                                   b_raw.as<dcp_step>(), b_steps.as<dcp_step>());
         (*launches)++;
         std::vector<dcp_step> got(tot);
         CU_TRY(cudaMemcpyAsync(got.data(), b_steps.p, tot * sizeof(dcp_step), cudaMemcpyDeviceToHost, st));
-        CU_TRY(cudaMemcpyAsync(&nerr, b_err.p, sizeof nerr, cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaStreamSynchronize(st));
-        if (nerr) return dcp_error(RC_EFAIL, "traceback walked off the DP matrix");
+        CU_TRY(cudaGetLastError());
         /* append in hit order */
         std::vector<uint32_t> inv(nj);
         for (uint32_t i = 0; i < nj; ++i) inv[order[i]] = i;
@@ -948,6 +855,7 @@ enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const
             res->steps.insert(res->steps.end(), got.begin() + off[i], got.begin() + off[i] + ns[i]);
         }
         done = end;
+        cap_mul = 1;
     }
     return RC_OK;
 }
