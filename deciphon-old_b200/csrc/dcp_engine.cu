@@ -453,6 +453,13 @@ extern "C" enum rc dcpgpu_db_commit(struct dcpgpu_db *db)
             free(p->match_emission);
             p->match_emission = nullptr;
         }
+    {
+        /* what the device has left once the tables are resident: the budget of later passes is taken from this and
+         * the pool's own counters (cudaMemGetInfo on the scan path costs up to 20 ms with a multi-GB pool) */
+        size_t free_b = 0, total_b = 0;
+        CU_TRY(cudaMemGetInfo(&free_b, &total_b));
+        db->free_at_commit = free_b;
+    }
     db->committed = true;
     return RC_OK;
 }

@@ -97,6 +97,7 @@ struct dcpgpu_db
     ProfMeta *d_metas = nullptr;
     uint32_t *d_class[kMaxClasses] = {nullptr};
     uint64_t device_bytes = 0;
+    size_t free_at_commit = 0; /* free device memory right after commit (pool empty) */
     void *h_stage = nullptr; /* pinned staging for sequence uploads (grow-only) */
     size_t h_stage_cap = 0;
 };

@@ -63,12 +63,11 @@ enum rc scan_range(dcpgpu_db *db, const std::vector<uint32_t> *gprofs, uint32_t 
                    char const *const *seqs, unsigned const *lens, dcpgpu_params const *prm, std::vector<Part> &out)
 {
     CU_TRY(cudaSetDevice(db->device));
-    size_t free_b = 0, total_b = 0;
-    CU_TRY(cudaMemGetInfo(&free_b, &total_b));
-    uint64_t reserved = 0, used = 0;
-    cudaMemPoolGetAttribute(db->pool, cudaMemPoolAttrReservedMemCurrent, &reserved);
+    /* what was free after commit less what the pool has handed out (cudaMemGetInfo costs up to 20 ms per call with a
+     * multi-GB pool, dcp_trace.cu) */
+    uint64_t used = 0;
     cudaMemPoolGetAttribute(db->pool, cudaMemPoolAttrUsedMemCurrent, &used);
-    const size_t avail = free_b + (size_t)(reserved > used ? reserved - used : 0);
+    const size_t avail = db->free_at_commit > used ? db->free_at_commit - (size_t)used : 0;
     /* 40 % of what is free, less 64 MB for the small buffers of a scan; the traceback pass sizes itself later */
     size_t budget = std::max<size_t>((size_t)(0.4 * (double)avail), (size_t)320 << 20) - ((size_t)64 << 20);
     if (const char *e = getenv("DCPGPU_SCAN_BUDGET_KB")) budget = (size_t)std::max(1.0, atof(e)) << 10; /* test knob */

@@ -11,8 +11,13 @@
  *             state the recurrence carries -- is stored: 40 B per node and C rows instead of a backpointer per cell
  *   backward  segment by segment from the last: reload the ring, recompute the segment's rows, this time storing
  *             Tin_M, Tin_I and D of every cell and E, B, Tin_N/J/C of every row into a per-group scratch
- *             ((C + 5) rows, reused by every segment and every hit: it lives in L2), then walk the path through the
- *             segment.  No backpointer is ever computed for a cell the path does not visit.
+ *             ((C + 5) rows, reused by every segment and every hit), then walk the path through the segment.  No
+ *             backpointer is ever computed for a cell the path does not visit.  The cells are first stored for a band
+ *             of nodes only -- the lanes just below the node the walk enters the segment at: a path moves down one
+ *             node per match or delete step, about C / 3 nodes per segment -- so the scratch lines in use stay in L2
+ *             and the stores do not evict the emission tables; a walk that needs a cell outside the band (a long
+ *             run of deletions, or E, whose source can be any node) has the segment recomputed once more with
+ *             every cell stored.
  *   walk      one warp per hit, one lane per candidate: at state s and row r the lanes evaluate the incoming
  *             (transition, source length) candidates of Tin_s[r] from the stored values -- fl(fl(Tin_src[r-l] +
  *             e_src(seq[r-l:r])) + t), the sums a start-position interpreter forms -- and the first lane that
@@ -30,6 +35,9 @@
 #include "dcp_score_mw.cuh"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -144,7 +152,8 @@ __device__ __forceinline__ void one_row(float (&tm)[5][Q], float (&ti)[5][Q], fl
                                         const RowRec *__restrict__ recs, const uint16_t *__restrict__ wc, uint32_t L,
                                         uint32_t jj, uint32_t j0, const Specials &k, const Who &me,
                                         Group<Shape<TW, Q>::CL, MwShared> &grp, const CarryBound &cb, bool store,
-                                        float *__restrict__ cells, float *__restrict__ rowrec, float &E_L, float &vC_L)
+                                        bool cells_on, float *__restrict__ cells, float *__restrict__ rowrec,
+                                        float &E_L, float &vC_L)
 {
     using S = Shape<TW, Q>;
     const RowRec *rn = recs + min(jj + 1u, L);
@@ -166,10 +175,13 @@ __device__ __forceinline__ void one_row(float (&tm)[5][Q], float (&ti)[5][Q], fl
     if (store)
     {
         const uint32_t slot = jj - j0 + 4u;
-        float *c = cells + (size_t)slot * (3 * S::MP);
-        store_q<Q, S::NT>(c, tm[R]);
-        store_q<Q, S::NT>(c + S::MP, ti[R]);
-        store_q<Q, S::NT>(c + 2 * S::MP, tap.d);
+        if (cells_on)
+        {
+            float *c = cells + (size_t)slot * (3 * S::MP);
+            store_q<Q, S::NT>(c, tm[R]);
+            store_q<Q, S::NT>(c + S::MP, ti[R]);
+            store_q<Q, S::NT>(c + 2 * S::MP, tap.d);
+        }
         if (me.xs >= 0)
         {
             float *rr = rowrec + (size_t)slot * S::RR;
@@ -186,8 +198,8 @@ __device__ __forceinline__ void run_rows(float (&tm)[5][Q], float (&ti)[5][Q], f
                                          const float *__restrict__ emis_lane, const RowRec *__restrict__ recs,
                                          const uint16_t *__restrict__ wc, uint32_t L, uint32_t j0, uint32_t C,
                                          const Specials &k, const Who &me, Group<Shape<TW, Q>::CL, MwShared> &grp,
-                                         const CarryBound &cb, bool store, float *__restrict__ cells,
-                                         float *__restrict__ rowrec, float &E_L, float &vC_L)
+                                         const CarryBound &cb, bool store, bool cells_on,
+                                         float *__restrict__ cells, float *__restrict__ rowrec, float &E_L, float &vC_L)
 {
     using S = Shape<TW, Q>;
     /* pipeline prologue of the score kernels, at row j0 + 1 */
@@ -206,7 +218,7 @@ __device__ __forceinline__ void run_rows(float (&tm)[5][Q], float (&ti)[5][Q], f
     rs.w3 = 0;
     /* whole groups of five rows (static ring slots); rows past L recompute on clamped inputs and are ignored */
     const uint32_t j1 = min(L, j0 + C);
-#define ONE(RR, jj) one_row<TW, Q, RR>(tm, ti, tx, p, rs, emis_lane, recs, wc, L, (jj), j0, k, me, grp, cb, store, cells, rowrec, E_L, vC_L)
+#define ONE(RR, jj) one_row<TW, Q, RR>(tm, ti, tx, p, rs, emis_lane, recs, wc, L, (jj), j0, k, me, grp, cb, store, cells_on, cells, rowrec, E_L, vC_L)
 #pragma unroll 1
     for (uint32_t j = j0 + 1; j <= j1; j += 5)
     {
@@ -229,7 +241,29 @@ struct Walker
     int st;
     uint32_t k, r, len, n;
     bool bad, over, done;
+    bool need_full; /* the walk stopped at a state whose candidates lie outside the stored band */
 };
+
+/* threads whose cells the backward pass stores: lo..hi (none when hi < lo), or all of them */
+struct Band
+{
+    int lo, hi;
+    bool full;
+    __device__ __forceinline__ bool has(int t) const { return full || (t >= lo && t <= hi); }
+};
+/* band for a walk that enters a segment in state (st, k): the thread of node k and the `lanes` - 1 threads below it */
+template <int Q>
+__device__ __forceinline__ Band band_of(int st, uint32_t k, int lanes)
+{
+    Band b;
+    b.full = false, b.lo = 1, b.hi = 0;
+    if (st == W_M || st == W_I || st == W_D)
+    {
+        b.hi = (int)((k - 1u) / Q);
+        b.lo = max(0, b.hi - lanes + 1);
+    }
+    return b;
+}
 
 __device__ __forceinline__ uint16_t state_id_of(int st, uint32_t k)
 {
@@ -265,7 +299,7 @@ __device__ __forceinline__ void walk_segment(Walker &w, uint32_t j0, uint32_t M,
                                              const float *__restrict__ rowrec, const float *__restrict__ emis,
                                              const float *__restrict__ tr, const RowRec *__restrict__ recs,
                                              const uint16_t *__restrict__ wc, const Specials &sp,
-                                             dcp_step *__restrict__ out, uint32_t cap, int c)
+                                             dcp_step *__restrict__ out, uint32_t cap, int c, const Band &band)
 {
     using S = Shape<TW, Q>;
     auto cell = [&](int which, uint32_t n, uint32_t row) -> float {
@@ -278,8 +312,28 @@ __device__ __forceinline__ void walk_segment(Walker &w, uint32_t j0, uint32_t M,
     };
     auto par = [&](int which, uint32_t n) -> float { return __ldg(tr + which * S::NP + n); };
 
+    auto stored = [&](uint32_t n) -> bool { return band.has((int)(n / Q)); };
+    w.need_full = false;
+    /* window of the current row; the windows of the five rows below it are loaded while a step's candidates are
+     * evaluated, so that the next step's emission addresses do not wait for a load of their own */
+    uint32_t win = __ldg(wc + w.r);
     while (!w.done && !w.bad && !w.over && (w.r > j0 || j0 == 0))
     {
+        /* are the cells this state's candidates read stored?  (before the step is emitted: the walk resumes here) */
+        if (w.r != 0 && !band.full)
+        {
+            const uint32_t n = w.k - 1u;
+            const bool ok = w.st == W_E   ? false
+                            : w.st == W_M ? (n == 0 || stored(n - 1))
+                            : w.st == W_I ? stored(n)
+                            : w.st == W_D ? (n == 0 || stored(n - 1))
+                                          : true;
+            if (!ok)
+            {
+                w.need_full = true;
+                break;
+            }
+        }
         /* arrive: emit this state's step (the path is produced backwards: the buffer fills from its end) */
         if (w.n >= cap)
         {
@@ -299,6 +353,7 @@ __device__ __forceinline__ void walk_segment(Walker &w, uint32_t j0, uint32_t M,
             break;
         }
         const uint32_t r = w.r;
+        const uint32_t wnext = __ldg(wc + (r - min((uint32_t)c, min(r, 5u)))); /* lane c: row r - c */
         int nst = w.st;
         uint32_t nk = w.k, src_len = 0;
         if (r == 0)
@@ -312,7 +367,6 @@ __device__ __forceinline__ void walk_segment(Walker &w, uint32_t j0, uint32_t M,
         {
             /* first M_k in node order, then the first length, whose sum equals E[r] */
             const float E = rowv(0, r);
-            const uint32_t win = __ldg(wc + r);
             bool found = false;
             for (uint32_t nb = 0; nb < M && !found; nb += 32)
             {
@@ -341,86 +395,88 @@ __device__ __forceinline__ void walk_segment(Walker &w, uint32_t j0, uint32_t M,
         }
         else
         {
-            const uint32_t win = __ldg(wc + r);
+            /*
+             * Lane c describes candidate c -- where its source value, its emission and its transition score live --
+             * with selects, then every lane loads and adds at once: (a + e) + t, e = 0 for a mute source (B, E, D).
+             * Branches per candidate kind would serialise their loads: three L2 round trips per step instead of one.
+             */
             const RowRec *rec = recs + r;
-            float v = NEG_INF;
-            if (w.st == W_M)
+            const float *pa = rowrec; /* any readable address: lanes without a candidate are masked below */
+            const float *pe = nullptr, *pt = nullptr;
+            float tc = 0.0f;
+            bool valid = false;
+            auto cell_p = [&](int which, uint32_t n, uint32_t row) -> const float * {
+                return cells + ((size_t)(row - j0 + 4u) * 3 + which) * S::MP + cell_slot<Q, S::NT>(n);
+            };
+            auto rowv_p = [&](int idx, uint32_t row) -> const float * { return rowrec + (size_t)(row - j0 + 4u) * S::RR + idx; };
+            auto emis_p = [&](uint32_t n, uint32_t code) -> const float * {
+                const uint32_t t = n / Q, sub = n % Q, wp = t / S::LN, ln = t % S::LN;
+                return emis + (size_t)code * S::MP + wp * (S::LN * S::QP) + (sub >> 2) * (S::LN * 4) + ln * 4 + (sub & 3);
+            };
+            if (w.st == W_M || w.st == W_I || w.st == W_D)
             {
                 const uint32_t n = w.k - 1u;
-                if (c == 0)
-                    v = rowv(1, r) + par(7, n);
-                else if (c <= 10)
+                /* per state: which candidates read M / I / D of the source node, and the first of each kind */
+                int which, par_i;
+                uint32_t l = 0, src;
+                if (w.st == W_M)
                 {
-                    if (n >= 1)
-                    {
-                        const int which = c <= 5 ? 0 : 1;
-                        const uint32_t l = (uint32_t)(c - 1) % 5u + 1u;
-                        const float e = which == 0 ? emis_m(n - 1, code_of_len(win, l)) : __ldg(&rec->eI[l - 1]);
-                        v = (cell(which, n - 1, r - l) + e) + par(which, n);
-                    }
+                    const bool isB = c == 0, isM = c >= 1 && c <= 5, isI = c >= 6 && c <= 10, isD = c == 11;
+                    which = isM ? 0 : isI ? 1 : 2;
+                    l = isM ? (uint32_t)c : isI ? (uint32_t)c - 5u : 0u;
+                    src = n >= 1 ? n - 1 : 0;
+                    valid = isB || ((isM || isI || isD) && n >= 1);
+                    par_i = isB ? 7 : which;
+                    if (isB) which = -1;
                 }
-                else if (c == 11)
+                else if (w.st == W_I)
                 {
-                    if (n >= 1) v = cell(2, n - 1, r) + par(2, n);
+                    const bool isM = c < 5, isI = c >= 5 && c < 10;
+                    which = isM ? 0 : 1;
+                    l = (uint32_t)c % 5u + 1u;
+                    src = n;
+                    valid = isM || isI;
+                    par_i = 5 + which;
                 }
-            }
-            else if (w.st == W_I)
-            {
-                const uint32_t n = w.k - 1u;
-                if (c < 10)
+                else
                 {
-                    const int which = c < 5 ? 0 : 1;
-                    const uint32_t l = (uint32_t)c % 5u + 1u;
-                    const float e = which == 0 ? emis_m(n, code_of_len(win, l)) : __ldg(&rec->eI[l - 1]);
-                    v = (cell(which, n, r - l) + e) + par(5 + which, n);
+                    const bool isM = c < 5, isD = c == 5;
+                    which = isM ? 0 : 2;
+                    l = isM ? (uint32_t)c + 1u : 0u;
+                    src = n >= 1 ? n - 1 : 0;
+                    valid = (isM || isD) && n >= 1;
+                    par_i = isM ? 3 : 4;
                 }
-            }
-            else if (w.st == W_D)
-            {
-                const uint32_t n = w.k - 1u;
-                if (n >= 1)
+                if (valid)
                 {
-                    if (c < 5)
-                    {
-                        const uint32_t l = (uint32_t)c + 1u;
-                        v = (cell(0, n - 1, r - l) + emis_m(n - 1, code_of_len(win, l))) + par(3, n);
-                    }
-                    else if (c == 5)
-                        v = cell(2, n - 1, r) + par(4, n);
+                    pa = which < 0 ? rowv_p(1, r) : cell_p(which, src, r - l);
+                    pe = which == 0 ? emis_p(src, code_of_len(win, l)) : which == 1 ? &rec->eI[l - 1] : nullptr;
+                    pt = tr + par_i * S::NP + n;
                 }
             }
             else
             {
                 /* specials: candidate 0 = E (T, C, J) or S (N, B: row 0 only); 1..5 and 6..10 = an emitting source by
                  * length; 11 = E -> B */
-                const uint32_t l = (uint32_t)(c - 1) % 5u + 1u;
-                const float eN = (c >= 1 && c <= 10) ? __ldg(&rec->eN[l - 1]) : 0.0f;
-                if (w.st == W_T)
+                const uint32_t l = (uint32_t)(c + 4) % 5u + 1u; /* 1..5 for c = 1..5 and 6..10 */
+                const bool lo = c >= 1 && c <= 5, hi = c >= 6 && c <= 10;
+                int idx = 0; /* row-record field of the source: 0 E, 2 Tin_N, 3 Tin_J, 4 Tin_C */
+                if (w.st == W_T) valid = c <= 5, idx = lo ? 4 : 0, tc = lo ? sp.CT : sp.ET;
+                else if (w.st == W_C) valid = c <= 5, idx = lo ? 4 : 0, tc = lo ? sp.CC : sp.ECC;
+                else if (w.st == W_J) valid = c <= 5, idx = lo ? 3 : 0, tc = lo ? sp.JJ : sp.EJJ;
+                else if (w.st == W_N) valid = lo, idx = 2, tc = sp.NN;
+                else /* W_B */ valid = lo || hi || c == 11, idx = lo ? 2 : hi ? 3 : 0, tc = lo ? sp.NB : hi ? sp.JB : sp.EB;
+                if (valid)
                 {
-                    if (c == 0) v = rowv(0, r) + sp.ET;
-                    else if (c <= 5) v = (rowv(4, r - l) + eN) + sp.CT;
-                }
-                else if (w.st == W_C)
-                {
-                    if (c == 0) v = rowv(0, r) + sp.ECC;
-                    else if (c <= 5) v = (rowv(4, r - l) + eN) + sp.CC;
-                }
-                else if (w.st == W_J)
-                {
-                    if (c == 0) v = rowv(0, r) + sp.EJJ;
-                    else if (c <= 5) v = (rowv(3, r - l) + eN) + sp.JJ;
-                }
-                else if (w.st == W_N)
-                {
-                    if (c >= 1 && c <= 5) v = (rowv(2, r - l) + eN) + sp.NN;
-                }
-                else /* W_B */
-                {
-                    if (c >= 1 && c <= 5) v = (rowv(2, r - l) + eN) + sp.NB;
-                    else if (c >= 6 && c <= 10) v = (rowv(3, r - l) + eN) + sp.JB;
-                    else if (c == 11) v = rowv(0, r) + sp.EB;
+                    const bool emits = idx != 0;
+                    pa = rowv_p(idx, emits ? r - l : r);
+                    pe = emits ? &rec->eN[l - 1] : nullptr;
                 }
             }
+            const float va = __ldcg(pa);
+            const float ve = pe ? __ldg(pe) : 0.0f;
+            const float vt = pt ? __ldg(pt) : tc;
+            const float v = valid ? (va + ve) + vt : NEG_INF;
             const float best = warp_max(v);
             const unsigned who = __ballot_sync(FULL, v == best);
             const uint32_t code = who ? (uint32_t)(__ffs(who) - 1) : 0u;
@@ -463,6 +519,7 @@ __device__ __forceinline__ void walk_segment(Walker &w, uint32_t j0, uint32_t M,
         if (src_len > r) w.bad = true;
         if (nst == W_S && r != 0) w.bad = true;
         if (w.bad) break;
+        win = __shfl_sync(FULL, wnext, (int)src_len);
         w.r = r - src_len;
         w.st = nst, w.k = nk, w.len = src_len;
     }
@@ -477,8 +534,11 @@ __global__ void __launch_bounds__(Shape<TW, Q>::BLOCK, Shape<TW, Q>::MINB) k_tra
     using S = Shape<TW, Q>;
     constexpr int CL = S::CL;
     __shared__ MwShared sh;
+    __shared__ int sh_band[4]; /* warp groups: the walker's verdict {band lo, band hi, recompute with every cell} */
     Group<CL, MwShared> grp;
     grp.init(&sh);
+    int *peer_band = sh_band;
+    if constexpr (CL == 2) peer_band = cg::this_cluster().map_shared_rank(sh_band, grp.rank ^ 1);
     Who me;
     const int wlane = threadIdx.x & 31;
     uint32_t group; /* index of this hit-at-a-time unit on the device: owner of one scratch area */
@@ -561,70 +621,113 @@ __global__ void __launch_bounds__(Shape<TW, Q>::BLOCK, Shape<TW, Q>::MINB) k_tra
         for (int i = 0; i < Q; ++i) tm[4][i] = k.NB + p.ent[i];
         tx[4] = me.xs == 0 ? k.NN : NEG_INF;
 
-        /* ---- forward: checkpoint the ring before every segment ---- */
-        float E_L = NEG_INF, vC_L = NEG_INF;
-#pragma unroll 1
-        for (uint32_t s = 0; s < nseg; ++s)
-        {
-            float *c = ck + (size_t)s * S::CK;
-#pragma unroll
-            for (int q = 0; q < 5; ++q)
-            {
-                store_q<Q, S::NT>(c + (q * 2 + 0) * S::MP, tm[q]);
-                store_q<Q, S::NT>(c + (q * 2 + 1) * S::MP, ti[q]);
-            }
-            if (me.xs >= 0 && me.xs < 3)
-            {
-                float *cx = a.ckpt + tj.ck_off + (size_t)s * S::CK + 10 * S::MP;
-#pragma unroll
-                for (int q = 0; q < 5; ++q) cx[q * 4 + me.xs] = tx[q];
-            }
-            run_rows<TW, Q>(tm, ti, tx, p, emis_lane, recs, wc, L, s * C, C, k, me, grp, cb, false, cells, rowrec, E_L, vC_L);
-        }
-        if constexpr (TW == 0) vC_L = __shfl_sync(FULL, vC_L, 2, 16);
-        if constexpr (TW == 1) vC_L = __shfl_sync(FULL, vC_L, 2);
-        const float T = fmaxf(E_L + k.ET, vC_L + k.CT);
-        /* warp groups: the shared row buffers alternate by row parity, and the backward pass restarts at other rows */
-        if constexpr (TW > 1) grp.sync();
-
-        /* ---- backward: recompute a segment with its cells stored, walk through it ---- */
+        /*
+         * One loop, one copy of the row code (ten copies -- five ring rotations, twice -- thrashed the instruction
+         * cache: no_instruction was the top stall of the rows): forward over the segments, checkpointing the ring
+         * before each; then backward, reloading the ring, recomputing the segment with cells stored, and walking.
+         */
+        float E_L = NEG_INF, vC_L = NEG_INF, T = NEG_INF;
         Walker w;
         w.st = W_T, w.k = 0, w.r = L, w.len = 0, w.n = 0, w.bad = false, w.over = false, w.done = false;
+        w.need_full = false;
         dcp_step *out = a.steps_raw + tj.step_off;
+        const int band_lanes = (int)((C / 3u + 8u) / Q + 2u);
+        Band band = band_of<Q>(W_T, 0, band_lanes); /* the walk starts at T: no cells */
+        bool back = false;
+        uint32_t s = 0;
 #pragma unroll 1
-        for (uint32_t s = nseg; s-- > 0;)
+        for (;;)
         {
             const uint32_t j0 = s * C;
-            const float *c = ck + (size_t)s * S::CK;
-#pragma unroll
-            for (int q = 0; q < 5; ++q)
+            float *c = ck + (size_t)s * S::CK;
+            float *cx = a.ckpt + tj.ck_off + (size_t)s * S::CK + 10 * S::MP;
+            const bool cells_on = back && band.has(me.t);
+            if (!back)
             {
-                load_q<Q, S::NT>(c + (q * 2 + 0) * S::MP, tm[q]);
-                load_q<Q, S::NT>(c + (q * 2 + 1) * S::MP, ti[q]);
-                tx[q] = NEG_INF;
-            }
-            if (me.xs >= 0 && me.xs < 3)
-            {
-                const float *cx = a.ckpt + tj.ck_off + (size_t)s * S::CK + 10 * S::MP;
 #pragma unroll
-                for (int q = 0; q < 5; ++q) tx[q] = __ldcg(cx + q * 4 + me.xs);
-            }
-            /* the ring rows j0 - 4 .. j0 are slots 0 .. 4 of the scratch: the walk reads up to five rows back */
+                for (int q = 0; q < 5; ++q)
+                {
+                    store_q<Q, S::NT>(c + (q * 2 + 0) * S::MP, tm[q]);
+                    store_q<Q, S::NT>(c + (q * 2 + 1) * S::MP, ti[q]);
+                }
+                if (me.xs >= 0 && me.xs < 3)
+                {
 #pragma unroll
-            for (int q = 0; q < 5; ++q)
-            {
-                float *d = cells + (size_t)q * (3 * S::MP);
-                store_q<Q, S::NT>(d, tm[q]);
-                store_q<Q, S::NT>(d + S::MP, ti[q]);
-                if (me.xs >= 0 && me.xs < 3) rowrec[q * S::RR + 2 + me.xs] = tx[q];
+                    for (int q = 0; q < 5; ++q) cx[q * 4 + me.xs] = tx[q];
+                }
             }
-            float e_dummy = NEG_INF, v_dummy = NEG_INF;
-            run_rows<TW, Q>(tm, ti, tx, p, emis_lane, recs, wc, L, j0, C, k, me, grp, cb, true, cells, rowrec, e_dummy, v_dummy);
+            else
+            {
+#pragma unroll
+                for (int q = 0; q < 5; ++q)
+                {
+                    load_q<Q, S::NT>(c + (q * 2 + 0) * S::MP, tm[q]);
+                    load_q<Q, S::NT>(c + (q * 2 + 1) * S::MP, ti[q]);
+                    tx[q] = NEG_INF;
+                }
+                if (me.xs >= 0 && me.xs < 3)
+                {
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) tx[q] = __ldcg(cx + q * 4 + me.xs);
+                }
+                /* the ring rows j0 - 4 .. j0 are slots 0 .. 4 of the scratch: the walk reads up to five rows back */
+#pragma unroll
+                for (int q = 0; q < 5; ++q)
+                {
+                    float *d = cells + (size_t)q * (3 * S::MP);
+                    if (cells_on)
+                    {
+                        store_q<Q, S::NT>(d, tm[q]);
+                        store_q<Q, S::NT>(d + S::MP, ti[q]);
+                    }
+                    if (me.xs >= 0 && me.xs < 3) rowrec[q * S::RR + 2 + me.xs] = tx[q];
+                }
+            }
+            run_rows<TW, Q>(tm, ti, tx, p, emis_lane, recs, wc, L, j0, C, k, me, grp, cb, back, cells_on, cells, rowrec, E_L,
+                            vC_L);
+            if (!back)
+            {
+                if (s + 1 < nseg)
+                {
+                    ++s;
+                    continue;
+                }
+                /* row L has passed: T[L] = max(E[L] + (EC+CT), V_C[L] + CT) */
+                float vC = vC_L;
+                if constexpr (TW == 0) vC = __shfl_sync(FULL, vC, 2, 16);
+                if constexpr (TW == 1) vC = __shfl_sync(FULL, vC, 2);
+                T = fmaxf(E_L + k.ET, vC + k.CT);
+                back = true; /* the last segment again, this time for the walk */
+                /* warp groups: the shared row buffers alternate by row parity, and the backward pass restarts at other rows */
+                if constexpr (TW > 1) grp.sync();
+                continue;
+            }
             if constexpr (TW <= 1) __syncwarp();
             else grp.sync();
-            if (walker) walk_segment<TW, Q>(w, j0, pm.M, scr, rowrec, emis_prof, a.trans + pm.trans_off, recs, wc, k, out, tj.cap, wlane);
+            bool again;
+            if (walker)
+            {
+                walk_segment<TW, Q>(w, j0, pm.M, scr, rowrec, emis_prof, a.trans + pm.trans_off, recs, wc, k, out, tj.cap,
+                                    wlane, band);
+                again = w.need_full;
+                band = band_of<Q>(w.st, w.k, band_lanes);
+                band.full = again;
+                if (TW > 1 && wlane == 0)
+                {
+                    sh_band[0] = band.lo, sh_band[1] = band.hi, sh_band[2] = again;
+                    if (CL == 2) peer_band[0] = band.lo, peer_band[1] = band.hi, peer_band[2] = again;
+                }
+            }
             if constexpr (TW <= 1) __syncwarp();
-            else grp.sync();
+            else
+            {
+                grp.sync();
+                band.lo = sh_band[0], band.hi = sh_band[1], band.full = sh_band[2] != 0;
+                again = band.full;
+            }
+            if (again) continue; /* once more with every cell: the walk left the band */
+            if (s == 0) break;
+            --s;
         }
         if (walker && wlane == 0)
         {
@@ -667,6 +770,8 @@ cudaError_t launch_trace(cudaStream_t st, int sm_count, TraceArgs a, float *scra
     }
     a.scratch = scratch_pool + *scratch_used;
     *scratch_used += need;
+    /* little or no shared memory: give the unified array to L1 (emission lines, row records), as the score kernels do */
+    cudaFuncSetAttribute(k_trace<TW, Q>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     unsigned blocks;
     if (TW <= 1) blocks = groups / (S::BLOCK / 32);
     else blocks = groups * S::CL;
@@ -675,7 +780,13 @@ cudaError_t launch_trace(cudaStream_t st, int sm_count, TraceArgs a, float *scra
 
 uint32_t segment_rows(uint32_t Lmax)
 {
-    /* about sqrt(L) rows, a multiple of five: checkpoints and scratch both shrink with it */
+    /* about sqrt(L) rows, a multiple of five: the checkpoints (40 B per node and segment) and the scratch ((C + 5)
+     * rows) both stay small, and a segment is long enough to amortise its fixed cost (ring reload, pipeline prologue,
+     * two group barriers; 2 sqrt(L) measured the same on 1 kbp reads -- 27 vs 29 ms for 10 000 hits -- and
+     * worse on 10 kbp contigs, 103 vs 96 ms for 200 hits: the band widens with C).  DCPGPU_TRACE_SEG overrides (tests,
+     * experiments). */
+    static const int forced = getenv("DCPGPU_TRACE_SEG") ? atoi(getenv("DCPGPU_TRACE_SEG")) : 0;
+    if (forced > 0) return (uint32_t)std::min(1000, (forced + 4) / 5 * 5);
     uint32_t c = (uint32_t)std::ceil(std::sqrt((double)Lmax) / 5.0) * 5u;
     return std::min(250u, std::max(20u, c));
 }
@@ -687,8 +798,19 @@ enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const
 {
     cudaStream_t st = db->stream;
     const size_t nhits = res->hits.size();
-    size_t free_b = 0, total_b = 0;
-    CU_TRY(cudaMemGetInfo(&free_b, &total_b));
+    /* DCPGPU_TRACE_TIMES=1: host-side timeline of the pass on stderr (where the time between the kernels goes) */
+    static const bool times = getenv("DCPGPU_TRACE_TIMES") && atoi(getenv("DCPGPU_TRACE_TIMES")) != 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto stamp = [&](const char *what) {
+        if (times)
+            fprintf(stderr, "[dcp_trace] %8.3f ms  %s\n",
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), what);
+    };
+    /* free memory = what was free after commit less what the pool has handed out (no cudaMemGetInfo here: it
+     * took 20 ms of a 50 ms pass) */
+    uint64_t pool_used = 0;
+    cudaMemPoolGetAttribute(db->pool, cudaMemPoolAttrUsedMemCurrent, &pool_used);
+    const size_t free_b = db->free_at_commit > pool_used ? db->free_at_commit - (size_t)pool_used : 0;
     const size_t budget = std::min<size_t>(std::max<size_t>(free_b / 2, (size_t)64 << 20), (size_t)16 << 30);
     const std::vector<float> &score_alt = res->hit_alt; /* score pass result of each hit */
 
@@ -698,9 +820,14 @@ enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const
         const size_t MP = (size_t)m.LN * m.W * m.QP, L = sq->metas[h.seq].len;
         return ((L + C - 1) / C) * (10 * MP + 32);
     };
+    /* steps a hit's buffer holds: generous for ordinary paths; a path that does not fit (many passes through the
+     * core) has its batch retried with eight times the room, up to the most a path can have.
+     * DCPGPU_TRACE_CAP overrides the first guess (tests). */
+    static const int cap0 = getenv("DCPGPU_TRACE_CAP") ? atoi(getenv("DCPGPU_TRACE_CAP")) : 0;
     auto step_cap = [&](const HitRec &h, uint32_t mul) -> uint64_t {
         const uint64_t L = sq->metas[h.seq].len, M = db->metas[h.prof].M;
-        return std::min<uint64_t>((2 * (L + M) + 64) * mul, (L + 2) * (M + 3) + 8);
+        const uint64_t first = cap0 > 0 ? (uint64_t)cap0 : 2 * (L + M) + 64;
+        return std::min<uint64_t>(first * mul, (L + 2) * (M + 3) + 8);
     };
 
     size_t done = 0;
@@ -728,6 +855,7 @@ enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const
             ++end;
         }
         const uint32_t nj = (uint32_t)jobs.size();
+        stamp("batch chosen");
         /* order jobs by class so each launch sees a contiguous range; inside a class the longest sequences first */
         std::vector<uint32_t> order(nj);
         for (uint32_t i = 0; i < nj; ++i) order[i] = i;
@@ -776,6 +904,7 @@ enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const
             if (launch_range(r, nullptr, base, nullptr, &scratch_floats, true) < 0)
                 return dcp_error(RC_EFAIL, "no trace kernel for this kernel class");
 
+        stamp("jobs sorted");
         DevBuf b_jobs, b_ck, b_scr, b_raw, b_alt, b_n, b_off, b_err, b_cnt, b_steps;
         CU_TRY(b_jobs.alloc(nj * sizeof(TraceJob), db));
         CU_TRY(b_ck.alloc(ckf * sizeof(float), db));
@@ -786,6 +915,7 @@ enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const
         CU_TRY(b_off.alloc(nj * sizeof(uint64_t), db));
         CU_TRY(b_err.alloc(2 * sizeof(uint32_t), db));
         CU_TRY(b_cnt.alloc(ranges.size() * sizeof(unsigned long long), db));
+        stamp("buffers allocated");
         CU_TRY(cudaMemcpyAsync(b_jobs.p, sorted.data(), nj * sizeof(TraceJob), cudaMemcpyHostToDevice, st));
         CU_TRY(cudaMemsetAsync(b_err.p, 0, 2 * sizeof(uint32_t), st));
         CU_TRY(cudaMemsetAsync(b_cnt.p, 0, ranges.size() * sizeof(unsigned long long), st));
@@ -810,6 +940,7 @@ enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const
         }
         CU_TRY(fan.join());
         CU_TRY(cudaGetLastError());
+        stamp("kernels queued");
         std::vector<uint32_t> ns(nj);
         std::vector<float> talt(nj);
         uint32_t nerr[2] = {0, 0};
@@ -817,6 +948,7 @@ enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const
         CU_TRY(cudaMemcpyAsync(talt.data(), b_alt.p, nj * sizeof(float), cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaMemcpyAsync(nerr, b_err.p, sizeof nerr, cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaStreamSynchronize(st));
+        stamp("kernels done, counts on the host");
         if (nerr[0]) return dcp_error(RC_EFAIL, "traceback walked off the DP matrix");
         if (nerr[1])
         {
@@ -825,37 +957,38 @@ enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const
             cap_mul *= 8;
             continue;
         }
-        std::vector<uint64_t> off(nj);
-        uint64_t tot = 0;
-        for (uint32_t i = 0; i < nj; ++i) off[i] = tot, tot += ns[i];
         for (uint32_t i = 0; i < nj; ++i)
         {
             size_t hit = done + order[i];
             if (memcmp(&talt[i], &score_alt[hit], sizeof(float)) != 0)
                 return dcp_error(RC_EFAIL, "trace pass and score pass disagree on the alt log-likelihood");
         }
+        /* the paths are packed on the device in hit order and land in the result's step array in one copy */
+        std::vector<uint32_t> inv(nj);
+        for (uint32_t i = 0; i < nj; ++i) inv[order[i]] = i;
+        std::vector<uint64_t> off(nj);
+        uint64_t tot = 0;
+        const size_t steps0 = res->steps.size();
+        for (uint32_t h = 0; h < nj; ++h)
+        {
+            const uint32_t i = inv[h];
+            HitRec &hr = res->hits[done + h];
+            hr.step_off = steps0 + tot, hr.nsteps = ns[i];
+            off[i] = tot, tot += ns[i];
+        }
+        res->steps.resize(steps0 + tot);
         CU_TRY(b_steps.alloc(std::max<uint64_t>(tot, 1) * sizeof(dcp_step), db));
         CU_TRY(cudaMemcpyAsync(b_off.p, off.data(), nj * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
         k_pack<<<nj, 128, 0, st>>>(b_jobs.as<TraceJob>(), nj, b_n.as<uint32_t>(), b_off.as<uint64_t>(),
                                    b_raw.as<dcp_step>(), b_steps.as<dcp_step>());
         (*launches)++;
-        std::vector<dcp_step> got(tot);
-        CU_TRY(cudaMemcpyAsync(got.data(), b_steps.p, tot * sizeof(dcp_step), cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(res->steps.data() + steps0, b_steps.p, tot * sizeof(dcp_step), cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaStreamSynchronize(st));
         CU_TRY(cudaGetLastError());
-        /* append in hit order */
-        std::vector<uint32_t> inv(nj);
-        for (uint32_t i = 0; i < nj; ++i) inv[order[i]] = i;
-        for (uint32_t h = 0; h < nj; ++h)
-        {
-            uint32_t i = inv[h];
-            HitRec &hr = res->hits[done + h];
-            hr.step_off = res->steps.size();
-            hr.nsteps = ns[i];
-            res->steps.insert(res->steps.end(), got.begin() + off[i], got.begin() + off[i] + ns[i]);
-        }
+        stamp("paths on the host");
         done = end;
         cap_mul = 1;
+        stamp("paths appended");
     }
     return RC_OK;
 }

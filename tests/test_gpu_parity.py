@@ -337,6 +337,61 @@ def test_scan_from_a_pressed_dcp_database(pkg, o32, tmp_path):
     assert out.returncode == 1 and "imm" in out.stderr
 
 
+def test_traceback_checkpointing_is_independent_of_its_knobs(pkg, o32, tmp_path):
+    """The traceback stores a ring checkpoint every C rows, recomputes segments backwards with a band of cells and
+    walks them (dcp_trace.cu).  Rows must not depend on C, on the step buffer's first size (a path that does not fit
+    is retried with a larger buffer), nor on whether a segment had to be recomputed with every cell: five-row
+    segments (a checkpoint before every group of rows, the walk crosses a segment boundary at almost every step), a
+    segment longer than the reads, and eight-step buffers, on profiles of one half-warp, one warp and two warps, with
+    a read that deletes 60 nodes (the walk leaves its band) and one with two domains (E and J)."""
+    import os
+    import subprocess
+    from common import write_hmm
+    rng = np.random.default_rng(2024)
+    models = []
+    for i, M in enumerate((70, 210, 400)):
+        _, ma, tr = plan7_profile_inputs(rng, M)
+        models.append(("tb%d" % i, "PF6%04d.1" % i, ma, tr))
+    hmm = str(tmp_path / "tb.hmm")
+    seen = write_hmm(hmm, models)
+    seqs = [sample_read(rng, seen[i % 3][0], int(rng.integers(150, 1100)), 0.02, 0.01) for i in range(9)]
+    full = sample_read(rng, seen[2][0], 1200, 0.0, 0.0)
+    seqs.append(full[:450] + full[630:1100])                                   # 60 deleted nodes
+    seqs.append(sample_read(rng, seen[0][0], 200, 0.0, 0.0) + random_seq(rng, 60) + sample_read(rng, seen[0][0], 200, 0.0, 0.0))
+    fasta = tmp_path / "reads.fasta"
+    fasta.write_text("".join(">s%d\n%s\n" % (i, s) for i, s in enumerate(seqs)))
+    exe = os.path.join(os.path.dirname(pkg.__file__), "dcp-scan")
+
+    def run(*flags, **env):
+        e = dict(os.environ)
+        e.update({k: str(v) for k, v in env.items()})
+        out = subprocess.run([exe, "--scan-id", "5", *flags, hmm, str(fasta)], capture_output=True, text=True, env=e)
+        assert out.returncode == 0, out.stderr
+        return out.stdout
+
+    import re
+    cfg = pkg.protein_cfg(pkg.ENTRY_DIST_OCCUPANCY, 0.01)
+    profs = pkg.read_hmm(hmm, cfg)
+    twins = [oracle_twin(o32, p, 0.01) for p in profs]
+    for flags, multi in (((), True), (("--single-hit",), False)):
+        base = run(*flags)
+        ref = o32.scan(twins, seqs, multi, False, 10.0, 1, True)
+        paths = ref_paths(ref, 3)
+        want = [twins[p].product_row(5, s + 1, profs[p].accession, float(ref["alt"][s, p]), float(ref["null"][s, p]),
+                                     seqs[s], paths[(s, p)])
+                for s in range(len(seqs)) for p in range(3) if ref["hit"][s, p]]
+        assert len(want) >= 10
+        assert base.splitlines(keepends=True)[1:] == want
+        if multi:
+            assert any(",J," in r for r in want)
+        else:
+            assert max(len(re.findall(r",D\d+,", r)) for r in want) >= 50
+        assert run(*flags, DCPGPU_TRACE_SEG=5) == base
+        assert run(*flags, DCPGPU_TRACE_SEG=1000) == base
+        assert run(*flags, DCPGPU_TRACE_CAP=8) == base
+        assert run(*flags, DCPGPU_TRACE_SEG=10, DCPGPU_TRACE_CAP=8) == base
+
+
 def test_every_kernel_class_on_short_ragged_sequences(pkg, o32):
     """One profile per row of the kernel class table (two pairs per warp, one warp, groups of 2 / 3 / 4 / 6 / 8 warps,
     two-block groups) against sequences of 1..97 nt, every pair traced: scores, paths and the (sequence, profile)
