@@ -70,7 +70,14 @@ struct TraceArgs
     uint32_t *nsteps;              /* per job; 0 on failure */
     float *alt_out;                /* per job: T[L] of the forward pass */
     uint32_t *errors;              /* [0] walks that left the DP matrix, [1] step buffers that were too small */
+    unsigned long long *prof;      /* DCP_TRACE_PROF builds: cycles in forward rows, backward rows, walks, the rest of
+                                    * a hit; walk steps; segments recomputed with every cell; segment passes */
 };
+
+#ifndef DCP_TRACE_PROF
+#define DCP_TRACE_PROF 0
+#endif
+#define PROF_CLK() (DCP_TRACE_PROF ? clock64() : 0ll)
 
 /* shape of a kernel class as the trace kernels see it: TW = 0 two hits^W halves per warp (16 lanes per hit; the trace
  * kernel runs the same hit on both halves: identical values, identical stores), 1 one warp, >= 2 a group of warps */
@@ -138,10 +145,23 @@ struct Who
     int xs;    /* 0..2: this thread carries N / J / C; 3: it writes E and B of the row; else -1 */
 };
 
+/* length-dependent special scores: what a row needs (the rest is read by the walk when it needs it, so that it does
+ * not occupy registers across the rows) */
+struct RowSpecials
+{
+    float NB, JB, EB, cE, cX;
+};
 struct Specials
 {
-    float NN, CC, JJ, NB, CT, JB, ET, ECC, EB, EJJ, cE, cX;
+    float NN, CC, JJ, NB, CT, JB, ET, ECC, EB, EJJ;
 };
+__device__ __forceinline__ Specials load_specials(const float *__restrict__ spv)
+{
+    Specials k;
+    k.NN = __ldg(spv + 0), k.CC = __ldg(spv + 1), k.JJ = __ldg(spv + 2), k.NB = __ldg(spv + 3), k.CT = __ldg(spv + 4);
+    k.JB = __ldg(spv + 5), k.ET = __ldg(spv + 9), k.ECC = __ldg(spv + 10), k.EB = __ldg(spv + 11), k.EJJ = __ldg(spv + 12);
+    return k;
+}
 
 /* ----------------------------------------------------------------------------------------- */
 /* rows j0 + 1 .. min(L, j0 + C) from the ring as it stands after row j0                       */
@@ -150,10 +170,9 @@ template <int TW, int Q, int R>
 __device__ __forceinline__ void one_row(float (&tm)[5][Q], float (&ti)[5][Q], float (&tx)[5], const NodeParams<Q> &p,
                                         RowState<Q> &rs, const float *__restrict__ emis_lane,
                                         const RowRec *__restrict__ recs, const uint16_t *__restrict__ wc, uint32_t L,
-                                        uint32_t jj, uint32_t j0, const Specials &k, const Who &me,
+                                        uint32_t jj, uint32_t j0, const RowSpecials &k, const Who &me,
                                         Group<Shape<TW, Q>::CL, MwShared> &grp, const CarryBound &cb, bool store,
-                                        bool cells_on, float *__restrict__ cells, float *__restrict__ rowrec,
-                                        float &E_L, float &vC_L)
+                                        bool cells_on, float *__restrict__ cells, float *__restrict__ rowrec)
 {
     using S = Shape<TW, Q>;
     const RowRec *rn = recs + min(jj + 1u, L);
@@ -170,8 +189,7 @@ __device__ __forceinline__ void one_row(float (&tm)[5][Q], float (&ti)[5][Q], fl
     else
         mw_row<S::W, S::CL, R, Q, 1>(tm, ti, tx, p, rs, emis_lane, rn, wn, me.gw, me.lane, (int)(jj & 1u), grp, k.NB, k.JB,
                                      k.EB, k.cE, k.cX, cb, E, vC, &tap);
-    /* TW <= 1: vC is this lane's special state (V_C in lane 2); warp groups: V_C itself */
-    if (jj == L) E_L = E, vC_L = vC;
+    (void)vC; /* T[L] comes out of the walk's first step, whose candidates are exactly T's */
     if (store)
     {
         const uint32_t slot = jj - j0 + 4u;
@@ -197,9 +215,9 @@ template <int TW, int Q>
 __device__ __forceinline__ void run_rows(float (&tm)[5][Q], float (&ti)[5][Q], float (&tx)[5], const NodeParams<Q> &p,
                                          const float *__restrict__ emis_lane, const RowRec *__restrict__ recs,
                                          const uint16_t *__restrict__ wc, uint32_t L, uint32_t j0, uint32_t C,
-                                         const Specials &k, const Who &me, Group<Shape<TW, Q>::CL, MwShared> &grp,
+                                         const RowSpecials &k, const Who &me, Group<Shape<TW, Q>::CL, MwShared> &grp,
                                          const CarryBound &cb, bool store, bool cells_on,
-                                         float *__restrict__ cells, float *__restrict__ rowrec, float &E_L, float &vC_L)
+                                         float *__restrict__ cells, float *__restrict__ rowrec)
 {
     using S = Shape<TW, Q>;
     /* pipeline prologue of the score kernels, at row j0 + 1 */
@@ -218,7 +236,7 @@ __device__ __forceinline__ void run_rows(float (&tm)[5][Q], float (&ti)[5][Q], f
     rs.w3 = 0;
     /* whole groups of five rows (static ring slots); rows past L recompute on clamped inputs and are ignored */
     const uint32_t j1 = min(L, j0 + C);
-#define ONE(RR, jj) one_row<TW, Q, RR>(tm, ti, tx, p, rs, emis_lane, recs, wc, L, (jj), j0, k, me, grp, cb, store, cells_on, cells, rowrec, E_L, vC_L)
+#define ONE(RR, jj) one_row<TW, Q, RR>(tm, ti, tx, p, rs, emis_lane, recs, wc, L, (jj), j0, k, me, grp, cb, store, cells_on, cells, rowrec)
 #pragma unroll 1
     for (uint32_t j = j0 + 1; j <= j1; j += 5)
     {
@@ -298,10 +316,12 @@ template <int TW, int Q>
 __device__ __forceinline__ void walk_segment(Walker &w, uint32_t j0, uint32_t M, const float *__restrict__ cells,
                                              const float *__restrict__ rowrec, const float *__restrict__ emis,
                                              const float *__restrict__ tr, const RowRec *__restrict__ recs,
-                                             const uint16_t *__restrict__ wc, const Specials &sp,
-                                             dcp_step *__restrict__ out, uint32_t cap, int c, const Band &band)
+                                             const uint16_t *__restrict__ wc, const float *__restrict__ spv,
+                                             dcp_step *__restrict__ out, uint32_t cap, int c, const Band &band,
+                                             float *__restrict__ alt_out)
 {
     using S = Shape<TW, Q>;
+    const Specials sp = load_specials(spv);
     auto cell = [&](int which, uint32_t n, uint32_t row) -> float {
         return __ldcg(cells + ((size_t)(row - j0 + 4u) * 3 + which) * S::MP + cell_slot<Q, S::NT>(n));
     };
@@ -478,6 +498,9 @@ __device__ __forceinline__ void walk_segment(Walker &w, uint32_t j0, uint32_t M,
             const float vt = pt ? __ldg(pt) : tc;
             const float v = valid ? (va + ve) + vt : NEG_INF;
             const float best = warp_max(v);
+            /* the candidates of T at row L are T[L] = max(E[L] + (EC+CT), V_C[L] + CT) itself: the alt log-likelihood
+             * of this pass, compared with the score pass's on the host */
+            if (w.st == W_T && c == 0) *alt_out = best;
             const unsigned who = __ballot_sync(FULL, v == best);
             const uint32_t code = who ? (uint32_t)(__ffs(who) - 1) : 0u;
             switch (w.st)
@@ -600,11 +623,10 @@ __global__ void __launch_bounds__(Shape<TW, Q>::BLOCK, Shape<TW, Q>::MINB) k_tra
         const RowRec *recs = a.rows + (size_t)pm.null_id * a.total_recs + sm.rec_off;
         const uint16_t *wc = a.wcodes + sm.rec_off;
         const float *spv = a.spec + (size_t)tj.seq * 16;
-        Specials k;
-        k.NN = spv[0], k.CC = spv[1], k.JJ = spv[2], k.NB = spv[3], k.CT = spv[4], k.JB = spv[5];
-        k.ET = spv[9], k.ECC = spv[10], k.EB = spv[11], k.EJJ = spv[12];
-        k.cE = me.xs == 0 ? NEG_INF : (me.xs == 1 ? k.EJJ : k.ECC);
-        k.cX = me.xs == 0 ? k.NN : (me.xs == 1 ? k.JJ : k.CC);
+        RowSpecials k;
+        k.NB = spv[3], k.JB = spv[5], k.EB = spv[11];
+        k.cE = me.xs == 0 ? NEG_INF : (me.xs == 1 ? spv[12] : spv[10]); /* E->J + J->J, E->C + C->C */
+        k.cX = me.xs == 0 ? spv[0] : (me.xs == 1 ? spv[2] : spv[1]);    /* N->N, J->J, C->C */
         const uint32_t nseg = (L + C - 1) / C;
         float *const ck = a.ckpt + tj.ck_off + (size_t)me.t * 4;
 
@@ -619,14 +641,14 @@ __global__ void __launch_bounds__(Shape<TW, Q>::BLOCK, Shape<TW, Q>::MINB) k_tra
         /* row 0: S = 0, B[0] = NB, Tin_N[0] = NN, Tin_Mk[0] = B[0] + entry_k */
 #pragma unroll
         for (int i = 0; i < Q; ++i) tm[4][i] = k.NB + p.ent[i];
-        tx[4] = me.xs == 0 ? k.NN : NEG_INF;
+        tx[4] = me.xs == 0 ? spv[0] : NEG_INF;
 
         /*
          * One loop, one copy of the row code (ten copies -- five ring rotations, twice -- thrashed the instruction
          * cache: no_instruction was the top stall of the rows): forward over the segments, checkpointing the ring
          * before each; then backward, reloading the ring, recomputing the segment with cells stored, and walking.
          */
-        float E_L = NEG_INF, vC_L = NEG_INF, T = NEG_INF;
+        long long pc_job = PROF_CLK(), pc_fwd = 0, pc_bwd = 0, pc_walk = 0, pc_full = 0, pc_pass = 0;
         Walker w;
         w.st = W_T, w.k = 0, w.r = L, w.len = 0, w.n = 0, w.bad = false, w.over = false, w.done = false;
         w.need_full = false;
@@ -683,8 +705,10 @@ __global__ void __launch_bounds__(Shape<TW, Q>::BLOCK, Shape<TW, Q>::MINB) k_tra
                     if (me.xs >= 0 && me.xs < 3) rowrec[q * S::RR + 2 + me.xs] = tx[q];
                 }
             }
-            run_rows<TW, Q>(tm, ti, tx, p, emis_lane, recs, wc, L, j0, C, k, me, grp, cb, back, cells_on, cells, rowrec, E_L,
-                            vC_L);
+            const long long pc0 = PROF_CLK();
+            run_rows<TW, Q>(tm, ti, tx, p, emis_lane, recs, wc, L, j0, C, k, me, grp, cb, back, cells_on, cells, rowrec);
+            if (back) pc_bwd += PROF_CLK() - pc0, pc_pass++, pc_full += band.full;
+            else pc_fwd += PROF_CLK() - pc0;
             if (!back)
             {
                 if (s + 1 < nseg)
@@ -692,12 +716,7 @@ __global__ void __launch_bounds__(Shape<TW, Q>::BLOCK, Shape<TW, Q>::MINB) k_tra
                     ++s;
                     continue;
                 }
-                /* row L has passed: T[L] = max(E[L] + (EC+CT), V_C[L] + CT) */
-                float vC = vC_L;
-                if constexpr (TW == 0) vC = __shfl_sync(FULL, vC, 2, 16);
-                if constexpr (TW == 1) vC = __shfl_sync(FULL, vC, 2);
-                T = fmaxf(E_L + k.ET, vC + k.CT);
-                back = true; /* the last segment again, this time for the walk */
+                back = true; /* row L has passed: the last segment again, this time for the walk */
                 /* warp groups: the shared row buffers alternate by row parity, and the backward pass restarts at other rows */
                 if constexpr (TW > 1) grp.sync();
                 continue;
@@ -707,8 +726,10 @@ __global__ void __launch_bounds__(Shape<TW, Q>::BLOCK, Shape<TW, Q>::MINB) k_tra
             bool again;
             if (walker)
             {
-                walk_segment<TW, Q>(w, j0, pm.M, scr, rowrec, emis_prof, a.trans + pm.trans_off, recs, wc, k, out, tj.cap,
-                                    wlane, band);
+                const long long pc1 = PROF_CLK();
+                walk_segment<TW, Q>(w, j0, pm.M, scr, rowrec, emis_prof, a.trans + pm.trans_off, recs, wc, spv, out, tj.cap,
+                                    wlane, band, a.alt_out + job);
+                pc_walk += PROF_CLK() - pc1;
                 again = w.need_full;
                 band = band_of<Q>(w.st, w.k, band_lanes);
                 band.full = again;
@@ -733,8 +754,15 @@ __global__ void __launch_bounds__(Shape<TW, Q>::BLOCK, Shape<TW, Q>::MINB) k_tra
         {
             const bool ok = w.done && !w.bad && !w.over;
             a.nsteps[job] = ok ? w.n : 0u;
-            a.alt_out[job] = T;
             if (!ok) atomicAdd(a.errors + (w.over ? 1 : 0), 1u);
+            if (DCP_TRACE_PROF)
+            {
+                atomicAdd(a.prof + 0, (unsigned long long)pc_fwd), atomicAdd(a.prof + 1, (unsigned long long)pc_bwd);
+                atomicAdd(a.prof + 2, (unsigned long long)pc_walk);
+                atomicAdd(a.prof + 3, (unsigned long long)(PROF_CLK() - pc_job));
+                atomicAdd(a.prof + 4, (unsigned long long)w.n), atomicAdd(a.prof + 5, (unsigned long long)pc_full);
+                atomicAdd(a.prof + 6, (unsigned long long)pc_pass), atomicAdd(a.prof + 7, 1ull);
+            }
         }
     }
     if constexpr (CL == 2) grp.sync(); /* no block may exit while its peer can still store into its shared memory */
@@ -913,13 +941,14 @@ enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const
         CU_TRY(b_alt.alloc(nj * sizeof(float), db));
         CU_TRY(b_n.alloc(nj * sizeof(uint32_t), db));
         CU_TRY(b_off.alloc(nj * sizeof(uint64_t), db));
-        CU_TRY(b_err.alloc(2 * sizeof(uint32_t), db));
+        CU_TRY(b_err.alloc(2 * sizeof(uint32_t) + 8 * sizeof(unsigned long long), db));
         CU_TRY(b_cnt.alloc(ranges.size() * sizeof(unsigned long long), db));
         stamp("buffers allocated");
         CU_TRY(cudaMemcpyAsync(b_jobs.p, sorted.data(), nj * sizeof(TraceJob), cudaMemcpyHostToDevice, st));
-        CU_TRY(cudaMemsetAsync(b_err.p, 0, 2 * sizeof(uint32_t), st));
+        CU_TRY(cudaMemsetAsync(b_err.p, 0, 2 * sizeof(uint32_t) + 8 * sizeof(unsigned long long), st));
         CU_TRY(cudaMemsetAsync(b_cnt.p, 0, ranges.size() * sizeof(unsigned long long), st));
         base.ckpt = b_ck.as<float>(), base.steps_raw = b_raw.as<dcp_step>(), base.errors = b_err.as<uint32_t>();
+        base.prof = reinterpret_cast<unsigned long long *>(b_err.as<uint32_t>() + 2);
         /* one launch per kernel class, side by side on the main and side streams: a class often holds a handful of
          * hits, and a trace launch lasts as long as its longest sequence however few hits it has */
         StreamFan fan(db);
@@ -949,6 +978,15 @@ enum rc dcp_trace_hits(dcpgpu_db *db, dcpgpu_seqs *sq, dcpgpu_result *res, const
         CU_TRY(cudaMemcpyAsync(nerr, b_err.p, sizeof nerr, cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaStreamSynchronize(st));
         stamp("kernels done, counts on the host");
+        if (DCP_TRACE_PROF)
+        {
+            unsigned long long pr[8];
+            CU_TRY(cudaMemcpy(pr, base.prof, sizeof pr, cudaMemcpyDeviceToHost));
+            const double n = (double)std::max(1ull, pr[7]);
+            fprintf(stderr, "[dcp_trace prof] hits %llu: per hit kcycles fwd rows %.0f, bwd rows %.0f, walk %.0f, whole hit %.0f; "
+                            "steps %.0f, segment passes %.1f of which with every cell %.1f\n",
+                    pr[7], pr[0] / n / 1e3, pr[1] / n / 1e3, pr[2] / n / 1e3, pr[3] / n / 1e3, pr[4] / n, pr[6] / n, pr[5] / n);
+        }
         if (nerr[0]) return dcp_error(RC_EFAIL, "traceback walked off the DP matrix");
         if (nerr[1])
         {
