@@ -24,7 +24,7 @@
     /* TW = 0: two pairs per warp, 16 lanes each (k_score_h<Q>): profiles of up to 16 Q nodes */                \
     X(0, 4, 12, 568) X(0, 5, 8, 584) X(0, 6, 8, 649) X(0, 8, 8, 707)                                            \
     /* one warp per pair, 8 resident warps per SM */                                                            \
-    X(1, 5, 8, 573) X(1, 6, 8, 644) X(1, 8, 8, 726)                                                             \
+    X(1, 5, 8, 573) X(1, 6, 8, 644) X(1, 7, 8, 0) X(1, 8, 8, 726)                                                          \
     /* two warps: 12 resident warps per SM with 5 nodes per lane (168 registers), else 8 */                     \
     X(2, 5, 6, 467) X(2, 6, 4, 485) X(2, 7, 4, 504) X(2, 8, 4, 560)                                             \
     /* three warps: 12 resident warps (6 at 255 registers leave the schedulers idle) */                         \

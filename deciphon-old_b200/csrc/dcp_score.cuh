@@ -99,7 +99,11 @@ struct TmaCtx
     uint32_t g; /* rows issued so far by this warp: stage = g & 1, phase parity = (g >> 1) & 1 */
 };
 
-template <int Q, int R, bool TMA, class Tap = NoTap>
+/* MODE: how the streamed 4- and 5-nt emission lines of a row reach the registers.  0: LDG.128 one row ahead (the product
+ * path).  1: bulk copies (cp.async.bulk, SASS UBLKCP) into a per-warp shared ring two rows ahead, one mbarrier per stage.
+ * 2: per-lane 16-byte asynchronous copies (cp.async.cg, SASS LDGSTS) into the same ring two rows ahead: no registers
+ * are held across the row and the copy is issued where the source puts it. */
+template <int Q, int R, int MODE, class Tap = NoTap>
 __device__ __forceinline__ void score_row(float (&tm)[5][Q], float (&ti)[5][Q], float (&tx)[5],
                                           const NodeParams<Q> &p, RowState<Q> &rs,
                                           const float *__restrict__ emis_lane,
@@ -111,11 +115,12 @@ __device__ __forceinline__ void score_row(float (&tm)[5][Q], float (&ti)[5][Q], 
     constexpr int S1 = (R + 4) % 5, S2 = (R + 3) % 5, S3 = (R + 2) % 5, S4 = (R + 1) % 5, S5 = R;
     constexpr int QP = Q <= 4 ? 4 : 8, LINE = 32 * QP;
 
-    if constexpr (TMA)
+    if constexpr (MODE != 0)
     {
-        /* this row's 4- and 5-nt lines were bulk-copied into the stage two rows ago */
+        /* this row's 4- and 5-nt lines were copied into the stage two rows ago */
         const uint32_t st = tc.g & 1u;
-        mbar_wait(tc.bar + st, (tc.g >> 1) & 1u);
+        if constexpr (MODE == 1) mbar_wait(tc.bar + st, (tc.g >> 1) & 1u);
+        else asm volatile("cp.async.wait_group 1;" ::: "memory"); /* all but the group of the previous row */
 #pragma unroll
         for (int l = 3; l < 5; ++l)
         {
@@ -150,7 +155,27 @@ __device__ __forceinline__ void score_row(float (&tm)[5][Q], float (&ti)[5][Q], 
      * the shared emissions (their registers were just consumed) and the window two rows ahead */
     uint32_t code[5];
     codes_of(rs.w1, code);
-    if constexpr (TMA)
+    if constexpr (MODE == 2)
+    {
+        /* the stage is consumed (vm above used its values): refill it with the lines of row j+2, every lane its own
+         * 16-byte quads (it reads back only what it copied itself: no barrier) */
+        const uint32_t st = tc.g & 1u;
+#pragma unroll
+        for (int l = 3; l < 5; ++l)
+        {
+            const uint32_t cd = l == 3 ? 84u + (rs.w2 & 255u) : 340u + (rs.w2 & 1023u);
+            const float *src = emis_lane + (size_t)cd * LINE;
+            const uint32_t dst = smem_u32(tc.ring + (st * 2 + (l - 3)) * LINE + lane * 4);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            if (Q > 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 512u), "l"(src + 128) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        tc.g++;
+        rs.w1 = rs.w2;
+        rs.w2 = rs.w3;
+        rs.w3 = __ldg(w_next2);
+    }
+    else if constexpr (MODE == 1)
     {
         /* the stage is consumed (vm above used its values): refill it with the lines of row j+2 */
         __syncwarp();
@@ -257,7 +282,7 @@ __device__ __forceinline__ void score_row(float (&tm)[5][Q], float (&ti)[5][Q], 
 }
 
 /* recs / wc = record and window of row 0 of this sequence (L+1 of each) */
-template <int Q, bool TMA>
+template <int Q, int MODE>
 __device__ __forceinline__ float score_pair(const NodeParams<Q> &p, const float *__restrict__ emis_lane,
                                             const RowRec *__restrict__ recs, const uint16_t *__restrict__ wc,
                                             uint32_t L, const float *__restrict__ sp, int lane, TmaCtx &tc)
@@ -294,7 +319,30 @@ __device__ __forceinline__ float score_pair(const NodeParams<Q> &p, const float 
     rs.w1 = __ldg(wc + min(2u, L));
     rs.w2 = __ldg(wc + min(3u, L));
     rs.w3 = 0;
-    if constexpr (TMA)
+    if constexpr (MODE == 2)
+    {
+        constexpr int LINE = 32 * (Q <= 4 ? 4 : 8);
+        const uint32_t wa = __ldg(wc + 1), wb = rs.w1;
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+        {
+            const uint32_t st = (tc.g + k) & 1u, w = k ? wb : wa;
+#pragma unroll
+            for (int l = 3; l < 5; ++l)
+            {
+                const uint32_t cd = l == 3 ? 84u + (w & 255u) : 340u + (w & 1023u);
+                const float *src = emis_lane + (size_t)cd * LINE;
+                const uint32_t dst = smem_u32(tc.ring + (st * 2 + (l - 3)) * LINE + lane * 4);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                if (Q > 4) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 512u), "l"(src + 128) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        rs.w1 = __ldg(wc + min(2u, L));
+        rs.w2 = __ldg(wc + min(3u, L));
+        rs.w3 = __ldg(wc + min(4u, L));
+    }
+    else if constexpr (MODE == 1)
     {
         /* the streamed lines of rows 1 and 2 go into the two stages; from here on every row refills the
          * stage it has just consumed with the lines of the row two ahead */
@@ -320,7 +368,7 @@ __device__ __forceinline__ float score_pair(const NodeParams<Q> &p, const float 
 
     float E = NEG_INF, vx = NEG_INF;
     uint32_t j = 1;
-#define ROW_ARGS(jj) recs + min((uint32_t)(jj) + 1u, L), wc + min((uint32_t)(jj) + (TMA ? 4u : 3u), L)
+#define ROW_ARGS(jj) recs + min((uint32_t)(jj) + 1u, L), wc + min((uint32_t)(jj) + (MODE ? 4u : 3u), L)
     if constexpr (Q <= DCP_NOTAIL_MAXQ)
     {
     /* always whole groups of five rows (one copy of the row code in the instruction cache): rows past L
@@ -330,15 +378,15 @@ __device__ __forceinline__ float score_pair(const NodeParams<Q> &p, const float 
     if ((jj) == L) E_L = E, vx_L = vx;
     for (; j <= L; j += 5)
     {
-        score_row<Q, 0, TMA>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j), lane, NB, JB, EB, cE, cX, E, vx, tc);
+        score_row<Q, 0, MODE>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j), lane, NB, JB, EB, cE, cX, E, vx, tc);
         LATCH(j)
-        score_row<Q, 1, TMA>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 1), lane, NB, JB, EB, cE, cX, E, vx, tc);
+        score_row<Q, 1, MODE>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 1), lane, NB, JB, EB, cE, cX, E, vx, tc);
         LATCH(j + 1)
-        score_row<Q, 2, TMA>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 2), lane, NB, JB, EB, cE, cX, E, vx, tc);
+        score_row<Q, 2, MODE>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 2), lane, NB, JB, EB, cE, cX, E, vx, tc);
         LATCH(j + 2)
-        score_row<Q, 3, TMA>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 3), lane, NB, JB, EB, cE, cX, E, vx, tc);
+        score_row<Q, 3, MODE>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 3), lane, NB, JB, EB, cE, cX, E, vx, tc);
         LATCH(j + 3)
-        score_row<Q, 4, TMA>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 4), lane, NB, JB, EB, cE, cX, E, vx, tc);
+        score_row<Q, 4, MODE>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 4), lane, NB, JB, EB, cE, cX, E, vx, tc);
         LATCH(j + 4)
     }
 #undef LATCH
@@ -348,19 +396,20 @@ __device__ __forceinline__ float score_pair(const NodeParams<Q> &p, const float 
     {
     for (; j + 4 <= L; j += 5)
     {
-        score_row<Q, 0, TMA>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j), lane, NB, JB, EB, cE, cX, E, vx, tc);
-        score_row<Q, 1, TMA>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 1), lane, NB, JB, EB, cE, cX, E, vx, tc);
-        score_row<Q, 2, TMA>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 2), lane, NB, JB, EB, cE, cX, E, vx, tc);
-        score_row<Q, 3, TMA>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 3), lane, NB, JB, EB, cE, cX, E, vx, tc);
-        score_row<Q, 4, TMA>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 4), lane, NB, JB, EB, cE, cX, E, vx, tc);
+        score_row<Q, 0, MODE>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j), lane, NB, JB, EB, cE, cX, E, vx, tc);
+        score_row<Q, 1, MODE>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 1), lane, NB, JB, EB, cE, cX, E, vx, tc);
+        score_row<Q, 2, MODE>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 2), lane, NB, JB, EB, cE, cX, E, vx, tc);
+        score_row<Q, 3, MODE>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 3), lane, NB, JB, EB, cE, cX, E, vx, tc);
+        score_row<Q, 4, MODE>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 4), lane, NB, JB, EB, cE, cX, E, vx, tc);
     }
-    if (j <= L) score_row<Q, 0, TMA>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j), lane, NB, JB, EB, cE, cX, E, vx, tc);
-    if (j + 1 <= L) score_row<Q, 1, TMA>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 1), lane, NB, JB, EB, cE, cX, E, vx, tc);
-    if (j + 2 <= L) score_row<Q, 2, TMA>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 2), lane, NB, JB, EB, cE, cX, E, vx, tc);
-    if (j + 3 <= L) score_row<Q, 3, TMA>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 3), lane, NB, JB, EB, cE, cX, E, vx, tc);
+    if (j <= L) score_row<Q, 0, MODE>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j), lane, NB, JB, EB, cE, cX, E, vx, tc);
+    if (j + 1 <= L) score_row<Q, 1, MODE>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 1), lane, NB, JB, EB, cE, cX, E, vx, tc);
+    if (j + 2 <= L) score_row<Q, 2, MODE>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 2), lane, NB, JB, EB, cE, cX, E, vx, tc);
+    if (j + 3 <= L) score_row<Q, 3, MODE>(tm, ti, tx, p, rs, emis_lane, ROW_ARGS(j + 3), lane, NB, JB, EB, cE, cX, E, vx, tc);
     }
 #undef ROW_ARGS
-    if constexpr (TMA)
+    if constexpr (MODE == 2) asm volatile("cp.async.wait_group 0;" ::: "memory"); /* rows past the last were requested too */
+    if constexpr (MODE == 1)
     {
         /* rows L+1 and L+2 were requested too (clamped windows): drain them so the stages are free again */
         mbar_wait(tc.bar + (tc.g & 1u), (tc.g >> 1) & 1u);
@@ -374,7 +423,7 @@ __device__ __forceinline__ float score_pair(const NodeParams<Q> &p, const float 
     return fmaxf(E + ET, vC + CT);
 }
 
-template <int Q, bool TMA>
+template <int Q, int MODE>
 __global__ void __launch_bounds__(score_warps(Q) * 32, 1)
 k_score(const float *__restrict__ emis, const float *__restrict__ trans, const ProfMeta *__restrict__ metas,
         const uint32_t *__restrict__ class_profs, uint32_t n_class_profs, const SeqMeta *__restrict__ seqs,
@@ -384,14 +433,14 @@ k_score(const float *__restrict__ emis, const float *__restrict__ trans, const P
 {
     const int lane = threadIdx.x & 31;
     TmaCtx tc = {nullptr, nullptr, 0};
-    if constexpr (TMA)
+    if constexpr (MODE != 0)
     {
         extern __shared__ __align__(128) unsigned char smem_raw[];
         constexpr int LINE = 32 * (Q <= 4 ? 4 : 8);
         const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
         tc.ring = reinterpret_cast<float *>(smem_raw) + (size_t)warp * 4 * LINE;
         tc.bar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)nwarps * 4 * LINE * sizeof(float)) + warp * 2;
-        if (lane == 0)
+        if (MODE == 1 && lane == 0)
         {
             mbar_init(tc.bar, 1);
             mbar_init(tc.bar + 1, 1);
@@ -432,7 +481,7 @@ k_score(const float *__restrict__ emis, const float *__restrict__ trans, const P
         for (uint32_t s = ci * kSeqChunk; s < s_end; ++s)
         {
             SeqMeta sm = seqs[s];
-            float T = score_pair<Q, TMA>(p, emis_lane, rows_t + sm.rec_off, wcodes + sm.rec_off, sm.len,
+            float T = score_pair<Q, MODE>(p, emis_lane, rows_t + sm.rec_off, wcodes + sm.rec_off, sm.len,
                                          spec + (size_t)s * 16, lane, tc);
             if (lane == 0) alt_out[(size_t)s * nprof + prof] = T;
         }

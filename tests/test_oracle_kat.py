@@ -132,6 +132,73 @@ def test_bruteforce_tiny(o64):
     assert rc == 0 and abs(al - best[0]) < 1e-9
 
 
+@pytest.mark.parametrize("M,L", [(3, 9), (5, 17), (8, 30), (13, 41)])
+def test_state_graph_dp_matches_oracle_beyond_two_nodes(o64, M, L):
+    """The reference's runnable goldens stop at two core nodes.  Here the alt model of SURVEY.md A.3 is written down a
+    third time, as an explicit state graph in Python built straight from the text of protein_model.c:410-494 (entry to
+    every M_k, M_k -> E and D_k -> E (k >= 2) at score 0, the seven core transitions of trans[i], I_M isolated, D_1
+    unreachable) and solved by a memoised best-completion recursion -- no code shared with the oracle's transition lists
+    or its end-position recurrence.  Both entry distributions, multi-hit on and off, HMMER3-compat on and off."""
+    import functools
+    import sys
+    sys.setrecursionlimit(10000)
+    rng = np.random.default_rng(100 * M + L)
+    off = [0, 0, 4, 20, 84, 340]
+    for entry in (orc.ENTRY_UNIFORM, orc.ENTRY_OCCUPANCY):
+        p = o64.sample(int(rng.integers(1, 1 << 30)), M, entry, 0.02)
+        tr, ent, emM, emI, emN = p.trans, p.entry, p.emM, p.emI, p.emN
+        for multi, compat in ((True, False), (False, False), (True, True)):
+            seq = random_seq(rng, L)
+            rc, x = o64.specials(L, multi, compat)
+            NN, CC, JJ, NB, CT, JB, RR, EJ, EC, ET, ECC, EB, EJJ = [float(v) for v in x]
+            edges = {"S": [("N", NN), ("B", NB)], "N": [("N", NN), ("B", NB)], "C": [("C", CC), ("T", CT)],
+                     "J": [("J", JJ), ("B", JB)], "E": [("T", ET), ("C", ECC), ("B", EB), ("J", EJJ)], "T": [],
+                     "B": [("M%d" % k, float(ent[k - 1])) for k in range(1, M + 1)]}
+            table = {"N": emN, "C": emN, "J": emN}
+            for k in range(1, M + 1):
+                MM, MI, MD, IM, II, DM, DD = [float(v) for v in tr[k]]
+                table["M%d" % k] = emM[k - 1]
+                edges["M%d" % k] = [("E", 0.0)]
+                if k >= 2:
+                    edges["D%d" % k] = [("E", 0.0)]
+                if k <= M - 1:
+                    table["I%d" % k] = emI
+                    edges["M%d" % k] += [("I%d" % k, MI), ("M%d" % (k + 1), MM), ("D%d" % (k + 1), MD)]
+                    edges["I%d" % k] = [("I%d" % k, II), ("M%d" % (k + 1), IM)]
+                    if k >= 2:
+                        edges["D%d" % k] += [("M%d" % (k + 1), DM), ("D%d" % (k + 1), DD)]
+            codes = {}
+            for a in range(L):
+                v = 0
+                for l in range(1, 6):
+                    if a + l > L:
+                        break
+                    v = v * 4 + "ACGT".index(seq[a + l - 1])
+                    codes[(a, l)] = off[l] + v
+
+            @functools.lru_cache(maxsize=None)
+            def best(state, pos):
+                if state == "T":
+                    return 0.0 if pos == L else -np.inf
+                r = -np.inf
+                for nxt, t in edges[state]:
+                    if t == -np.inf:
+                        continue
+                    if nxt in table:
+                        for l in range(1, 6):
+                            if pos + l <= L:
+                                r = max(r, t + float(table[nxt][codes[(pos, l)]]) + best(nxt, pos + l))
+                    else:
+                        r = max(r, t + best(nxt, pos))
+                return r
+
+            want = best("S", 0)
+            rc, al, path = p.viterbi_alt(seq, multi, compat)
+            assert rc == 0 and np.isfinite(want)
+            assert abs(al - want) <= 1e-9 * abs(want), (M, L, entry, multi, compat, al, want)
+            assert sum(l for _, l in path) == L
+
+
 def test_long_sequence_runs(o32):
     p = o32.sample(7, 40, orc.ENTRY_OCCUPANCY, 0.01)
     rc, al, path = p.viterbi_alt(SEQ1053)
