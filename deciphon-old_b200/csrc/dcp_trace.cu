@@ -79,8 +79,8 @@ struct TraceArgs
 #endif
 #define PROF_CLK() (DCP_TRACE_PROF ? clock64() : 0ll)
 
-/* shape of a kernel class as the trace kernels see it: TW = 0 two hits^W halves per warp (16 lanes per hit; the trace
- * kernel runs the same hit on both halves: identical values, identical stores), 1 one warp, >= 2 a group of warps */
+/* shape of a kernel class as the trace kernel sees it: TW = 0 the half-warp classes (16 lanes per hit; the trace kernel
+ * runs the same hit on both halves of a warp: identical values, identical stores), 1 one warp, >= 2 a group of warps */
 template <int TW, int Q>
 struct Shape
 {
@@ -330,7 +330,6 @@ __device__ __forceinline__ void walk_segment(Walker &w, uint32_t j0, uint32_t M,
         const uint32_t t = n / Q, sub = n % Q, wp = t / S::LN, ln = t % S::LN;
         return __ldg(emis + (size_t)code * S::MP + wp * (S::LN * S::QP) + (sub >> 2) * (S::LN * 4) + ln * 4 + (sub & 3));
     };
-    auto par = [&](int which, uint32_t n) -> float { return __ldg(tr + which * S::NP + n); };
 
     auto stored = [&](uint32_t n) -> bool { return band.has((int)(n / Q)); };
     w.need_full = false;
