@@ -145,24 +145,12 @@ struct Who
     int xs;    /* 0..2: this thread carries N / J / C; 3: it writes E and B of the row; else -1 */
 };
 
-/* length-dependent special scores: what a row needs (the rest is read by the walk when it needs it, so that it does
- * not occupy registers across the rows) */
+/* length-dependent special scores: what a row needs (the walk reads the rest from the sequence's record when a
+ * candidate uses it) */
 struct RowSpecials
 {
     float NB, JB, EB, cE, cX;
 };
-struct Specials
-{
-    float NN, CC, JJ, NB, CT, JB, ET, ECC, EB, EJJ;
-};
-__device__ __forceinline__ Specials load_specials(const float *__restrict__ spv)
-{
-    Specials k;
-    k.NN = __ldg(spv + 0), k.CC = __ldg(spv + 1), k.JJ = __ldg(spv + 2), k.NB = __ldg(spv + 3), k.CT = __ldg(spv + 4);
-    k.JB = __ldg(spv + 5), k.ET = __ldg(spv + 9), k.ECC = __ldg(spv + 10), k.EB = __ldg(spv + 11), k.EJJ = __ldg(spv + 12);
-    return k;
-}
-
 /* ----------------------------------------------------------------------------------------- */
 /* rows j0 + 1 .. min(L, j0 + C) from the ring as it stands after row j0                       */
 /* ----------------------------------------------------------------------------------------- */
@@ -300,6 +288,51 @@ __device__ __forceinline__ uint16_t state_id_of(int st, uint32_t k)
     }
 }
 
+/*
+ * Candidates of Tin_s[r] by state and index, in the canonical order (header of this file), 16 bits each:
+ *   kind:3 (0 none, WK_M / WK_I / WK_D a cell of the source node, WK_ROW a field of the row record) | source length:3 |
+ *   source node is this node (1) or the one before (0):1 | transition: index of the per-node parameter array (core)
+ *   or of the sequence's specials record:4 | row-record field:3 | needs a node before this one:1 | core:1
+ */
+enum { WK_NONE, WK_M, WK_I, WK_D, WK_ROW };
+__device__ __forceinline__ uint32_t walk_entry(int st, int c)
+{
+    auto cellc = [](uint32_t kind, uint32_t l, uint32_t same, uint32_t par, uint32_t need) {
+        return kind | l << 3 | same << 6 | par << 7 | need << 14 | 1u << 15;
+    };
+    auto rowc = [](uint32_t field, uint32_t l, uint32_t spec, uint32_t core) {
+        return (uint32_t)WK_ROW | l << 3 | spec << 7 | field << 11 | core << 15;
+    };
+    /* specials record (dcp_specials): 0 NN, 1 CC, 2 JJ, 3 NB, 4 CT, 5 JB, 9 E->T, 10 E->C, 11 E->B, 12 E->J;
+     * parameter arrays: 0 MM, 1 IM, 2 DM, 3 MD, 4 DD (into this node), 5 MI, 6 II (own), 7 entry */
+    const bool lo = c >= 1 && c <= 5, hi = c >= 6 && c <= 10;
+    const uint32_t l = lo ? (uint32_t)c : hi ? (uint32_t)c - 5u : 0u;
+    switch (st)
+    {
+    case W_M:
+        if (c == 0) return rowc(1, 0, 7, 1); /* B[r] + entry */
+        if (lo) return cellc(WK_M, l, 0, 0, 1);
+        if (hi) return cellc(WK_I, l, 0, 1, 1);
+        if (c == 11) return cellc(WK_D, 0, 0, 2, 1);
+        return 0;
+    case W_I:
+        if (c < 5) return cellc(WK_M, (uint32_t)c + 1u, 1, 5, 0);
+        if (c < 10) return cellc(WK_I, (uint32_t)c - 4u, 1, 6, 0);
+        return 0;
+    case W_D:
+        if (c < 5) return cellc(WK_M, (uint32_t)c + 1u, 0, 3, 1);
+        if (c == 5) return cellc(WK_D, 0, 0, 4, 1);
+        return 0;
+    case W_T: return c == 0 ? rowc(0, 0, 9, 0) : lo ? rowc(4, l, 4, 0) : 0;
+    case W_C: return c == 0 ? rowc(0, 0, 10, 0) : lo ? rowc(4, l, 1, 0) : 0;
+    case W_J: return c == 0 ? rowc(0, 0, 12, 0) : lo ? rowc(3, l, 2, 0) : 0;
+    case W_N: return lo ? rowc(2, l, 0, 0) : 0;
+    case W_B: return lo ? rowc(2, l, 3, 0) : hi ? rowc(3, l, 5, 0) : c == 11 ? rowc(0, 0, 11, 0) : 0;
+    default: return 0;
+    }
+}
+constexpr int kWalkTab = 10 * 16; /* [state][candidate] */
+
 /* frame-table code of seq[r-l:r] from the packed window of row r */
 __device__ __forceinline__ uint32_t code_of_len(uint32_t w, uint32_t l)
 {
@@ -318,10 +351,9 @@ __device__ __forceinline__ void walk_segment(Walker &w, uint32_t j0, uint32_t M,
                                              const float *__restrict__ tr, const RowRec *__restrict__ recs,
                                              const uint16_t *__restrict__ wc, const float *__restrict__ spv,
                                              dcp_step *__restrict__ out, uint32_t cap, int c, const Band &band,
-                                             float *__restrict__ alt_out)
+                                             float *__restrict__ alt_out, const uint16_t *tab)
 {
     using S = Shape<TW, Q>;
-    const Specials sp = load_specials(spv);
     auto cell = [&](int which, uint32_t n, uint32_t row) -> float {
         return __ldcg(cells + ((size_t)(row - j0 + 4u) * 3 + which) * S::MP + cell_slot<Q, S::NT>(n));
     };
@@ -416,126 +448,56 @@ __device__ __forceinline__ void walk_segment(Walker &w, uint32_t j0, uint32_t M,
         {
             /*
              * Lane c describes candidate c -- where its source value, its emission and its transition score live --
-             * with selects, then every lane loads and adds at once: (a + e) + t, e = 0 for a mute source (B, E, D).
-             * Branches per candidate kind would serialise their loads: three L2 round trips per step instead of one.
+             * from a table entry and selects, then every lane loads and adds at once: (a + e) + t, e = 0 for a mute
+             * source (B, E, D).  No branch depends on the lane: branches per candidate kind serialise their loads (three
+             * L2 round trips per step instead of one), and a divergent description costs more than the arithmetic.
              */
             const RowRec *rec = recs + r;
-            const float *pa = rowrec; /* any readable address: lanes without a candidate are masked below */
-            const float *pe = nullptr, *pt = nullptr;
-            float tc = 0.0f;
-            bool valid = false;
-            auto cell_p = [&](int which, uint32_t n, uint32_t row) -> const float * {
-                return cells + ((size_t)(row - j0 + 4u) * 3 + which) * S::MP + cell_slot<Q, S::NT>(n);
-            };
-            auto rowv_p = [&](int idx, uint32_t row) -> const float * { return rowrec + (size_t)(row - j0 + 4u) * S::RR + idx; };
-            auto emis_p = [&](uint32_t n, uint32_t code) -> const float * {
-                const uint32_t t = n / Q, sub = n % Q, wp = t / S::LN, ln = t % S::LN;
-                return emis + (size_t)code * S::MP + wp * (S::LN * S::QP) + (sub >> 2) * (S::LN * 4) + ln * 4 + (sub & 3);
-            };
-            if (w.st == W_M || w.st == W_I || w.st == W_D)
-            {
-                const uint32_t n = w.k - 1u;
-                /* per state: which candidates read M / I / D of the source node, and the first of each kind */
-                int which, par_i;
-                uint32_t l = 0, src;
-                if (w.st == W_M)
-                {
-                    const bool isB = c == 0, isM = c >= 1 && c <= 5, isI = c >= 6 && c <= 10, isD = c == 11;
-                    which = isM ? 0 : isI ? 1 : 2;
-                    l = isM ? (uint32_t)c : isI ? (uint32_t)c - 5u : 0u;
-                    src = n >= 1 ? n - 1 : 0;
-                    valid = isB || ((isM || isI || isD) && n >= 1);
-                    par_i = isB ? 7 : which;
-                    if (isB) which = -1;
-                }
-                else if (w.st == W_I)
-                {
-                    const bool isM = c < 5, isI = c >= 5 && c < 10;
-                    which = isM ? 0 : 1;
-                    l = (uint32_t)c % 5u + 1u;
-                    src = n;
-                    valid = isM || isI;
-                    par_i = 5 + which;
-                }
-                else
-                {
-                    const bool isM = c < 5, isD = c == 5;
-                    which = isM ? 0 : 2;
-                    l = isM ? (uint32_t)c + 1u : 0u;
-                    src = n >= 1 ? n - 1 : 0;
-                    valid = (isM || isD) && n >= 1;
-                    par_i = isM ? 3 : 4;
-                }
-                if (valid)
-                {
-                    pa = which < 0 ? rowv_p(1, r) : cell_p(which, src, r - l);
-                    pe = which == 0 ? emis_p(src, code_of_len(win, l)) : which == 1 ? &rec->eI[l - 1] : nullptr;
-                    pt = tr + par_i * S::NP + n;
-                }
-            }
-            else
-            {
-                /* specials: candidate 0 = E (T, C, J) or S (N, B: row 0 only); 1..5 and 6..10 = an emitting source by
-                 * length; 11 = E -> B */
-                const uint32_t l = (uint32_t)(c + 4) % 5u + 1u; /* 1..5 for c = 1..5 and 6..10 */
-                const bool lo = c >= 1 && c <= 5, hi = c >= 6 && c <= 10;
-                int idx = 0; /* row-record field of the source: 0 E, 2 Tin_N, 3 Tin_J, 4 Tin_C */
-                if (w.st == W_T) valid = c <= 5, idx = lo ? 4 : 0, tc = lo ? sp.CT : sp.ET;
-                else if (w.st == W_C) valid = c <= 5, idx = lo ? 4 : 0, tc = lo ? sp.CC : sp.ECC;
-                else if (w.st == W_J) valid = c <= 5, idx = lo ? 3 : 0, tc = lo ? sp.JJ : sp.EJJ;
-                else if (w.st == W_N) valid = lo, idx = 2, tc = sp.NN;
-                else /* W_B */ valid = lo || hi || c == 11, idx = lo ? 2 : hi ? 3 : 0, tc = lo ? sp.NB : hi ? sp.JB : sp.EB;
-                if (valid)
-                {
-                    const bool emits = idx != 0;
-                    pa = rowv_p(idx, emits ? r - l : r);
-                    pe = emits ? &rec->eN[l - 1] : nullptr;
-                }
-            }
+            const uint32_t n = w.k - 1u; /* core states: this node */
+            const uint32_t ent = tab[w.st * 16 + (c & 15)] & (c < 16 ? 0xffffu : 0u);
+            const uint32_t kind = ent & 7u, l = (ent >> 3) & 7u, dn = (ent >> 6) & 1u, tix = (ent >> 7) & 15u;
+            const uint32_t idx = (ent >> 11) & 7u;
+            const bool need_n1 = (ent >> 14) & 1u, core = (ent >> 15) & 1u;
+            const bool valid = kind != 0 && !(need_n1 && n == 0);
+            const uint32_t src = valid && kind <= WK_D ? n - 1u + dn : 0u;
+            const uint32_t slot = valid ? r - l - j0 + 4u : 4u;
+            const float *pa = kind <= WK_D ? cells + ((size_t)slot * 3 + (kind - 1u)) * S::MP + cell_slot<Q, S::NT>(src)
+                                           : rowrec + (size_t)slot * S::RR + idx;
+            if (!valid) pa = rowrec;
+            const uint32_t t_ = src / Q, sub = src % Q, wp = t_ / S::LN, ln = t_ % S::LN;
+            const uint32_t lc = l ? l : 1u;
+            const float *pe_m = emis + (size_t)code_of_len(win, lc) * S::MP + wp * (S::LN * S::QP) + (sub >> 2) * (S::LN * 4) +
+                                ln * 4 + (sub & 3);
+            const float *pe_r = (kind == WK_I ? rec->eI : rec->eN) + (lc - 1u);
+            const bool emits = valid && l != 0 && kind != WK_D;
+            const float *pe = kind == WK_M ? pe_m : pe_r;
+            const float *pt = core ? tr + tix * S::NP + n : spv + tix;
             const float va = __ldcg(pa);
-            const float ve = pe ? __ldg(pe) : 0.0f;
-            const float vt = pt ? __ldg(pt) : tc;
+            const float ve = emits ? __ldg(pe) : 0.0f;
+            const float vt = valid ? __ldg(pt) : 0.0f;
             const float v = valid ? (va + ve) + vt : NEG_INF;
             const float best = warp_max(v);
             /* the candidates of T at row L are T[L] = max(E[L] + (EC+CT), V_C[L] + CT) itself: the alt log-likelihood
              * of this pass, compared with the score pass's on the host */
             if (w.st == W_T && c == 0) *alt_out = best;
             const unsigned who = __ballot_sync(FULL, v == best);
-            const uint32_t code = who ? (uint32_t)(__ffs(who) - 1) : 0u;
-            switch (w.st)
+            const int code = who ? __ffs(who) - 1 : 0;
+            /* the winner's entry says what the source is */
+            const uint32_t went = __shfl_sync(FULL, valid ? ent : 0u, code);
+            const uint32_t wkind = went & 7u;
+            src_len = (went >> 3) & 7u;
+            if (wkind == 0)
+                w.bad = true; /* nothing finite leads here (or S below row 0) */
+            else if (wkind <= WK_D)
             {
-            case W_M:
-                if (code == 0) nst = W_B;
-                else if (code <= 5) nst = W_M, nk = w.k - 1, src_len = code;
-                else if (code <= 10) nst = W_I, nk = w.k - 1, src_len = code - 5;
-                else nst = W_D, nk = w.k - 1;
-                if (nk == 0 && nst != W_B) w.bad = true;
-                break;
-            case W_I:
-                if (code <= 4) nst = W_M, src_len = code + 1;
-                else nst = W_I, src_len = code - 4;
-                break;
-            case W_D:
-                if (code <= 4) nst = W_M, nk = w.k - 1, src_len = code + 1;
-                else nst = W_D, nk = w.k - 1;
+                nst = wkind == WK_M ? W_M : wkind == WK_I ? W_I : W_D;
+                nk = w.k - 1u + ((went >> 6) & 1u);
                 if (nk == 0) w.bad = true;
-                break;
-            case W_T:
-            case W_C:
-                if (code == 0) nst = W_E; else nst = W_C, src_len = code;
-                break;
-            case W_J:
-                if (code == 0) nst = W_E; else nst = W_J, src_len = code;
-                break;
-            case W_N:
-                if (code == 0) nst = W_S; else nst = W_N, src_len = code;
-                break;
-            default: /* W_B */
-                if (code == 0) nst = W_S;
-                else if (code <= 5) nst = W_N, src_len = code;
-                else if (code <= 10) nst = W_J, src_len = code - 5;
-                else nst = W_E;
-                break;
+            }
+            else
+            {
+                const uint32_t f = (went >> 11) & 7u; /* row-record field of the source: E, B, Tin_N, Tin_J, Tin_C */
+                nst = f == 0 ? W_E : f == 1 ? W_B : f == 2 ? W_N : f == 3 ? W_J : W_C;
             }
         }
         if (src_len > r) w.bad = true;
@@ -560,8 +522,8 @@ struct WalkShared
 };
 
 template <int TW, int Q>
-__device__ __noinline__ void walk_pass(const TraceArgs *__restrict__ a, WalkShared *ws, WalkShared *peer_ws, uint32_t job,
-                                       uint32_t j0, float *scr)
+__device__ __noinline__ void walk_pass(const TraceArgs *__restrict__ a, WalkShared *ws, WalkShared *peer_ws,
+                                       const uint16_t *tab, uint32_t job, uint32_t j0, float *scr)
 {
     using S = Shape<TW, Q>;
     const int c = threadIdx.x & 31;
@@ -574,7 +536,7 @@ __device__ __noinline__ void walk_pass(const TraceArgs *__restrict__ a, WalkShar
     band.lo = ws->band_lo, band.hi = ws->band_hi, band.full = ws->again != 0; /* what this pass stored */
     walk_segment<TW, Q>(w, j0, pm.M, scr, rowrec, a->emis + pm.emis_off, a->trans + pm.trans_off,
                         a->rows + (size_t)pm.null_id * a->total_recs + sm.rec_off, a->wcodes + sm.rec_off,
-                        a->spec + (size_t)tj.seq * 16, a->steps_raw + tj.step_off, tj.cap, c, band, a->alt_out + job);
+                        a->spec + (size_t)tj.seq * 16, a->steps_raw + tj.step_off, tj.cap, c, band, a->alt_out + job, tab);
     const int band_lanes = (int)((a->C / 3u + 8u) / Q + 2u);
     const Band next = band_of<Q>(w.st, w.k, band_lanes);
     __syncwarp();
@@ -600,7 +562,9 @@ __global__ void __launch_bounds__(Shape<TW, Q>::BLOCK, Shape<TW, Q>::MINB) k_tra
     __shared__ WalkShared sh_walk[TW <= 1 ? 4 : 1];  /* walker state and its verdict, per hit in flight in this block */
     Group<CL, MwShared> grp;
     grp.init(&sh);
+    __shared__ uint16_t sh_tab[kWalkTab];            /* the walk's candidate table */
     if (threadIdx.x == 0) sh_args = a;
+    for (int i = threadIdx.x; i < kWalkTab; i += blockDim.x) sh_tab[i] = (uint16_t)walk_entry(i / 16, i % 16);
     __syncthreads();
     WalkShared *const ws = sh_walk + (TW <= 1 ? (threadIdx.x >> 5) : 0);
     WalkShared *peer_ws = nullptr;
@@ -773,7 +737,7 @@ __global__ void __launch_bounds__(Shape<TW, Q>::BLOCK, Shape<TW, Q>::MINB) k_tra
             if (walker)
             {
                 const long long pc1 = PROF_CLK();
-                walk_pass<TW, Q>(&sh_args, ws, peer_ws, job, j0, scr);
+                walk_pass<TW, Q>(&sh_args, ws, peer_ws, sh_tab, job, j0, scr);
                 pc_walk += PROF_CLK() - pc1;
             }
             if constexpr (TW <= 1) __syncwarp();
