@@ -4,8 +4,8 @@
  *
  * The reference keeps one backpointer per (row, state) of the whole DP matrix of a task (imm_task, reused per
  * thread: src/server/scan_thread.c:40-55).  Here a hit is traced by row checkpointing, with the score kernels' own
- * row code (score_row / score_row_h / mw_row: same lane layout, same fp32 operation order, so T[L] is bit-equal
- * and is cross-checked against the score pass):
+ * row code (score_row / score_row_h / mw_row: same lane layout, same fp32 operation order, so every value is bit-equal
+ * to the score pass's; T[L], which falls out of the walk's first step, is compared with it on the host):
  *
  *   forward   rows 1..L; before every segment of C rows the five-row ring of Tin_M / Tin_I / Tin_N,J,C -- all the
  *             state the recurrence carries -- is stored: 40 B per node and C rows instead of a backpointer per cell
@@ -68,7 +68,7 @@ struct TraceArgs
     float *scratch;                /* per resident group: (C + 5) rows of cells and row records */
     dcp_step *steps_raw;
     uint32_t *nsteps;              /* per job; 0 on failure */
-    float *alt_out;                /* per job: T[L] of the forward pass */
+    float *alt_out;                /* per job: T[L] as the walk's first step forms it (compared with the score pass) */
     uint32_t *errors;              /* [0] walks that left the DP matrix, [1] step buffers that were too small */
     unsigned long long *prof;      /* DCP_TRACE_PROF builds: cycles in forward rows, backward rows, walks, the rest of
                                     * a hit; walk steps; segments recomputed with every cell; segment passes */
