@@ -11,7 +11,9 @@
  *   BPS   resident blocks per SM the kernel is compiled for (TW = 1: warps per block, one block per SM).  The
  *         register file gives 8 warps per SM at 255 registers a thread, 12 at 168, 16 at 128.
  *   RATE  measured score-pass rate in 1e9 padded (row, node) cells per second on one B200
- *         (tools/class_sweep.py, profiles/r02_class_sweep*.jsonl); 0 = compiled in for experiments
+ *         (tools/class_sweep.py, profiles/r02_class_sweep*.jsonl; the seven classes that read whole 32-byte emission
+ *         lines per lane -- dcp_kernels.cuh: emis256 -- scaled by their measured gain, tools/r2_e256_probe.sh);
+ *         0 = compiled in for experiments
  *         (DCPGPU_FORCE_SHAPE) but never chosen.
  *
  * A profile of M nodes runs in the class that minimises padded width / RATE among those that hold it
@@ -22,15 +24,15 @@
 
 #define DCP_CLASS_TABLE(X)                                                                                      \
     /* TW = 0: two pairs per warp, 16 lanes each (k_score_h<Q>): profiles of up to 16 Q nodes */                \
-    X(0, 4, 12, 568) X(0, 5, 8, 584) X(0, 6, 8, 649) X(0, 8, 8, 707)                                            \
+    X(0, 4, 12, 568) X(0, 5, 8, 584) X(0, 6, 8, 649) X(0, 8, 8, 715)                                            \
     /* one warp per pair, 8 resident warps per SM */                                                            \
-    X(1, 5, 8, 573) X(1, 6, 8, 644) X(1, 7, 8, 0) X(1, 8, 8, 726)                                                          \
+    X(1, 5, 8, 573) X(1, 6, 8, 647) X(1, 7, 8, 0) X(1, 8, 8, 730)                                                          \
     /* two warps: 12 resident warps per SM with 5 nodes per lane (168 registers), else 8 */                     \
-    X(2, 5, 6, 467) X(2, 6, 4, 485) X(2, 7, 4, 504) X(2, 8, 4, 560)                                             \
+    X(2, 5, 6, 480) X(2, 6, 4, 485) X(2, 7, 4, 504) X(2, 8, 4, 582)                                             \
     /* three warps: 12 resident warps (6 at 255 registers leave the schedulers idle) */                         \
-    X(3, 6, 4, 382)                                                                                             \
+    X(3, 6, 4, 387)                                                                                             \
     /* four warps */                                                                                            \
-    X(4, 5, 3, 393) X(4, 6, 2, 404) X(4, 7, 2, 436) X(4, 8, 2, 468)                                             \
+    X(4, 5, 3, 393) X(4, 6, 2, 407) X(4, 7, 2, 436) X(4, 8, 2, 468)                                             \
     /* six and eight warps: 12 or 8 resident warps per SM; five or seven leave issue slots idle */                       \
     X(6, 6, 2, 359) X(8, 6, 1, 355) X(8, 7, 1, 391) X(8, 8, 1, 417)                             \
     /* two blocks of a cluster */                                                                               \

@@ -99,7 +99,7 @@ __global__ void k_null(const SeqMeta *__restrict__ seqs, uint32_t nseq, uint32_t
  * (node k-1 = warp * 32 Q + lane * Q + sub sits in half sub/4, float sub%4 of its lane; pads are -inf).
  */
 __global__ void k_layout(const float *__restrict__ raw, float *__restrict__ out, uint32_t M, uint32_t Q, uint32_t QP,
-                         uint32_t W, uint32_t LN)
+                         uint32_t W, uint32_t LN, bool whole)
 {
     /* LN lanes per pair (32, or 16 for the half-warp classes): a line is [warp][half][LN lanes][4] */
     const uint32_t ROW = LN * QP * W;
@@ -107,7 +107,8 @@ __global__ void k_layout(const float *__restrict__ raw, float *__restrict__ out,
     if (x >= (size_t)kTab * ROW) return;
     const uint32_t code = (uint32_t)(x / ROW), pos = (uint32_t)(x % ROW);
     const uint32_t warp = pos / (LN * QP), r = pos % (LN * QP);
-    const uint32_t half = r / (LN * 4), lane = (r % (LN * 4)) / 4, sub = half * 4 + (r % 4);
+    uint32_t half = r / (LN * 4), lane = (r % (LN * 4)) / 4, sub = half * 4 + (r % 4);
+    if (whole) lane = r / QP, sub = r % QP; /* [lane][8]: one 256-bit load per lane (dcp_kernels.cuh: emis256) */
     float v = NEG_INF;
     if (sub < Q)
     {
@@ -382,7 +383,8 @@ enum rc db_commit(dcpgpu_db *db)
         const uint32_t ROW = m.LN * m.QP * m.W;
         const size_t out = (size_t)kTab * ROW;
         k_layout<<<(unsigned)((out + 255) / 256), 256, 0, db->stream>>>(stg.dev[b], db->d_emis + m.emis_off, m.M, m.Q,
-                                                                         m.QP, m.W, m.LN);
+                                                                         m.QP, m.W, m.LN,
+                                                                         emis256(m.LN == 16 ? 0 : (int)m.W, (int)m.Q));
         const uint32_t NP = m.LN * m.Q * m.W;
         float *tr = tr_all.data() + m.trans_off;
         for (uint32_t k = 1; k <= m.M; ++k) /* node k, slot k-1 */

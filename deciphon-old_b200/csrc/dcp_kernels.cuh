@@ -76,9 +76,33 @@ __device__ __forceinline__ void load_row_special(const RowRec *__restrict__ r, f
 #ifndef DCP_POLICY
 #define DCP_POLICY 0
 #endif
-#ifndef DCP_Q7_LOAD8
-#define DCP_Q7_LOAD8 0
+/*
+ * Two layouts of an emission line.  Split: [code][warp][half][lane][4], a lane's first quad by one 128-bit load and
+ * its second quad by a 4..16-byte load 512 bytes further on.  Whole: [code][warp][lane][8], a lane's eight floats by one
+ * 256-bit load (SASS LDG.E.ENL2.256): five instead of ten loads per row.  Which one is faster is a property of the
+ * kernel's schedule, not of the memory system -- measured per class (tools/r2_e256_probe.sh, kernel-only GCUPS, whole
+ * against split): (2,8) +3.9 %, (2,5) +2.7 %, (3,6) +1.2 %, (0,8) +1.1 %, (4,6) +0.8 %, (1,8) +0.6 %, (1,6) +0.4 %;
+ * (2,6) -2.9 %, (2,7) -3.0 %, (8,8) -1.8 %, (0,5) -1.7 %, (1,5) -1.2 %, (4,8) -0.9 % -- so the layout is chosen by
+ * class (TW = warps per pair, 0 for the half-warp classes; Q = nodes per lane).  DCP_EMIS256_ALL = 0 / 1 forces
+ * split / whole everywhere (variant builds).
+ */
+#ifndef DCP_EMIS256_ALL
+#define DCP_EMIS256_ALL -1
 #endif
+__host__ __device__ constexpr bool emis256(int TW, int Q)
+{
+    return Q <= 4 ? false
+           : DCP_EMIS256_ALL >= 0
+               ? DCP_EMIS256_ALL != 0
+               : (TW == 0 && Q == 8) || (TW == 1 && (Q == 6 || Q == 8)) || (TW == 2 && (Q == 5 || Q == 8)) ||
+                     (TW == 3 && Q == 6) || (TW == 4 && Q == 6);
+}
+/* floats between consecutive lanes' data in a line, and the position of a lane's sub-node inside its warp-unit */
+__host__ __device__ constexpr int emis_lane_stride(int TW, int Q) { return emis256(TW, Q) ? 8 : 4; }
+__host__ __device__ inline uint32_t emis_pos(uint32_t lane, uint32_t sub, uint32_t LN, int TW, int Q)
+{
+    return emis256(TW, Q) ? lane * 8 + sub : (sub >> 2) * (LN * 4) + lane * 4 + (sub & 3);
+}
 
 /* L1 policy experiments for the emission lines, by window length l (0..4 = 1..5 nt):
  * 0 default everywhere; 1: 5-nt lines no_allocate; 2: 4- and 5-nt lines no_allocate;
@@ -102,7 +126,7 @@ __device__ __forceinline__ float4 ldg4(const float *p, int L)
 
 /* ROW = floats per table line of the profile; HOFF = floats between a lane's first and second quad (lanes per
  * pair x 4: 128 for a whole warp per pair, 64 for a half-warp per pair) */
-template <int Q, int L0, int L1, int ROW = 32 * (Q <= 4 ? 4 : 8), int HOFF = 128>
+template <int Q, int L0, int L1, int ROW = 32 * (Q <= 4 ? 4 : 8), int HOFF = 128, bool E256 = false>
 __device__ __forceinline__ void load_emis_part(float (&em)[5][Q], const float *__restrict__ emis_lane,
                                                const uint32_t (&code)[5])
 {
@@ -110,6 +134,16 @@ __device__ __forceinline__ void load_emis_part(float (&em)[5][Q], const float *_
     for (int l = L0; l < L1; ++l)
     {
         const float *src = emis_lane + (size_t)code[l] * ROW;
+        if (E256)
+        {
+            float t[8];
+            asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                : "=f"(t[0]), "=f"(t[1]), "=f"(t[2]), "=f"(t[3]), "=f"(t[4]), "=f"(t[5]), "=f"(t[6]), "=f"(t[7])
+                : "l"(src));
+#pragma unroll
+            for (int i = 0; i < Q; ++i) em[l][i] = t[i];
+            continue;
+        }
         if (Q >= 4)
         {
             float4 a = ldg4(src, l);
@@ -156,11 +190,11 @@ __device__ __forceinline__ void load_emis_part(float (&em)[5][Q], const float *_
     }
 }
 
-template <int Q, int ROW = 32 * (Q <= 4 ? 4 : 8), int HOFF = 128>
+template <int Q, int ROW = 32 * (Q <= 4 ? 4 : 8), int HOFF = 128, bool E256 = false>
 __device__ __forceinline__ void load_emis(float (&em)[5][Q], const float *__restrict__ emis_lane,
                                           const uint32_t (&code)[5])
 {
-    load_emis_part<Q, 0, 5, ROW, HOFF>(em, emis_lane, code);
+    load_emis_part<Q, 0, 5, ROW, HOFF, E256>(em, emis_lane, code);
 }
 
 /* ----------------------------------------------------------------------------------------- */

@@ -114,6 +114,7 @@ __device__ __forceinline__ void score_row(float (&tm)[5][Q], float (&ti)[5][Q], 
 {
     constexpr int S1 = (R + 4) % 5, S2 = (R + 3) % 5, S3 = (R + 2) % 5, S4 = (R + 1) % 5, S5 = R;
     constexpr int QP = Q <= 4 ? 4 : 8, LINE = 32 * QP;
+    static_assert(MODE == 0 || !emis256(1, Q), "the shared-memory staging experiments read the split line layout: build with -DDCP_EMIS256_ALL=0");
 
     if constexpr (MODE != 0)
     {
@@ -194,7 +195,7 @@ __device__ __forceinline__ void score_row(float (&tm)[5][Q], float (&ti)[5][Q], 
     }
     else
     {
-        load_emis_part<Q, 3, 5>(rs.em, emis_lane, code);
+        load_emis_part<Q, 3, 5, 32 * QP, 128, emis256(1, Q)>(rs.em, emis_lane, code);
         rs.w1 = rs.w2;
         rs.w2 = __ldg(w_next2);
     }
@@ -237,7 +238,7 @@ __device__ __forceinline__ void score_row(float (&tm)[5][Q], float (&ti)[5][Q], 
     if (lane == 0) vi_prev = NEG_INF;
 
     /* issue row j+1, part 2: the short lines (L1 resident) */
-    load_emis_part<Q, 0, 3>(rs.em, emis_lane, code);
+    load_emis_part<Q, 0, 3, 32 * QP, 128, emis256(1, Q)>(rs.em, emis_lane, code);
 
     /* B[j] = max(V_N + NB, V_J + JB, E + (EJ+JB)) */
     float vN = __shfl_sync(FULL, vx, 0);
@@ -312,7 +313,7 @@ __device__ __forceinline__ float score_pair(const NodeParams<Q> &p, const float 
     {
         uint32_t code[5];
         codes_of(__ldg(wc + 1), code);
-        load_emis<Q>(rs.em, emis_lane, code);
+        load_emis<Q, 32 * (Q <= 4 ? 4 : 8), 128, emis256(1, Q)>(rs.em, emis_lane, code);
     }
     load_row_insert(recs + 1, rs.eI);
     if (lane < 3) load_row_special(recs + 1, rs.eN);
@@ -475,7 +476,7 @@ k_score(const float *__restrict__ emis, const float *__restrict__ trans, const P
         ProfMeta pm = metas[prof];
         NodeParams<Q> p;
         load_params<Q>(p, trans + pm.trans_off, 32 * Q, lane * Q);
-        const float *emis_lane = emis + pm.emis_off + lane * 4;
+        const float *emis_lane = emis + pm.emis_off + lane * emis_lane_stride(1, Q);
         const RowRec *rows_t = rows + (size_t)pm.null_id * total_recs;
         uint32_t s_end = min(nseq, (ci + 1) * kSeqChunk);
         for (uint32_t s = ci * kSeqChunk; s < s_end; ++s)
@@ -536,7 +537,7 @@ __device__ __forceinline__ void score_row_h(float (&tm)[5][Q], float (&ti)[5][Q]
 
     uint32_t code[5];
     codes_of(rs.w1, code);
-    load_emis_part<Q, 3, 5, ROW, HOFF>(rs.em, emis_lane, code);
+    load_emis_part<Q, 3, 5, ROW, HOFF, emis256(0, Q)>(rs.em, emis_lane, code);
     rs.w1 = rs.w2;
     rs.w2 = __ldg(w_next2);
     load_row_insert(rec_next, rs.eI);
@@ -572,7 +573,7 @@ __device__ __forceinline__ void score_row_h(float (&tm)[5][Q], float (&ti)[5][Q]
     float vi_prev = __shfl_up_sync(FULL, vi[Q - 1], 1, 16);
     if (hl == 0) vi_prev = NEG_INF;
 
-    load_emis_part<Q, 0, 3, ROW, HOFF>(rs.em, emis_lane, code);
+    load_emis_part<Q, 0, 3, ROW, HOFF, emis256(0, Q)>(rs.em, emis_lane, code);
 
     const float vN = __shfl_sync(FULL, vx, 0, 16);
     const float vJ = __shfl_sync(FULL, vx, 1, 16);
@@ -644,7 +645,7 @@ __device__ __forceinline__ float score_pair_h(const NodeParams<Q> &p, const floa
     {
         uint32_t code[5];
         codes_of(__ldg(wc + 1), code);
-        load_emis<Q, 16 * QP, 64>(rs.em, emis_lane, code);
+        load_emis<Q, 16 * QP, 64, emis256(0, Q)>(rs.em, emis_lane, code);
     }
     load_row_insert(recs + 1, rs.eI);
     if (hl < 3) load_row_special(recs + 1, rs.eN);
@@ -710,7 +711,7 @@ k_score_h(const float *__restrict__ emis, const float *__restrict__ trans, const
         const ProfMeta pm = metas[prof];
         NodeParams<Q> p;
         load_params<Q>(p, trans + pm.trans_off, 16 * Q, hl * Q);
-        const float *emis_lane = emis + pm.emis_off + hl * 4;
+        const float *emis_lane = emis + pm.emis_off + hl * emis_lane_stride(0, Q);
         const RowRec *rows_t = rows + (size_t)pm.null_id * total_recs;
         const uint32_t s_end = min(nseq, (ci + 1) * kSeqChunk);
         for (uint32_t s0 = ci * kSeqChunk; s0 < s_end; s0 += 2)

@@ -107,7 +107,7 @@ __device__ __forceinline__ void mw_row(float (&tm)[5][Q], float (&ti)[5][Q], flo
 
     uint32_t code[5];
     codes_of(rs.w1, code);
-    load_emis_part<Q, 3, 5, ROW>(rs.em, emis_lane, code);
+    load_emis_part<Q, 3, 5, ROW, 128, emis256(TW, Q)>(rs.em, emis_lane, code);
     load_row_insert(rec_next, rs.eI);
     if (gw == 0 && lane < 3) load_row_special(rec_next, rs.eN);
     rs.w1 = rs.w2;
@@ -120,7 +120,7 @@ __device__ __forceinline__ void mw_row(float (&tm)[5][Q], float (&ti)[5][Q], flo
     float vm_prev = __shfl_up_sync(FULL, vm[Q - 1], 1);
     float vi_prev = __shfl_up_sync(FULL, vi[Q - 1], 1);
     if (lane == 0) vm_prev = NEG_INF, vi_prev = NEG_INF; /* the left warp's values arrive with the rendezvous */
-    load_emis_part<Q, 0, 3, ROW>(rs.em, emis_lane, code);
+    load_emis_part<Q, 0, 3, ROW, 128, emis256(TW, Q)>(rs.em, emis_lane, code);
 
     /* D chain inside the warp (nothing from the warp to the left yet), first carry round straight-line */
     float d[Q];
@@ -379,7 +379,7 @@ k_score_mw(const float *__restrict__ emis, const float *__restrict__ trans, cons
             const float *b = trans + pm.trans_off + 8 * (32 * Q * TW); /* [3][TW] after the eight parameter arrays */
             cb.S = __ldg(b + lane), cb.md0 = __ldg(b + TW + lane), cb.dd0 = __ldg(b + 2 * TW + lane);
         }
-        const float *emis_lane = emis + pm.emis_off + gw * 256 + lane * 4;
+        const float *emis_lane = emis + pm.emis_off + gw * 256 + lane * emis_lane_stride(TW, Q);
         const SeqMeta sm = seqs[s];
         const RowRec *recs = rows + (size_t)pm.null_id * total_recs + sm.rec_off;
         const uint16_t *wc = wcodes + sm.rec_off;
@@ -409,7 +409,7 @@ k_score_mw(const float *__restrict__ emis, const float *__restrict__ trans, cons
         {
             uint32_t code[5];
             codes_of(__ldg(wc + 1), code);
-            load_emis<Q, ROW>(rs.em, emis_lane, code);
+            load_emis<Q, ROW, 128, emis256(TW, Q)>(rs.em, emis_lane, code);
         }
         load_row_insert(recs + 1, rs.eI);
         if (gw == 0 && lane < 3) load_row_special(recs + 1, rs.eN);

@@ -215,7 +215,7 @@ __device__ __forceinline__ void run_rows(float (&tm)[5][Q], float (&ti)[5][Q], f
     {
         uint32_t code[5];
         codes_of(__ldg(wc + j0 + 1), code);
-        load_emis<Q, S::MP, S::LN * 4>(rs.em, emis_lane, code);
+        load_emis<Q, S::MP, S::LN * 4, emis256(TW, Q)>(rs.em, emis_lane, code);
     }
     load_row_insert(recs + j0 + 1, rs.eI);
     if (me.xs >= 0 && me.xs < 3) load_row_special(recs + j0 + 1, rs.eN);
@@ -360,7 +360,7 @@ __device__ __forceinline__ void walk_segment(Walker &w, uint32_t j0, uint32_t M,
     auto rowv = [&](int idx, uint32_t row) -> float { return __ldcg(rowrec + (size_t)(row - j0 + 4u) * S::RR + idx); };
     auto emis_m = [&](uint32_t n, uint32_t code) -> float {
         const uint32_t t = n / Q, sub = n % Q, wp = t / S::LN, ln = t % S::LN;
-        return __ldg(emis + (size_t)code * S::MP + wp * (S::LN * S::QP) + (sub >> 2) * (S::LN * 4) + ln * 4 + (sub & 3));
+        return __ldg(emis + (size_t)code * S::MP + wp * (S::LN * S::QP) + emis_pos(ln, sub, S::LN, TW, Q));
     };
 
     auto stored = [&](uint32_t n) -> bool { return band.has((int)(n / Q)); };
@@ -466,8 +466,7 @@ __device__ __forceinline__ void walk_segment(Walker &w, uint32_t j0, uint32_t M,
             if (!valid) pa = rowrec;
             const uint32_t t_ = src / Q, sub = src % Q, wp = t_ / S::LN, ln = t_ % S::LN;
             const uint32_t lc = l ? l : 1u;
-            const float *pe_m = emis + (size_t)code_of_len(win, lc) * S::MP + wp * (S::LN * S::QP) + (sub >> 2) * (S::LN * 4) +
-                                ln * 4 + (sub & 3);
+            const float *pe_m = emis + (size_t)code_of_len(win, lc) * S::MP + wp * (S::LN * S::QP) + emis_pos(ln, sub, S::LN, TW, Q);
             const float *pe_r = (kind == WK_I ? rec->eI : rec->eN) + (lc - 1u);
             const bool emits = valid && l != 0 && kind != WK_D;
             const float *pe = kind == WK_M ? pe_m : pe_r;
@@ -626,7 +625,7 @@ __global__ void __launch_bounds__(Shape<TW, Q>::BLOCK, Shape<TW, Q>::MINB) k_tra
             cb.S = __ldg(b + me.lane), cb.md0 = __ldg(b + S::NW + me.lane), cb.dd0 = __ldg(b + 2 * S::NW + me.lane);
         }
         const float *emis_prof = a.emis + pm.emis_off;
-        const float *emis_lane = emis_prof + me.gw * (S::LN * S::QP) + me.lane * 4;
+        const float *emis_lane = emis_prof + me.gw * (S::LN * S::QP) + me.lane * emis_lane_stride(TW, Q);
         const RowRec *recs = a.rows + (size_t)pm.null_id * a.total_recs + sm.rec_off;
         const uint16_t *wc = a.wcodes + sm.rec_off;
         const float *spv = a.spec + (size_t)tj.seq * 16;
