@@ -95,13 +95,13 @@ __global__ void k_null(const SeqMeta *__restrict__ seqs, uint32_t nseq, uint32_t
 }
 
 /*
- * Match emission tables, host layout [node][code] -> device layout [code][warp][half][lane][4]
+ * Match emission tables, host layout [node][code] -> device layout [code][warp][half][lane][4] or [code][warp][lane][8]
  * (node k-1 = warp * 32 Q + lane * Q + sub sits in half sub/4, float sub%4 of its lane; pads are -inf).
  */
 __global__ void k_layout(const float *__restrict__ raw, float *__restrict__ out, uint32_t M, uint32_t Q, uint32_t QP,
                          uint32_t W, uint32_t LN, bool whole)
 {
-    /* LN lanes per pair (32, or 16 for the half-warp classes): a line is [warp][half][LN lanes][4] */
+    /* LN lanes per pair (32, or 16 for the half-warp classes): a line is [warp][half][LN lanes][4] (or, `whole`, [warp][LN lanes][8]) */
     const uint32_t ROW = LN * QP * W;
     const size_t x = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (x >= (size_t)kTab * ROW) return;
@@ -360,7 +360,7 @@ enum rc db_commit(dcpgpu_db *db)
                        nprof * sizeof(ProfMeta);
 
     /* Upload the tables as the host holds them ([node][code], contiguous) through two pinned buffers and let
-     * k_layout transpose them into the kernels' [code][warp][half][lane][4] layout on the device. */
+     * k_layout transpose them into the layout the profile's kernel class reads (dcp_kernels.cuh: emis256) on the device. */
     const size_t raw_max = (size_t)max_M * kTab;
     CommitStage stg;
     for (int b = 0; b < 2; ++b)
