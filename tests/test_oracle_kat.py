@@ -197,6 +197,21 @@ def test_state_graph_dp_matches_oracle_beyond_two_nodes(o64, M, L):
             assert rc == 0 and np.isfinite(want)
             assert abs(al - want) <= 1e-9 * abs(want), (M, L, entry, multi, compat, al, want)
             assert sum(l for _, l in path) == L
+            # the oracle's path, rescored edge by edge in the graph, attains that optimum: its traceback is a best path
+            pos, tot, prev = 0, 0.0, None
+            for st, ln in path:
+                name = o64.state_name(st)
+                if prev is not None:
+                    t = dict(edges[prev]).get(name)
+                    assert t is not None, (prev, name)
+                    tot += t
+                assert (ln > 0) == (name in table), (name, ln)
+                if ln:
+                    tot += float(table[name][codes[(pos, ln)]])
+                    pos += ln
+                prev = name
+            assert path[0][0] == orc.ST_S and prev == "T" and pos == L
+            assert abs(tot - want) <= 1e-9 * abs(want), (tot, want)
 
 
 def test_long_sequence_runs(o32):
