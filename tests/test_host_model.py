@@ -261,3 +261,61 @@ def test_dcp_database_round_trip(pkg, tmp_path):
     assert e.value.rc == pkg.RC_EPARSE and "magic" in str(e.value)
     with pytest.raises(pkg.DcpError):
         pkg.write_dcp(str(tmp_path / "x.dcp"), [pkg.ProteinProfile.sample(1, 2, pkg.protein_cfg(2, 0.02))], cfg)
+
+
+def test_dcp_reader_is_memory_safe_on_corrupt_files(pkg, tmp_path):
+    """protein_db_reader_* (src/db/protein_reader.c's role) on ~1600 truncated and corrupted databases -- structure bytes
+    overwritten, lengths blown up to 2^32 - 1, container types swapped -- under AddressSanitizer and UBSan: every file
+    ends in a return code, none in a memory error."""
+    import os
+    import random
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csrc = os.path.join(root, "deciphon-old_b200", "csrc")
+    exe = str(tmp_path / "fuzz")
+    build = subprocess.run(["gcc", "-std=c11", "-g", "-O1", "-fsanitize=address,undefined", "-fno-omit-frame-pointer",
+                            "-I", os.path.join(root, "include"), "-I", csrc, os.path.join(root, "tests", "dcp_reader_fuzz.c")] +
+                           [os.path.join(csrc, f) for f in ("dcp_db.c", "dcp_model.c", "dcp_error.c", "dcp_shape.c")] +
+                           ["-lm", "-o", exe], capture_output=True, text=True)
+    if build.returncode != 0:
+        pytest.skip("sanitizers not available: " + build.stderr[-200:])
+    cfg = pkg.protein_cfg(pkg.ENTRY_DIST_OCCUPANCY, 0.01)
+    good = str(tmp_path / "db.dcp")
+    pkg.write_dcp(good, [pkg.ProteinProfile.sample(1, 2, cfg, "seed1"), pkg.ProteinProfile.sample(3, 40, cfg, "PF00003.1")], cfg)
+    raw = open(good, "rb").read()
+    rng = random.Random(11)
+    files = []
+
+    def put(b):
+        path = str(tmp_path / ("f%04d" % len(files)))
+        open(path, "wb").write(bytes(b))
+        files.append(path)
+
+    for c in sorted(set([0, 1, 2, 7, 8, 9, 20, 39, 40, 41, 64, 100, 200, 300, 400, 1000, len(raw) - 1] +
+                        [rng.randrange(len(raw)) for _ in range(100)])):
+        put(raw[:c])
+    structure = [i for i in range(len(raw) - 6) if raw[i] in (0x82, 0x88, 0x90, 0x93, 0xa3, 0xa4, 0xa5, 0xa6, 0xa7, 0xa8, 0xa9,
+                                                               0xaa, 0xab, 0xac, 0xdc, 0xdd, 0xca, 0xcd, 0xce, 0xc4, 0xc5, 0xc6,
+                                                               0xd9, 0xda, 0xdb)]
+    for k in range(1500):
+        b = bytearray(raw)
+        pos = rng.randrange(min(len(raw), 400)) if k % 2 else rng.choice(structure)
+        if k % 4 == 0:
+            b[pos] = rng.randrange(256)
+        elif k % 4 == 1:
+            b[pos:pos + 4] = bytes(rng.randrange(256) for _ in range(4))
+        elif k % 4 == 2:
+            b[pos] = rng.choice([0xdd, 0xdc, 0xdb, 0xc6, 0xdf, 0xde, 0xcf, 0xce])
+        else:
+            b[pos + 1:pos + 5] = b"\xff\xff\xff\xff"
+        put(b)
+    put(raw)
+    out = subprocess.run([exe] + files, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "AddressSanitizer" not in out.stderr and "runtime error" not in out.stderr, out.stderr[-2000:]
+    assert out.stdout.startswith("files %d " % len(files))
+    nerr = int(out.stdout.split()[3])
+    assert 100 < nerr < len(files)  # every truncation and most structure damage is refused; the intact file is read
