@@ -319,3 +319,84 @@ def test_dcp_reader_is_memory_safe_on_corrupt_files(pkg, tmp_path):
     assert out.stdout.startswith("files %d " % len(files))
     nerr = int(out.stdout.split()[3])
     assert 100 < nerr < len(files)  # every truncation and most structure damage is refused; the intact file is read
+
+
+def test_h3reader_is_memory_safe_on_corrupt_files(pkg, tmp_path):
+    """protein_h3reader_* (src/model/protein_h3reader.c + hmmer-reader's role) on ~1350 damaged HMMER3 ASCII files --
+    truncations, bytes and tokens replaced ("*", "nan", 300-character tokens), lines dropped, duplicated and padded, LENG
+    out of range or disagreeing with the body -- under AddressSanitizer and UBSan: a return code every time."""
+    import os
+    import random
+    import shutil
+    import subprocess
+    from common import plan7_profile_inputs, write_hmm
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csrc = os.path.join(root, "deciphon-old_b200", "csrc")
+    exe = str(tmp_path / "h3fuzz")
+    build = subprocess.run(["gcc", "-std=c11", "-g", "-O1", "-fsanitize=address,undefined", "-fno-omit-frame-pointer",
+                            "-I", os.path.join(root, "include"), "-I", csrc, os.path.join(root, "tests", "h3reader_fuzz.c")] +
+                           [os.path.join(csrc, f) for f in ("dcp_h3reader.c", "dcp_model.c", "dcp_error.c", "dcp_shape.c")] +
+                           ["-lm", "-o", exe], capture_output=True, text=True)
+    if build.returncode != 0:
+        pytest.skip("sanitizers not available: " + build.stderr[-200:])
+    nrng = np.random.default_rng(3)
+    models = []
+    for i, M in enumerate((5, 30)):
+        _, ma, tr = plan7_profile_inputs(nrng, M)
+        models.append(("fam%d" % i, "PF1%04d.1" % i, ma, tr))
+    good = str(tmp_path / "good.hmm")
+    write_hmm(good, models)
+    raw = open(good, "rb").read()
+    r = random.Random(5)
+    files = []
+
+    def put(b):
+        path = str(tmp_path / ("h%04d" % len(files)))
+        open(path, "wb").write(bytes(b))
+        files.append(path)
+
+    for c in sorted(set([0, 1, 5, 17, 40, 100] + [r.randrange(len(raw)) for _ in range(150)])):
+        put(raw[:c])
+    lines = raw.split(b"\n")
+    for k in range(1200):
+        mode = k % 6
+        if mode == 0:
+            b = bytearray(raw)
+            b[r.randrange(len(raw))] = r.randrange(256)
+            put(b)
+        elif mode == 1:
+            b = bytearray(raw)
+            pos = r.randrange(len(raw))
+            b[pos:pos + 8] = bytes(r.choice(b" \t\n*-.0123456789eE+x") for _ in range(8))
+            put(b)
+        elif mode == 2:
+            ls = list(lines)
+            del ls[r.randrange(len(ls))]
+            put(b"\n".join(ls))
+        elif mode == 3:
+            ls = list(lines)
+            ls.insert(r.randrange(len(ls)), ls[r.randrange(len(ls))])
+            put(b"\n".join(ls))
+        elif mode == 4:
+            ls = list(lines)
+            i = r.randrange(len(ls))
+            toks = ls[i].split()
+            if toks:
+                toks[r.randrange(len(toks))] = r.choice([b"*", b"nan", b"inf", b"-1e999", b"99999999999999999999", b"", b"x" * 300])
+                ls[i] = b" ".join(toks)
+            put(b"\n".join(ls))
+        else:
+            ls = list(lines)
+            i = r.randrange(len(ls))
+            ls[i] = ls[i] + b" 1.0" * r.randrange(1, 40)
+            put(b"\n".join(ls))
+    for leng in (b"4097", b"0", b"-5", b"29", b"31"):
+        put(raw.replace(b"LENG  30", b"LENG  " + leng))
+    put(raw)
+    out = subprocess.run([exe] + files, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "AddressSanitizer" not in out.stderr and "runtime error" not in out.stderr, out.stderr[-2000:]
+    words = out.stdout.split()
+    assert int(words[1]) == len(files) and 100 < int(words[3]) < len(files) and int(words[5]) >= 2
