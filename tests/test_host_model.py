@@ -400,3 +400,28 @@ def test_h3reader_is_memory_safe_on_corrupt_files(pkg, tmp_path):
     assert "AddressSanitizer" not in out.stderr and "runtime error" not in out.stderr, out.stderr[-2000:]
     words = out.stdout.split()
     assert int(words[1]) == len(files) and 100 < int(words[3]) < len(files) and int(words[5]) >= 2
+
+
+def test_model_layer_under_sanitizers(tmp_path):
+    """protein_model_* / protein_profile_* (src/model/protein_model.c, protein_profile.c) compiled with
+    AddressSanitizer, LeakSanitizer and UBSan: sampled profiles of 2..70 nodes under both entry distributions, specials
+    for lengths 1..10^5, decode of every fragment length in N / J / C / M / I states, a model full of zero probabilities
+    (no NaN in the tables), and the error paths (setup range, add before setup, one node or transition too many,
+    fragment or node out of range) -- tests/model_sanitize.c returns the number of the first check that fails."""
+    import os
+    import shutil
+    import subprocess
+    if not shutil.which("gcc"):
+        pytest.skip("no gcc")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csrc = os.path.join(root, "deciphon-old_b200", "csrc")
+    exe = str(tmp_path / "model_san")
+    build = subprocess.run(["gcc", "-std=c11", "-g", "-O1", "-fsanitize=address,undefined", "-fno-omit-frame-pointer",
+                            "-I", os.path.join(root, "include"), "-I", csrc, os.path.join(root, "tests", "model_sanitize.c")] +
+                           [os.path.join(csrc, f) for f in ("dcp_model.c", "dcp_error.c", "dcp_shape.c")] + ["-lm", "-o", exe],
+                           capture_output=True, text=True)
+    if build.returncode != 0:
+        pytest.skip("sanitizers not available: " + build.stderr[-200:])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stderr[-2000:])
+    assert out.stdout.startswith("ok ") and "runtime error" not in out.stderr and "Sanitizer" not in out.stderr
